@@ -1,0 +1,242 @@
+/*
+ * ofa_sr_b200.h — C ABI of the B200 (sm_100a) elastic-MBConv super-resolution hot path.
+ *
+ * This is the drop-in boundary.  The reference has no FFI: its "operator API" is a
+ * set of Python nn.Modules that call ATen.  Each entry point below therefore cites the reference
+ * call site (path:line under the reference tree) whose arithmetic it replaces; the Python host
+ * package `ofa_b200` binds them with ctypes (INTEGRATION.md shows the stub a maintainer of the
+ * reference would add).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless a name says host;
+ *   - activations are addressed through explicit element strides (sn, sc, sh, sw), so NCHW,
+ *     NHWC (torch channels_last) and channel-sliced views all work without copies; the tensor-core
+ *     paths additionally require NHWC-dense bf16 and say so;
+ *   - dtype codes: OFA_F32 = 0, OFA_BF16 = 1 (accumulation is always fp32);
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant, and
+ *     keeps no global mutable state besides a per-thread error string / launch counter and a
+ *     per-device cache of device attributes (nn.DataParallel calls in from one thread per GPU);
+ *   - return value: 0 = OFA_OK, otherwise an OFA_ERR_* code; ofa_last_error() gives the text.
+ *     The Python layer turns non-zero into RuntimeError (the reference's error style is Python
+ *     assert / ValueError: ofa/utils.py:217-218,306).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point returns OFA_ERR_CUDA.
+ */
+#ifndef OFA_SR_B200_H_
+#define OFA_SR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OFA_OK 0
+#define OFA_ERR_ARG 1
+#define OFA_ERR_CUDA 2
+#define OFA_ERR_UNSUPPORTED 3
+
+#define OFA_F32 0
+#define OFA_BF16 1
+
+/* activation codes (ofa/utils.py:242-314 build_activation) */
+#define OFA_ACT_NONE 0
+#define OFA_ACT_RELU6 1
+#define OFA_ACT_HSWISH 2
+#define OFA_ACT_RELU 3
+
+/* store modes of a ConvLayer's third op (ofa/layers.py:94-98 + ofa/utils.py:259-260,383-410) */
+#define OFA_STORE_PLAIN 0
+#define OFA_STORE_PIXELSHUFFLE2 1   /* out[n, c, 2h+i, 2w+j] = conv[n, 4c+2i+j, h, w] */
+#define OFA_STORE_PIXELUNSHUFFLE2 2 /* out[n, 4c+2y+x, h, w] = conv[n, c, 2h+y, 2w+x] */
+
+/* implementation selectors (testing / profiling); 0 picks the fastest valid one */
+#define OFA_IMPL_AUTO 0
+#define OFA_IMPL_SIMT 1 /* CUDA-core kernels: any layout, fp32 or bf16 I/O                      */
+#define OFA_IMPL_FAST 2 /* TMA halo tiles (depthwise) / tcgen05+TMEM implicit GEMM (dense conv)  */
+
+/* A 4-D activation view: element (n, c, h, w) lives at ptr + n*sn + c*sc + h*sh + w*sw (elements). */
+typedef struct OfaTensor4 {
+  void* ptr;
+  int32_t dtype; /* OFA_F32 | OFA_BF16 */
+  int32_t n, c, h, w;
+  int64_t sn, sc, sh, sw;
+} OfaTensor4;
+
+/* Per-output-channel affine + activation + residual applied by every forward kernel's epilogue.
+ * Inference BN folding (dynamic_op.py:148-167 with bn.training == False; layers.py:46-50) is done
+ * inside the kernel: scale = gamma * rsqrt(var + eps), shift = beta - mean * scale, all read from
+ * the FULL supernet-width arrays (the active slice is always the prefix [:C], dynamic_op.py:163-165).
+ * Any of gamma/beta/mean/var may be NULL (treated as 1/0/0/1 and eps ignored when var is NULL). */
+typedef struct OfaEpilogue {
+  const float* gamma;
+  const float* beta;
+  const float* mean;
+  const float* var;
+  float eps;
+  int32_t act;               /* OFA_ACT_* */
+  const OfaTensor4* residual; /* optional tensor added AFTER affine+act (proxyless_nets.py:50
+                                 residual, ofa_mbs4.py:159 long skip); indexed like the output y */
+} OfaEpilogue;
+
+/* ---------------------------------------------------------------------------------------------
+ * Library / device
+ * ------------------------------------------------------------------------------------------- */
+int ofa_version(void);
+const char* ofa_last_error(void);
+/* host query; fills SM count and compute capability of the current device */
+int ofa_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
+/* number of kernels this library has launched on this thread since the last reset (bench.py's
+ * gpu_launches counter) */
+int64_t ofa_launch_count(void);
+void ofa_launch_count_reset(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * (a1) DynamicSeparableConv2d.get_active_filter — dynamic_op.py:46-71
+ *   w7   [Cmax, kmax*kmax] fp32 (the nn.Conv2d depthwise weight [Cmax,1,kmax,kmax], contiguous)
+ *   m75  [25,25] / m53 [9,9] fp32 or NULL; transform_on mirrors KERNEL_TRANSFORM_MODE is not None
+ *   out  [C, ks*ks] fp32, contiguous
+ * ------------------------------------------------------------------------------------------- */
+int ofa_dw_active_filter(const float* w7, int32_t kmax, const float* m75, const float* m53,
+                         int32_t transform_on, int32_t ks, int32_t C, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (a2 [+a5 eval, +a6]) DynamicSeparableConv2d.forward — dynamic_op.py:73-84
+ *   depthwise ks x ks, stride 1, dilation 1, pad ks/2, groups = C, filter derived on the fly from
+ *   (w7, m75, m53) exactly as (a1).  x and y have C channels, same N/H/W.  epi may be NULL.
+ *   OFA_IMPL_FAST requires NHWC-dense bf16 x and y and C % 64 == 0.
+ * ------------------------------------------------------------------------------------------- */
+int ofa_dw_fwd(const OfaTensor4* x, const OfaTensor4* y, const float* w7, int32_t kmax,
+               const float* m75, const float* m53, int32_t transform_on, int32_t ks,
+               const OfaEpilogue* epi, int32_t impl, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (a3, a4) DynamicPointConv2d.forward — dynamic_op.py:104-112  (1x1, channel-sliced weight)
+ * (a9..a11) ConvLayer = conv k x k -> BN -> {none | PixelShuffle(2) | PixelUnshuffle(2)}
+ *            — layers.py:94-98,120-151; utils.py:259-260,383-410
+ *   w      fp32 weight addressed as w[o*w_so + i*w_si + ky*w_sh + kx*w_sw]: pass the FULL supernet
+ *          parameter with its strides and the active Cin/Cout — the slice W[:Cout,:Cin] is never copied
+ *   w_bf16 optional packed copy [ks*ks][cout_pad][cin_pad] bf16 made by ofa_pack_weight_bf16
+ *          (required by OFA_IMPL_FAST; a derived cache owned by the caller)
+ *   y      describes the tensor actually written: for PIXELSHUFFLE2 it has c = Cout/4, h = 2H, w = 2W;
+ *          for PIXELUNSHUFFLE2 c = 4*Cout, h = H/2, w = W/2.  epi.residual is indexed like y.
+ *          The per-channel affine of epi is indexed by the CONV output channel (BN sits before the
+ *          shuffle in the reference, layers.py:94-98).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct OfaConvArgs {
+  OfaTensor4 x;
+  OfaTensor4 y;
+  const float* w;
+  int64_t w_so, w_si, w_sh, w_sw;
+  const void* w_bf16;
+  int32_t cin_pad, cout_pad; /* padded dims of w_bf16 */
+  int32_t cin, cout, ks;
+  int32_t flip;  /* 1: use w[.., ks-1-ky, ks-1-kx] (the data-gradient correlation) */
+  int32_t store; /* OFA_STORE_* */
+  OfaEpilogue epi;
+} OfaConvArgs;
+
+int ofa_conv_fwd(const OfaConvArgs* a, int32_t impl, void* stream);
+/* named aliases of the same entry point, kept for the reference-facing vocabulary */
+int ofa_pw_fwd(const OfaConvArgs* a, int32_t impl, void* stream);       /* requires ks == 1 */
+int ofa_conv_kxk_fwd(const OfaConvArgs* a, int32_t impl, void* stream); /* any odd ks        */
+
+/* fp32 strided weight (as above) -> bf16 [ks*ks][cout_pad][cin_pad], zero padded.  `store` is the
+ * store mode of the layer the pack is for: PixelShuffle layers are packed sub-pixel major (row
+ * s*(cout/4) + c holds conv output channel 4c + s) so one sub-pixel's channels are contiguous. */
+int ofa_pack_weight_bf16(const float* w, int64_t w_so, int64_t w_si, int64_t w_sh, int64_t w_sw,
+                         int32_t cin, int32_t cout, int32_t ks, int32_t cin_pad, int32_t cout_pad,
+                         int32_t store, void* out_bf16, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (a5) DynamicBatchNorm2d.bn_forward in TRAINING mode — dynamic_op.py:148-167
+ *   stats : per-channel batch mean and BIASED variance over N*H*W (what F.batch_norm normalises with)
+ *   update: running = (1-momentum)*running + momentum*{mean, var * P/(P-1)} on the slice [:C]
+ *   apply : y = act(gamma*(x-mean)*rsqrt(var+eps)+beta) is ofa_affine_act with mean/var = batch stats
+ * ------------------------------------------------------------------------------------------- */
+int ofa_bn_stats(const OfaTensor4* x, float* mean, float* var_biased, void* stream);
+int ofa_bn_update_running(const float* mean, const float* var_biased, int64_t count,
+                          float* running_mean, float* running_var, float momentum, int32_t C,
+                          void* stream);
+/* (a5 eval, a6, a8, a10, a11) stand-alone per-channel affine + activation (+ residual) with an
+ * optional PixelShuffle / PixelUnshuffle store:  y = store(act(affine(x))) + res */
+int ofa_affine_act(const OfaTensor4* x, const OfaTensor4* y, const OfaEpilogue* epi, int32_t store,
+                   void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (a7 + a8) DynamicMBConvLayer.forward + MobileInvertedResidualBlock — dynamic_layers.py:70-84,
+ * proxyless_nets.py:44-51, inference mode (BN folded): expand 1x1 -> BN -> ReLU6 -> elastic
+ * depthwise -> BN -> ReLU6 -> project 1x1 -> BN (+ x).  NHWC-dense bf16 x / y with `cin` channels.
+ *   w_exp  [Mmax, cin_max] fp32 (full), w_proj [cout_max, Mmax] fp32 (full); `mid` active channels
+ *   bn_*   the three BatchNorm parameter sets (full width; prefixes are used)
+ *   ws     caller-owned scratch of ofa_mbconv_workspace_bytes(...) bytes
+ * ------------------------------------------------------------------------------------------- */
+typedef struct OfaBn {
+  const float* gamma;
+  const float* beta;
+  const float* mean;
+  const float* var;
+  float eps;
+} OfaBn;
+
+typedef struct OfaMBConvArgs {
+  OfaTensor4 x;
+  OfaTensor4 y;
+  const float* w_exp;
+  int64_t w_exp_so, w_exp_si;
+  const float* w_dw; /* [Mmax, kmax*kmax] */
+  int32_t kmax;
+  const float* m75;
+  const float* m53;
+  int32_t transform_on;
+  const float* w_proj;
+  int64_t w_proj_so, w_proj_si;
+  int32_t cin, mid, cout, ks;
+  int32_t act; /* activation after expand and depthwise (OFA_ACT_*) */
+  OfaBn bn_exp, bn_dw, bn_proj;
+  int32_t add_residual; /* 1: y = block(x) + x */
+  void* ws;
+  int64_t ws_bytes;
+} OfaMBConvArgs;
+
+int64_t ofa_mbconv_workspace_bytes(int32_t n, int32_t h, int32_t w, int32_t cin, int32_t mid,
+                                   int32_t cout);
+int ofa_mbconv_fwd(const OfaMBConvArgs* a, int32_t impl, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (a14) backward of the path — autograd of dynamic_op.py:73-84,104-112,148-167
+ * ------------------------------------------------------------------------------------------- */
+/* dX of the depthwise conv = correlation of dY with the 180-degree rotated active filter */
+int ofa_dw_bwd_data(const OfaTensor4* dy, const OfaTensor4* dx, const float* w7, int32_t kmax,
+                    const float* m75, const float* m53, int32_t transform_on, int32_t ks,
+                    void* stream);
+/* dW_active [C, ks*ks] fp32 (overwritten) */
+int ofa_dw_bwd_filter(const OfaTensor4* x, const OfaTensor4* dy, int32_t ks, float* dw_active,
+                      void* stream);
+/* chain rule through (a1): dW_active -> accumulates (+=) into dw7 [Cmax,kmax*kmax], dm75, dm53 */
+int ofa_dw_active_filter_bwd(const float* w7, int32_t kmax, const float* m75, const float* m53,
+                             int32_t transform_on, int32_t ks, int32_t C, const float* dw_active,
+                             float* dw7, float* dm75, float* dm53, void* stream);
+/* dense conv backward: dX (full correlation with W) and dW (accumulated += into the strided slice) */
+int ofa_conv_bwd_data(const OfaTensor4* dy, const OfaTensor4* dx, const float* w, int64_t w_so,
+                      int64_t w_si, int64_t w_sh, int64_t w_sw, int32_t cin, int32_t cout,
+                      int32_t ks, void* stream);
+int ofa_conv_bwd_weight(const OfaTensor4* x, const OfaTensor4* dy, float* dw, int64_t w_so,
+                        int64_t w_si, int64_t w_sh, int64_t w_sw, int32_t cin, int32_t cout,
+                        int32_t ks, void* stream);
+/* BN (+ activation) backward, x = the BN input, dy = gradient of act(BN(x)).
+ *   reduce: dz = dy * act'(z), z recomputed from x; sum_dz[c], sum_dz_xhat[c] (overwritten)
+ *           (dgamma = sum_dz_xhat, dbeta = sum_dz)
+ *   apply : training: dx = gamma*rstd*(dz - sum_dz/P - xhat*sum_dz_xhat/P)
+ *           eval    : dx = gamma*rstd*dz   (sum pointers may be NULL)                            */
+int ofa_bn_bwd_reduce(const OfaTensor4* x, const OfaTensor4* dy, const float* gamma,
+                      const float* beta, const float* mean, const float* var, float eps,
+                      int32_t act, float* sum_dz, float* sum_dz_xhat, void* stream);
+int ofa_bn_bwd_apply(const OfaTensor4* x, const OfaTensor4* dy, const OfaTensor4* dx,
+                     const float* gamma, const float* beta, const float* mean, const float* var,
+                     float eps, int32_t act, int32_t training, const float* sum_dz,
+                     const float* sum_dz_xhat, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OFA_SR_B200_H_ */

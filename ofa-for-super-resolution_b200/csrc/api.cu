@@ -1,0 +1,389 @@
+// C ABI of libofa_sr_b200: argument checking and dispatch.  See include/ofa_sr_b200.h.
+#include "ofa_common.cuh"
+#include "kernels.h"
+
+#include <string.h>
+
+namespace ofa {
+
+char* err_buf() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+int64_t& launch_counter() {
+  static thread_local int64_t n = 0;
+  return n;
+}
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(err_buf(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(OFA_ERR_CUDA, "%s launch failed: %s", what, cudaGetErrorString(e));
+  launch_counter()++;
+  return OFA_OK;
+}
+int sm_count() {
+  static int cache[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cache[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[dev] = n;
+  }
+  return cache[dev];
+}
+
+static int require_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(OFA_ERR_CUDA, "no CUDA device: libofa_sr_b200 has no CPU fallback");
+  }
+  return OFA_OK;
+}
+
+static int check_transform_args(int kmax, const float* m75, const float* m53, int transform_on, int ks) {
+  OFA_REQUIRE(kmax == 3 || kmax == 5 || kmax == 7, "kmax must be 3, 5 or 7 (got %d)", kmax);
+  OFA_REQUIRE(ks == 3 || ks == 5 || ks == 7, "kernel size must be 3, 5 or 7 (got %d)", ks);
+  OFA_REQUIRE(ks <= kmax, "active kernel size %d exceeds the stored %d", ks, kmax);
+  if (transform_on && ks < kmax) {
+    if (ks == 5) OFA_REQUIRE(m75 != nullptr, "7to5 matrix required for ks=5");
+    if (ks == 3) OFA_REQUIRE(m53 != nullptr, "a ->3 transform matrix is required for ks=3");
+  }
+  return OFA_OK;
+}
+
+static int same_shape(const OfaTensor4* a, const OfaTensor4* b, const char* what) {
+  OFA_REQUIRE(a->n == b->n && a->c == b->c && a->h == b->h && a->w == b->w,
+              "%s: shape mismatch [%d,%d,%d,%d] vs [%d,%d,%d,%d]", what, a->n, a->c, a->h, a->w, b->n,
+              b->c, b->h, b->w);
+  return OFA_OK;
+}
+
+static int check_epi(const OfaEpilogue* e, const OfaTensor4* y) {
+  if (!e) return OFA_OK;
+  OFA_REQUIRE(e->act >= OFA_ACT_NONE && e->act <= OFA_ACT_RELU, "bad activation code %d", e->act);
+  if (e->residual) {
+    int rc = check_tensor(e->residual, "residual");
+    if (rc) return rc;
+    rc = same_shape(e->residual, y, "residual vs output");
+    if (rc) return rc;
+  }
+  return OFA_OK;
+}
+
+static int store_shape_ok(const OfaConvArgs* a) {
+  const OfaTensor4 &x = a->x, &y = a->y;
+  if (a->store == OFA_STORE_PLAIN) {
+    OFA_REQUIRE(y.n == x.n && y.c == a->cout && y.h == x.h && y.w == x.w, "conv: output shape mismatch");
+  } else if (a->store == OFA_STORE_PIXELSHUFFLE2) {
+    OFA_REQUIRE(a->cout % 4 == 0, "pixelshuffle needs cout %% 4 == 0");
+    OFA_REQUIRE(y.n == x.n && y.c == a->cout / 4 && y.h == 2 * x.h && y.w == 2 * x.w,
+                "conv+pixelshuffle: output shape mismatch");
+  } else if (a->store == OFA_STORE_PIXELUNSHUFFLE2) {
+    OFA_REQUIRE(x.h % 2 == 0 && x.w % 2 == 0, "pixelunshuffle needs even H and W");
+    OFA_REQUIRE(y.n == x.n && y.c == a->cout * 4 && y.h == x.h / 2 && y.w == x.w / 2,
+                "conv+pixelunshuffle: output shape mismatch");
+  } else {
+    return fail(OFA_ERR_ARG, "bad store mode %d", a->store);
+  }
+  return OFA_OK;
+}
+
+}  // namespace ofa
+
+using namespace ofa;
+
+extern "C" {
+
+int ofa_version(void) { return 100; }
+const char* ofa_last_error(void) { return err_buf(); }
+
+int ofa_device_info(int32_t* sm, int32_t* major, int32_t* minor) {
+  int rc = require_device();
+  if (rc) return rc;
+  int dev = 0;
+  OFA_CUDA(cudaGetDevice(&dev));
+  int a = 0, b = 0, c = 0;
+  OFA_CUDA(cudaDeviceGetAttribute(&a, cudaDevAttrMultiProcessorCount, dev));
+  OFA_CUDA(cudaDeviceGetAttribute(&b, cudaDevAttrComputeCapabilityMajor, dev));
+  OFA_CUDA(cudaDeviceGetAttribute(&c, cudaDevAttrComputeCapabilityMinor, dev));
+  if (sm) *sm = a;
+  if (major) *major = b;
+  if (minor) *minor = c;
+  return OFA_OK;
+}
+
+int64_t ofa_launch_count(void) { return launch_counter(); }
+void ofa_launch_count_reset(void) { launch_counter() = 0; }
+
+int ofa_dw_active_filter(const float* w7, int32_t kmax, const float* m75, const float* m53,
+                         int32_t transform_on, int32_t ks, int32_t C, float* out, void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  OFA_REQUIRE(w7 && out, "ofa_dw_active_filter: null pointer");
+  OFA_REQUIRE(C >= 0, "negative channel count");
+  rc = check_transform_args(kmax, m75, m53, transform_on, ks);
+  if (rc) return rc;
+  return launch_active_filter(w7, kmax, m75, m53, transform_on, ks, C, out, (cudaStream_t)stream);
+}
+
+static int dw_common(const OfaTensor4* x, const OfaTensor4* y, const float* w7, int32_t kmax,
+                     const float* m75, const float* m53, int32_t transform_on, int32_t ks, int flip,
+                     const OfaEpilogue* epi, int32_t impl, void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  if ((rc = check_tensor(x, "x"))) return rc;
+  if ((rc = check_tensor(y, "y"))) return rc;
+  if ((rc = same_shape(x, y, "depthwise x vs y"))) return rc;
+  OFA_REQUIRE(w7 != nullptr, "depthwise: null weight");
+  if ((rc = check_transform_args(kmax, m75, m53, transform_on, ks))) return rc;
+  if ((rc = check_epi(epi, y))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  bool fast_ok = !flip && dw_fast_supported(x, y, ks, epi);
+  if (impl == OFA_IMPL_FAST && !fast_ok)
+    return fail(OFA_ERR_UNSUPPORTED, "depthwise FAST path needs NHWC-dense bf16 x/y with C %% 64 == 0");
+  if (fast_ok && impl != OFA_IMPL_SIMT)
+    return launch_dw_fast(x, y, w7, kmax, m75, m53, transform_on, ks, epi, st);
+  return launch_dw_simt(make_tv(x), make_tv(y), w7, kmax, m75, m53, transform_on, ks, flip, make_epi(epi), st);
+}
+
+int ofa_dw_fwd(const OfaTensor4* x, const OfaTensor4* y, const float* w7, int32_t kmax, const float* m75,
+               const float* m53, int32_t transform_on, int32_t ks, const OfaEpilogue* epi, int32_t impl,
+               void* stream) {
+  return dw_common(x, y, w7, kmax, m75, m53, transform_on, ks, 0, epi, impl, stream);
+}
+
+int ofa_dw_bwd_data(const OfaTensor4* dy, const OfaTensor4* dx, const float* w7, int32_t kmax,
+                    const float* m75, const float* m53, int32_t transform_on, int32_t ks, void* stream) {
+  return dw_common(dy, dx, w7, kmax, m75, m53, transform_on, ks, 1, nullptr, OFA_IMPL_SIMT, stream);
+}
+
+int ofa_conv_fwd(const OfaConvArgs* a, int32_t impl, void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  OFA_REQUIRE(a != nullptr, "ofa_conv_fwd: null args");
+  if ((rc = check_tensor(&a->x, "x"))) return rc;
+  if ((rc = check_tensor(&a->y, "y"))) return rc;
+  OFA_REQUIRE(a->ks >= 1 && (a->ks & 1), "conv kernel size must be odd (got %d)", a->ks);
+  OFA_REQUIRE(a->cin >= 1 && a->cout >= 1, "conv: cin/cout must be positive");
+  OFA_REQUIRE(a->x.c == a->cin, "conv: x has %d channels, cin = %d", a->x.c, a->cin);
+  if ((rc = store_shape_ok(a))) return rc;
+  if ((rc = check_epi(&a->epi, &a->y))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  bool tc_ok = conv_tc_supported(a);
+  if (impl == OFA_IMPL_FAST && !tc_ok)
+    return fail(OFA_ERR_UNSUPPORTED, "conv FAST path: needs NHWC-dense bf16 x, packed bf16 weights, cin %% 64 == 0, cout <= 256 (or a multiple of 128/192)");
+  if (tc_ok && impl != OFA_IMPL_SIMT) return launch_conv_tc(a, st);
+  OFA_REQUIRE(a->w != nullptr, "conv: null fp32 weight");
+  return launch_conv_simt(make_tv(&a->x), make_tv(&a->y), a->w, a->w_so, a->w_si, a->w_sh, a->w_sw, a->cin,
+                          a->cout, a->ks, a->flip, a->store, make_epi(&a->epi), st);
+}
+
+int ofa_pw_fwd(const OfaConvArgs* a, int32_t impl, void* stream) {
+  OFA_REQUIRE(a != nullptr && a->ks == 1, "ofa_pw_fwd requires ks == 1");
+  return ofa_conv_fwd(a, impl, stream);
+}
+int ofa_conv_kxk_fwd(const OfaConvArgs* a, int32_t impl, void* stream) { return ofa_conv_fwd(a, impl, stream); }
+
+int ofa_pack_weight_bf16(const float* w, int64_t w_so, int64_t w_si, int64_t w_sh, int64_t w_sw, int32_t cin,
+                         int32_t cout, int32_t ks, int32_t cin_pad, int32_t cout_pad, int32_t store, void* out,
+                         void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  OFA_REQUIRE(w && out, "ofa_pack_weight_bf16: null pointer");
+  OFA_REQUIRE(cin_pad >= cin && cout_pad >= cout && cin >= 0 && cout >= 0 && ks >= 1, "bad pack dims");
+  OFA_REQUIRE(store != OFA_STORE_PIXELSHUFFLE2 || cout % 4 == 0, "pixelshuffle pack needs cout %% 4 == 0");
+  return launch_pack_weight(w, w_so, w_si, w_sh, w_sw, cin, cout, ks, cin_pad, cout_pad, store, out,
+                            (cudaStream_t)stream);
+}
+
+int ofa_bn_stats(const OfaTensor4* x, float* mean, float* var, void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  if ((rc = check_tensor(x, "x"))) return rc;
+  OFA_REQUIRE(mean && var, "ofa_bn_stats: null output");
+  OFA_REQUIRE((long long)x->n * x->h * x->w > 0, "ofa_bn_stats: empty batch");
+  return launch_bn_stats(make_tv(x), mean, var, (cudaStream_t)stream);
+}
+
+int ofa_bn_update_running(const float* mean, const float* var, int64_t count, float* rm, float* rv,
+                          float momentum, int32_t C, void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  OFA_REQUIRE(mean && var && rm && rv, "ofa_bn_update_running: null pointer");
+  return launch_bn_update_running(mean, var, count, rm, rv, momentum, C, (cudaStream_t)stream);
+}
+
+int ofa_affine_act(const OfaTensor4* x, const OfaTensor4* y, const OfaEpilogue* epi, int32_t store, void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  if ((rc = check_tensor(x, "x"))) return rc;
+  if ((rc = check_tensor(y, "y"))) return rc;
+  OfaConvArgs tmp;
+  memset(&tmp, 0, sizeof(tmp));
+  tmp.x = *x; tmp.y = *y; tmp.cout = x->c; tmp.store = store;
+  if ((rc = store_shape_ok(&tmp))) return rc;
+  if ((rc = check_epi(epi, y))) return rc;
+  return launch_affine_act(make_tv(x), make_tv(y), make_epi(epi), store, (cudaStream_t)stream);
+}
+
+int64_t ofa_mbconv_workspace_bytes(int32_t n, int32_t h, int32_t w, int32_t cin, int32_t mid, int32_t cout) {
+  (void)cin; (void)cout;
+  int64_t P = (int64_t)n * h * w;
+  int64_t mid_pad = (mid + 63) / 64 * 64;
+  // two bf16 [P, mid] intermediates + three packed bf16 weights (<= 384*64 each, padded) + slack
+  return 2 * P * mid_pad * 2 + 2 * (int64_t)(384 + 64) * 384 * 2 + 4096;
+}
+
+int ofa_mbconv_fwd(const OfaMBConvArgs* a, int32_t impl, void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  OFA_REQUIRE(a != nullptr, "ofa_mbconv_fwd: null args");
+  if ((rc = check_tensor(&a->x, "x"))) return rc;
+  if ((rc = check_tensor(&a->y, "y"))) return rc;
+  OFA_REQUIRE(is_nhwc_dense(&a->x) && is_nhwc_dense(&a->y) && a->x.dtype == OFA_BF16 && a->y.dtype == OFA_BF16,
+              "ofa_mbconv_fwd: x and y must be NHWC-dense bf16");
+  OFA_REQUIRE(a->x.c == a->cin && a->y.c == a->cout, "ofa_mbconv_fwd: channel mismatch");
+  OFA_REQUIRE(a->cin % 64 == 0 && a->mid % 64 == 0 && a->cout % 64 == 0 && a->mid <= 384 && a->cin <= 384 && a->cout <= 256,
+              "ofa_mbconv_fwd: cin/mid/cout must be multiples of 64 (cin,mid <= 384, cout <= 256)");
+  OFA_REQUIRE(!a->add_residual || a->cin == a->cout, "ofa_mbconv_fwd: residual needs cin == cout");
+  OFA_REQUIRE(a->w_exp && a->w_dw && a->w_proj, "ofa_mbconv_fwd: null weight");
+  int64_t need = ofa_mbconv_workspace_bytes(a->x.n, a->x.h, a->x.w, a->cin, a->mid, a->cout);
+  OFA_REQUIRE(a->ws && a->ws_bytes >= need, "ofa_mbconv_fwd: workspace too small (%lld < %lld)",
+              (long long)a->ws_bytes, (long long)need);
+  if ((rc = check_transform_args(a->kmax, a->m75, a->m53, a->transform_on, a->ks))) return rc;
+  (void)impl;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t P = (int64_t)a->x.n * a->x.h * a->x.w;
+  char* ws = reinterpret_cast<char*>(a->ws);
+  void* t1 = ws;
+  void* t2 = ws + P * a->mid * 2;
+  void* wexp_p = ws + 2 * P * a->mid * 2;
+  void* wproj_p = reinterpret_cast<char*>(wexp_p) + (int64_t)384 * 384 * 2;
+  // pack the active weight slices (tiny) — the slice W[:mid,:cin] is read in place from the full parameter
+  if ((rc = launch_pack_weight(a->w_exp, a->w_exp_so, a->w_exp_si, 0, 0, a->cin, a->mid, 1, a->cin, a->mid, OFA_STORE_PLAIN, wexp_p, st))) return rc;
+  if ((rc = launch_pack_weight(a->w_proj, a->w_proj_so, a->w_proj_si, 0, 0, a->mid, a->cout, 1, a->mid, a->cout, OFA_STORE_PLAIN, wproj_p, st))) return rc;
+
+  OfaTensor4 mid1 = a->x, mid2 = a->x;
+  mid1.ptr = t1; mid2.ptr = t2;
+  mid1.c = mid2.c = a->mid;
+  mid1.sc = mid2.sc = 1;
+  mid1.sw = mid2.sw = a->mid;
+  mid1.sh = mid2.sh = (int64_t)a->x.w * a->mid;
+  mid1.sn = mid2.sn = (int64_t)a->x.h * a->x.w * a->mid;
+  mid1.dtype = mid2.dtype = OFA_BF16;
+
+  OfaConvArgs c1;
+  memset(&c1, 0, sizeof(c1));
+  c1.x = a->x; c1.y = mid1; c1.w = a->w_exp; c1.w_so = a->w_exp_so; c1.w_si = a->w_exp_si;
+  c1.w_bf16 = wexp_p; c1.cin_pad = a->cin; c1.cout_pad = a->mid; c1.cin = a->cin; c1.cout = a->mid; c1.ks = 1;
+  c1.epi.gamma = a->bn_exp.gamma; c1.epi.beta = a->bn_exp.beta; c1.epi.mean = a->bn_exp.mean;
+  c1.epi.var = a->bn_exp.var; c1.epi.eps = a->bn_exp.eps; c1.epi.act = a->act;
+  if ((rc = ofa_conv_fwd(&c1, impl, stream))) return rc;
+
+  OfaEpilogue e2;
+  memset(&e2, 0, sizeof(e2));
+  e2.gamma = a->bn_dw.gamma; e2.beta = a->bn_dw.beta; e2.mean = a->bn_dw.mean; e2.var = a->bn_dw.var;
+  e2.eps = a->bn_dw.eps; e2.act = a->act;
+  if ((rc = ofa_dw_fwd(&mid1, &mid2, a->w_dw, a->kmax, a->m75, a->m53, a->transform_on, a->ks, &e2, impl, stream))) return rc;
+
+  OfaConvArgs c3;
+  memset(&c3, 0, sizeof(c3));
+  c3.x = mid2; c3.y = a->y; c3.w = a->w_proj; c3.w_so = a->w_proj_so; c3.w_si = a->w_proj_si;
+  c3.w_bf16 = wproj_p; c3.cin_pad = a->mid; c3.cout_pad = a->cout; c3.cin = a->mid; c3.cout = a->cout; c3.ks = 1;
+  c3.epi.gamma = a->bn_proj.gamma; c3.epi.beta = a->bn_proj.beta; c3.epi.mean = a->bn_proj.mean;
+  c3.epi.var = a->bn_proj.var; c3.epi.eps = a->bn_proj.eps; c3.epi.act = OFA_ACT_NONE;
+  c3.epi.residual = a->add_residual ? &a->x : nullptr;
+  return ofa_conv_fwd(&c3, impl, stream);
+}
+
+int ofa_dw_bwd_filter(const OfaTensor4* x, const OfaTensor4* dy, int32_t ks, float* dw_active, void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  if ((rc = check_tensor(x, "x"))) return rc;
+  if ((rc = check_tensor(dy, "dy"))) return rc;
+  if ((rc = same_shape(x, dy, "dw_bwd_filter x vs dy"))) return rc;
+  OFA_REQUIRE(dw_active != nullptr, "null dw_active");
+  return launch_dw_bwd_filter(make_tv(x), make_tv(dy), ks, dw_active, (cudaStream_t)stream);
+}
+
+int ofa_dw_active_filter_bwd(const float* w7, int32_t kmax, const float* m75, const float* m53,
+                             int32_t transform_on, int32_t ks, int32_t C, const float* dw_active, float* dw7,
+                             float* dm75, float* dm53, void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  OFA_REQUIRE(w7 && dw_active && dw7, "ofa_dw_active_filter_bwd: null pointer");
+  if ((rc = check_transform_args(kmax, m75, m53, transform_on, ks))) return rc;
+  if (transform_on && ks < kmax) {
+    if (kmax == 7 && m75) OFA_REQUIRE(dm75 != nullptr, "dm75 required");
+    if (ks == 3) OFA_REQUIRE(dm53 != nullptr, "dm53 required");
+  }
+  return launch_active_filter_bwd(w7, kmax, m75, m53, transform_on, ks, C, dw_active, dw7, dm75, dm53,
+                                  (cudaStream_t)stream);
+}
+
+int ofa_conv_bwd_data(const OfaTensor4* dy, const OfaTensor4* dx, const float* w, int64_t w_so, int64_t w_si,
+                      int64_t w_sh, int64_t w_sw, int32_t cin, int32_t cout, int32_t ks, void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  if ((rc = check_tensor(dy, "dy"))) return rc;
+  if ((rc = check_tensor(dx, "dx"))) return rc;
+  OFA_REQUIRE(w != nullptr, "null weight");
+  OFA_REQUIRE(dy->c == cout && dx->c == cin && dy->n == dx->n && dy->h == dx->h && dy->w == dx->w,
+              "conv_bwd_data: shape mismatch");
+  // dX[p, i] = sum_{tap, o} dY[p - tap, o] W[o, i, tap]  ==  conv of dY with (o <-> i swapped, flipped) W
+  Epi none = make_epi(nullptr);
+  return launch_conv_simt(make_tv(dy), make_tv(dx), w, /*so=*/w_si, /*si=*/w_so, w_sh, w_sw, /*cin=*/cout,
+                          /*cout=*/cin, ks, /*flip=*/1, OFA_STORE_PLAIN, none, (cudaStream_t)stream);
+}
+
+int ofa_conv_bwd_weight(const OfaTensor4* x, const OfaTensor4* dy, float* dw, int64_t w_so, int64_t w_si,
+                        int64_t w_sh, int64_t w_sw, int32_t cin, int32_t cout, int32_t ks, void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  if ((rc = check_tensor(x, "x"))) return rc;
+  if ((rc = check_tensor(dy, "dy"))) return rc;
+  OFA_REQUIRE(dw != nullptr, "null dw");
+  OFA_REQUIRE(x->c == cin && dy->c == cout && dy->n == x->n && dy->h == x->h && dy->w == x->w,
+              "conv_bwd_weight: shape mismatch");
+  return launch_conv_bwd_weight(make_tv(x), make_tv(dy), dw, w_so, w_si, w_sh, w_sw, cin, cout, ks,
+                                (cudaStream_t)stream);
+}
+
+int ofa_bn_bwd_reduce(const OfaTensor4* x, const OfaTensor4* dy, const float* gamma, const float* beta,
+                      const float* mean, const float* var, float eps, int32_t act, float* sum_dz,
+                      float* sum_dz_xhat, void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  if ((rc = check_tensor(x, "x"))) return rc;
+  if ((rc = check_tensor(dy, "dy"))) return rc;
+  if ((rc = same_shape(x, dy, "bn_bwd_reduce x vs dy"))) return rc;
+  OFA_REQUIRE(mean && var && sum_dz && sum_dz_xhat, "ofa_bn_bwd_reduce: null pointer");
+  return launch_bn_bwd_reduce(make_tv(x), make_tv(dy), gamma, beta, mean, var, eps, act, sum_dz, sum_dz_xhat,
+                              (cudaStream_t)stream);
+}
+
+int ofa_bn_bwd_apply(const OfaTensor4* x, const OfaTensor4* dy, const OfaTensor4* dx, const float* gamma,
+                     const float* beta, const float* mean, const float* var, float eps, int32_t act,
+                     int32_t training, const float* sum_dz, const float* sum_dz_xhat, void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  if ((rc = check_tensor(x, "x"))) return rc;
+  if ((rc = check_tensor(dy, "dy"))) return rc;
+  if ((rc = check_tensor(dx, "dx"))) return rc;
+  if ((rc = same_shape(x, dy, "bn_bwd_apply x vs dy"))) return rc;
+  if ((rc = same_shape(x, dx, "bn_bwd_apply x vs dx"))) return rc;
+  if (training) OFA_REQUIRE(sum_dz && sum_dz_xhat && mean && var, "bn_bwd_apply(training): null stats");
+  return launch_bn_bwd_apply(make_tv(x), make_tv(dy), make_tv(dx), gamma, beta, mean, var, eps, act, training,
+                             sum_dz, sum_dz_xhat, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,221 @@
+// Kernel-size-elastic depthwise convolution, NHWC bf16, with the folded BatchNorm + ReLU6 epilogue
+// (dynamic_op.py:46-84 + dynamic_layers.py:48-57 in inference mode).
+//
+//   * a CTA owns a TH x TW pixel tile of one 64-channel chunk; the (TH+ks-1) x (TW+ks-1) x 64 halo
+//     box arrives with ONE TMA load whose out-of-bounds zero fill is the conv's zero padding;
+//   * while the load is in flight all threads derive the chunk's active filters from the 7x7
+//     weights and the learned 7->5 / 5->3 matrices (the transform is applied on the fly);
+//   * lane = channel pair, so every shared-memory access of a warp is one conflict-free 128-byte
+//     pixel row; each thread slides a window over 16 output pixels per pass so one smem word feeds
+//     up to ks taps; math is packed fp32x2 FMA (fma.rn.f32x2), fp32 accumulation.
+#include "ofa_common.cuh"
+#include "kernels.h"
+#include "sm100_ptx.cuh"
+
+#include <string.h>
+
+namespace ofa {
+namespace {
+
+constexpr int TH = 8, TW = 32, CH = 64, RUN = 16;
+constexpr int THREADS = 256;
+
+struct DwParams {
+  int N, H, W, C;
+  int kmax, transform_on;
+  const float* w7;
+  const float* m75;
+  const float* m53;
+  const float* gamma; const float* beta; const float* mean; const float* var; float eps;
+  int act;
+  __nv_bfloat16* y;
+  int tiles_w, tiles_h;
+};
+
+template <int KS>
+struct DwSmem {
+  static constexpr int HALO_H = TH + KS - 1;
+  static constexpr int HALO_W = TW + KS - 1;
+  static constexpr int TILE_BYTES = HALO_H * HALO_W * CH * 2;
+  static constexpr int FILT_OFF = (TILE_BYTES + 127) / 128 * 128;
+  static constexpr int FILT_BYTES = KS * KS * CH * 4;
+  static constexpr int K5_OFF = FILT_OFF + FILT_BYTES;
+  static constexpr int K5_BYTES = CH * 25 * 4;
+  static constexpr int SS_OFF = K5_OFF + K5_BYTES;
+  static constexpr int BAR_OFF = SS_OFF + 2 * CH * 4;
+  static constexpr int TOTAL = BAR_OFF + 16 + 128;  // + alignment slack
+};
+
+__device__ __forceinline__ float2 bf2_unpack(uint32_t u) {
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+
+template <int KS>
+__global__ void __launch_bounds__(THREADS, 2)
+dw_fast_kernel(const __grid_constant__ CUtensorMap tmap_x, const DwParams p) {
+  using L = DwSmem<KS>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  const uint32_t* tile = reinterpret_cast<const uint32_t*>(smem);           // [HALO_H][HALO_W][32] words
+  float* filt = reinterpret_cast<float*>(smem + L::FILT_OFF);               // [KS*KS][CH]
+  float* k5s = reinterpret_cast<float*>(smem + L::K5_OFF);                  // [CH][25]
+  float* s_scale = reinterpret_cast<float*>(smem + L::SS_OFF);
+  float* s_shift = s_scale + CH;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+
+  const int tid = threadIdx.x;
+  const int c0 = blockIdx.y * CH;
+  const int t = blockIdx.x;
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
+  const int n = t / tiles_per_img;
+  const int r = t - n * tiles_per_img;
+  const int h0 = (r / p.tiles_w) * TH, w0 = (r % p.tiles_w) * TW;
+  constexpr int R = KS / 2;
+
+  if (tid == 0) {
+    ptx::mbar_init(bar, 1);
+    ptx::fence_barrier_init();
+    ptx::mbar_arrive_expect_tx(bar, (uint32_t)L::TILE_BYTES);
+    ptx::tma_load_4d(smem, &tmap_x, bar, c0, w0 - R, h0 - R, n);
+  }
+
+  // ---- active filters of this channel chunk (overlaps the TMA load) -------------------------------
+  const int kmax = p.kmax;
+  const bool transform = p.transform_on && KS < kmax;
+  const bool step75 = transform && kmax == 7 && p.m75 != nullptr;
+  if (tid < CH) {
+    int c = c0 + tid;
+    float g = p.gamma ? p.gamma[c] : 1.f, b = p.beta ? p.beta[c] : 0.f;
+    float m = p.mean ? p.mean[c] : 0.f, rstd = p.var ? rsqrtf(p.var[c] + p.eps) : 1.f;
+    s_scale[tid] = g * rstd;
+    s_shift[tid] = b - m * g * rstd;
+  }
+  if (step75) {
+    for (int it = tid; it < CH * 25; it += THREADS) {
+      int c = it / 25, j = it - c * 25;
+      const float* w = p.w7 + (size_t)(c0 + c) * 49;
+      float acc = 0.f;
+#pragma unroll 5
+      for (int i = 0; i < 25; ++i) acc = fmaf(w[(i / 5 + 1) * 7 + (i % 5 + 1)], p.m75[j * 25 + i], acc);
+      k5s[c * 25 + j] = acc;
+    }
+  }
+  __syncthreads();
+  for (int it = tid; it < CH * KS * KS; it += THREADS) {
+    int c = it % CH, j = it / CH;
+    const float* w = p.w7 + (size_t)(c0 + c) * kmax * kmax;
+    float v;
+    if (!transform) {
+      const int s = kmax / 2 - R;
+      v = w[(j / KS + s) * kmax + (j % KS + s)];
+    } else {
+      const float* cur = step75 ? (k5s + c * 25) : w;
+      const int kc = step75 ? 5 : kmax;
+      if (KS == kc) {
+        v = cur[j];
+      } else {  // KS == 3
+        const int s = kc / 2 - 1;
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) acc = fmaf(cur[(i / 3 + s) * kc + (i % 3 + s)], p.m53[j * 9 + i], acc);
+        v = acc;
+      }
+    }
+    filt[j * CH + c] = v;
+  }
+  __syncthreads();
+  ptx::mbar_wait(bar, 0);
+
+  // ---- main: warp = output row, lane = channel pair, RUN output pixels per pass -------------------
+  const int warp = tid >> 5, lane = tid & 31;
+  const int h = h0 + warp;
+  const float2 sc = make_float2(s_scale[2 * lane], s_scale[2 * lane + 1]);
+  const float2 sh = make_float2(s_shift[2 * lane], s_shift[2 * lane + 1]);
+  const float2* filt2 = reinterpret_cast<const float2*>(filt);  // [KS*KS][32]
+#pragma unroll 1
+  for (int x0 = 0; x0 < TW; x0 += RUN) {
+    float2 acc[RUN];
+#pragma unroll
+    for (int i = 0; i < RUN; ++i) acc[i] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int ky = 0; ky < KS; ++ky) {
+      const uint32_t* row = tile + ((warp + ky) * L::HALO_W + x0) * 32 + lane;
+      float2 in[RUN + KS - 1];
+#pragma unroll
+      for (int i = 0; i < RUN + KS - 1; ++i) in[i] = bf2_unpack(row[i * 32]);
+#pragma unroll
+      for (int kx = 0; kx < KS; ++kx) {
+        const float2 wv = filt2[(ky * KS + kx) * 32 + lane];
+#pragma unroll
+        for (int i = 0; i < RUN; ++i) ptx::ffma2(acc[i], in[i + kx], wv);
+      }
+    }
+    if (h < p.H) {
+      __nv_bfloat16* yrow = p.y + (((size_t)n * p.H + h) * p.W) * p.C + c0 + 2 * lane;
+#pragma unroll
+      for (int i = 0; i < RUN; ++i) {
+        int w = w0 + x0 + i;
+        if (w < p.W) {
+          float a = apply_act(fmaf(acc[i].x, sc.x, sh.x), p.act);
+          float b = apply_act(fmaf(acc[i].y, sc.y, sh.y), p.act);
+          __nv_bfloat162 o = __floats2bfloat162_rn(a, b);
+          *reinterpret_cast<__nv_bfloat162*>(yrow + (size_t)w * p.C) = o;
+        }
+      }
+    }
+  }
+}
+
+template <int KS>
+int launch_ks(const CUtensorMap& tm, const DwParams& p, cudaStream_t st) {
+  using L = DwSmem<KS>;
+  OFA_CUDA(cudaFuncSetAttribute(dw_fast_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+  dim3 grid((unsigned)(p.N * p.tiles_w * p.tiles_h), p.C / CH);
+  dw_fast_kernel<KS><<<grid, THREADS, L::TOTAL, st>>>(tm, p);
+  return check_launch("dw_fast_kernel");
+}
+
+}  // namespace
+
+bool dw_fast_supported(const OfaTensor4* x, const OfaTensor4* y, int ks, const OfaEpilogue* epi) {
+  if (x->dtype != OFA_BF16 || y->dtype != OFA_BF16) return false;
+  if (!is_nhwc_dense(x) || !is_nhwc_dense(y)) return false;
+  if (x->c % CH != 0 || x->c == 0) return false;
+  if (ks != 3 && ks != 5 && ks != 7) return false;
+  if (epi && epi->residual) return false;
+  if ((reinterpret_cast<uintptr_t>(x->ptr) & 15) || (reinterpret_cast<uintptr_t>(y->ptr) & 3)) return false;
+  if (x->n <= 0 || x->h <= 0 || x->w <= 0) return false;
+  return true;
+}
+
+int launch_dw_fast(const OfaTensor4* x, const OfaTensor4* y, const float* w7, int kmax, const float* m75,
+                   const float* m53, int transform_on, int ks, const OfaEpilogue* epi, cudaStream_t st) {
+  if (kmax != 7 && transform_on && ks < kmax && kmax != 5)
+    return fail(OFA_ERR_UNSUPPORTED, "dw_fast: kmax %d", kmax);
+  DwParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = x->n; p.H = x->h; p.W = x->w; p.C = x->c;
+  p.kmax = kmax; p.transform_on = transform_on;
+  p.w7 = w7; p.m75 = m75; p.m53 = m53;
+  if (epi) {
+    p.gamma = epi->gamma; p.beta = epi->beta; p.mean = epi->mean; p.var = epi->var; p.eps = epi->eps;
+    p.act = epi->act;
+  }
+  p.y = reinterpret_cast<__nv_bfloat16*>(y->ptr);
+  p.tiles_w = (p.W + TW - 1) / TW;
+  p.tiles_h = (p.H + TH - 1) / TH;
+  CUtensorMap tm;
+  uint64_t dims[4] = {(uint64_t)p.C, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.N};
+  uint64_t strides[3] = {(uint64_t)p.C * 2, (uint64_t)p.W * p.C * 2, (uint64_t)p.H * p.W * p.C * 2};
+  uint32_t box[4] = {CH, (uint32_t)(TW + ks - 1), (uint32_t)(TH + ks - 1), 1};
+  int rc = encode_tmap(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x->ptr, dims, strides, box,
+                       CU_TENSOR_MAP_SWIZZLE_NONE);
+  if (rc) return rc;
+  switch (ks) {
+    case 3: return launch_ks<3>(tm, p, st);
+    case 5: return launch_ks<5>(tm, p, st);
+    default: return launch_ks<7>(tm, p, st);
+  }
+}
+
+}  // namespace ofa

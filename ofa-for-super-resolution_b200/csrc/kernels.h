@@ -1,0 +1,43 @@
+// Internal launch interface between api.cu (C ABI, argument checking, dispatch) and the kernel files.
+#pragma once
+#include "ofa_common.cuh"
+
+namespace ofa {
+
+// ---- simt_kernels.cu ----------------------------------------------------------------------------
+int launch_active_filter(const float* w7, int kmax, const float* m75, const float* m53, int transform_on,
+                         int ks, int C, float* out, cudaStream_t st);
+int launch_dw_simt(const TV& x, const TV& y, const float* w7, int kmax, const float* m75,
+                   const float* m53, int transform_on, int ks, int flip, const Epi& epi, cudaStream_t st);
+int launch_conv_simt(const TV& x, const TV& y, const float* w, long long w_so, long long w_si,
+                     long long w_sh, long long w_sw, int cin, int cout, int ks, int flip, int store,
+                     const Epi& epi, cudaStream_t st);
+int launch_pack_weight(const float* w, long long w_so, long long w_si, long long w_sh, long long w_sw,
+                       int cin, int cout, int ks, int cin_pad, int cout_pad, int store, void* out, cudaStream_t st);
+int launch_affine_act(const TV& x, const TV& y, const Epi& epi, int store, cudaStream_t st);
+int launch_bn_stats(const TV& x, float* mean, float* var, cudaStream_t st);
+int launch_bn_update_running(const float* mean, const float* var, long long count, float* rm, float* rv,
+                             float momentum, int C, cudaStream_t st);
+int launch_bn_bwd_reduce(const TV& x, const TV& dy, const float* gamma, const float* beta,
+                         const float* mean, const float* var, float eps, int act, float* sum_dz,
+                         float* sum_dz_xhat, cudaStream_t st);
+int launch_bn_bwd_apply(const TV& x, const TV& dy, const TV& dx, const float* gamma, const float* beta,
+                        const float* mean, const float* var, float eps, int act, int training,
+                        const float* sum_dz, const float* sum_dz_xhat, cudaStream_t st);
+int launch_dw_bwd_filter(const TV& x, const TV& dy, int ks, float* dw, cudaStream_t st);
+int launch_active_filter_bwd(const float* w7, int kmax, const float* m75, const float* m53,
+                             int transform_on, int ks, int C, const float* dwa, float* dw7, float* dm75,
+                             float* dm53, cudaStream_t st);
+int launch_conv_bwd_weight(const TV& x, const TV& dy, float* dw, long long w_so, long long w_si,
+                           long long w_sh, long long w_sw, int cin, int cout, int ks, cudaStream_t st);
+
+// ---- dw_fast.cu : NHWC bf16 depthwise, smem halo tiles --------------------------------------------
+bool dw_fast_supported(const OfaTensor4* x, const OfaTensor4* y, int ks, const OfaEpilogue* epi);
+int launch_dw_fast(const OfaTensor4* x, const OfaTensor4* y, const float* w7, int kmax, const float* m75,
+                   const float* m53, int transform_on, int ks, const OfaEpilogue* epi, cudaStream_t st);
+
+// ---- conv_tc.cu : NHWC bf16 implicit GEMM on tcgen05 / TMEM / TMA --------------------------------
+bool conv_tc_supported(const OfaConvArgs* a);
+int launch_conv_tc(const OfaConvArgs* a, cudaStream_t st);
+
+}  // namespace ofa

@@ -1,0 +1,739 @@
+// CUDA-core kernels of the elastic-MBConv SR path: any layout (strided views), fp32 or bf16 I/O,
+// fp32 math.  This is the exact path (fp32 parity, training forward/backward); the tensor-core /
+// TMA kernels of the bf16 inference path live in conv_tc.cu and dw_fast.cu.
+#include "ofa_common.cuh"
+#include "kernels.h"
+
+namespace ofa {
+
+// =================================================================================================
+// (a1) active depthwise filter  — one thread per channel
+// =================================================================================================
+__global__ void active_filter_kernel(const float* __restrict__ w7, int kmax,
+                                     const float* __restrict__ m75, const float* __restrict__ m53,
+                                     int transform_on, int ks, int C, float* __restrict__ out) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float f[49], tmp[25];
+  active_filter_channel(w7 + (size_t)c * kmax * kmax, kmax, m75, m53, transform_on, ks, f, tmp);
+  for (int j = 0; j < ks * ks; ++j) out[(size_t)c * ks * ks + j] = f[j];
+}
+
+int launch_active_filter(const float* w7, int kmax, const float* m75, const float* m53,
+                         int transform_on, int ks, int C, float* out, cudaStream_t st) {
+  if (C == 0) return OFA_OK;
+  active_filter_kernel<<<(C + 63) / 64, 64, 0, st>>>(w7, kmax, m75, m53, transform_on, ks, C, out);
+  return check_launch("active_filter_kernel");
+}
+
+// =================================================================================================
+// (a2) depthwise conv, generic layout.  Block = 32 channels x DW_PIX pixels per pass; the block's
+// 32 active filters are derived once in the prologue (the transform is applied on the fly, no
+// global scratch).  flip = 1 gives the data gradient.
+// =================================================================================================
+constexpr int DW_CH = 32;
+constexpr int DW_THREADS = 256;
+constexpr int DW_PIX_PER_BLOCK = 1024;
+
+template <int KS>
+__global__ void __launch_bounds__(DW_THREADS)
+dw_simt_kernel(TV x, TV y, const float* __restrict__ w7, int kmax, const float* __restrict__ m75,
+               const float* __restrict__ m53, int transform_on, int flip, Epi epi, int c_is_inner) {
+  __shared__ float sf[DW_CH][KS * KS + 1];
+  const int c0 = blockIdx.y * DW_CH;
+  const int C = x.c;
+  // prologue: one thread per channel derives its filter
+  if (threadIdx.x < DW_CH) {
+    int c = c0 + threadIdx.x;
+    if (c < C) {
+      float f[49], tmp[25];
+      active_filter_channel(w7 + (size_t)c * kmax * kmax, kmax, m75, m53, transform_on, KS, f, tmp);
+      for (int j = 0; j < KS * KS; ++j) sf[threadIdx.x][flip ? (KS * KS - 1 - j) : j] = f[j];
+    }
+  }
+  __syncthreads();
+
+  int cl, pl, pstep;
+  if (c_is_inner) { cl = threadIdx.x % DW_CH; pl = threadIdx.x / DW_CH; }
+  else            { pl = threadIdx.x % (DW_THREADS / DW_CH); cl = threadIdx.x / (DW_THREADS / DW_CH); }
+  pstep = DW_THREADS / DW_CH;
+  const int c = c0 + cl;
+  if (c >= C) return;
+  float scale, shift;
+  epi_scale_shift(epi, c, scale, shift);
+  const long long HW = (long long)x.h * x.w;
+  const long long P = HW * x.n;
+  const long long p_begin = (long long)blockIdx.x * DW_PIX_PER_BLOCK;
+  long long p_end = p_begin + DW_PIX_PER_BLOCK;
+  if (p_end > P) p_end = P;
+  constexpr int R = KS / 2;
+  for (long long p = p_begin + pl; p < p_end; p += pstep) {
+    int n = (int)(p / HW);
+    int rem = (int)(p - (long long)n * HW);
+    int h = rem / x.w, w = rem - h * x.w;
+    float acc = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < KS; ++ky) {
+      int ih = h + ky - R;
+      if (ih < 0 || ih >= x.h) continue;
+#pragma unroll
+      for (int kx = 0; kx < KS; ++kx) {
+        int iw = w + kx - R;
+        if (iw < 0 || iw >= x.w) continue;
+        acc = fmaf(x.ld(x.off(n, c, ih, iw)), sf[cl][ky * KS + kx], acc);
+      }
+    }
+    float v = apply_act(fmaf(acc, scale, shift), epi.act);
+    if (epi.res.ptr) v += epi.res.ld(epi.res.off(n, c, h, w));
+    y.st(y.off(n, c, h, w), v);
+  }
+}
+
+int launch_dw_simt(const TV& x, const TV& y, const float* w7, int kmax, const float* m75,
+                   const float* m53, int transform_on, int ks, int flip, const Epi& epi,
+                   cudaStream_t st) {
+  long long P = (long long)x.n * x.h * x.w;
+  if (P == 0 || x.c == 0) return OFA_OK;
+  dim3 grid((unsigned)((P + DW_PIX_PER_BLOCK - 1) / DW_PIX_PER_BLOCK), (x.c + DW_CH - 1) / DW_CH);
+  int ci = (x.sc == 1);
+  switch (ks) {
+    case 3: dw_simt_kernel<3><<<grid, DW_THREADS, 0, st>>>(x, y, w7, kmax, m75, m53, transform_on, flip, epi, ci); break;
+    case 5: dw_simt_kernel<5><<<grid, DW_THREADS, 0, st>>>(x, y, w7, kmax, m75, m53, transform_on, flip, epi, ci); break;
+    case 7: dw_simt_kernel<7><<<grid, DW_THREADS, 0, st>>>(x, y, w7, kmax, m75, m53, transform_on, flip, epi, ci); break;
+    default: return fail(OFA_ERR_UNSUPPORTED, "depthwise kernel size %d (supported: 3, 5, 7)", ks);
+  }
+  return check_launch("dw_simt_kernel");
+}
+
+// =================================================================================================
+// (a3, a4, a9-a11) dense conv as an implicit GEMM on CUDA cores.
+//   C[p, o] = sum_k A[p, k] * B[k, o],  k = (ky*ks + kx)*cin + ci,  A gathered with zero padding.
+//   Tile 64 pixels x 64 outputs, 256 threads, 4x4 register tile, K chunk 16.
+// =================================================================================================
+constexpr int CV_TP = 64, CV_TO = 64, CV_TK = 16, CV_THREADS = 256;
+
+__global__ void __launch_bounds__(CV_THREADS)
+conv_simt_kernel(TV x, TV y, const float* __restrict__ w, long long w_so, long long w_si,
+                 long long w_sh, long long w_sw, int cin, int cout, int ks, int flip, int store,
+                 Epi epi) {
+  __shared__ float sA[CV_TK][CV_TP + 4];
+  __shared__ float sB[CV_TK][CV_TO + 4];
+  const int H = x.h, W = x.w;
+  const long long HW = (long long)H * W;
+  const long long P = HW * x.n;
+  const long long p0 = (long long)blockIdx.x * CV_TP;
+  const int o0 = blockIdx.y * CV_TO;
+  const int K = ks * ks * cin;
+  const int R = ks / 2;
+  const int tid = threadIdx.x;
+  const int tp = (tid % 16) * 4;  // pixel sub-tile
+  const int to = (tid / 16) * 4;  // output sub-tile
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  // A loader: thread -> (kk = tid % 16, pixel = tid / 16 + 16*r)
+  const int a_kk = tid % CV_TK;
+  const int a_p = tid / CV_TK;
+  int a_n[4], a_h[4], a_w[4];
+  bool a_ok[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    long long p = p0 + a_p + 16 * r;
+    a_ok[r] = p < P;
+    long long pp = a_ok[r] ? p : 0;
+    a_n[r] = (int)(pp / HW);
+    int rem = (int)(pp - (long long)a_n[r] * HW);
+    a_h[r] = rem / W;
+    a_w[r] = rem - a_h[r] * W;
+  }
+  // B loader: thread -> (oo = tid % 64, kk = tid / 64 + 4*r)
+  const int b_o = tid % CV_TO;
+  const int b_k = tid / CV_TO;
+
+  for (int k0 = 0; k0 < K; k0 += CV_TK) {
+    {
+      int k = k0 + a_kk;
+      int tap = k / cin, ci = k - tap * cin;
+      int ky = tap / ks, kx = tap - ky * ks;
+      bool kok = k < K;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        float v = 0.f;
+        int ih = a_h[r] + ky - R, iw = a_w[r] + kx - R;
+        if (kok && a_ok[r] && ih >= 0 && ih < H && iw >= 0 && iw < W) v = x.ld(x.off(a_n[r], ci, ih, iw));
+        sA[a_kk][a_p + 16 * r] = v;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      int kk = b_k + 4 * r;
+      int k = k0 + kk;
+      float v = 0.f;
+      int o = o0 + b_o;
+      if (k < K && o < cout) {
+        int tap = k / cin, ci = k - tap * cin;
+        int ky = tap / ks, kx = tap - ky * ks;
+        if (flip) { ky = ks - 1 - ky; kx = ks - 1 - kx; }
+        v = w[o * w_so + ci * w_si + ky * w_sh + kx * w_sw];
+      }
+      sB[kk][b_o] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < CV_TK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = sA[kk][tp + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = sB[kk][to + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    long long p = p0 + tp + i;
+    if (p >= P) continue;
+    int n = (int)(p / HW);
+    int rem = (int)(p - (long long)n * HW);
+    int h = rem / W, wq = rem - h * W;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int o = o0 + to + j;
+      if (o >= cout) continue;
+      float scale, shift;
+      epi_scale_shift(epi, o, scale, shift);
+      float v = apply_act(fmaf(acc[i][j], scale, shift), epi.act);
+      int oc, oh, ow;
+      store_coord(store, o, h, wq, oc, oh, ow);
+      if (epi.res.ptr) v += epi.res.ld(epi.res.off(n, oc, oh, ow));
+      y.st(y.off(n, oc, oh, ow), v);
+    }
+  }
+}
+
+int launch_conv_simt(const TV& x, const TV& y, const float* w, long long w_so, long long w_si,
+                     long long w_sh, long long w_sw, int cin, int cout, int ks, int flip, int store,
+                     const Epi& epi, cudaStream_t st) {
+  long long P = (long long)x.n * x.h * x.w;
+  if (P == 0 || cout == 0) return OFA_OK;
+  dim3 grid((unsigned)((P + CV_TP - 1) / CV_TP), (cout + CV_TO - 1) / CV_TO);
+  conv_simt_kernel<<<grid, CV_THREADS, 0, st>>>(x, y, w, w_so, w_si, w_sh, w_sw, cin, cout, ks, flip, store, epi);
+  return check_launch("conv_simt_kernel");
+}
+
+// =================================================================================================
+// weight packing: fp32 strided slice -> bf16 [tap][cout_pad][cin_pad]
+// =================================================================================================
+__global__ void pack_weight_kernel(const float* __restrict__ w, long long w_so, long long w_si,
+                                   long long w_sh, long long w_sw, int cin, int cout, int ks,
+                                   int cin_pad, int cout_pad, int store,
+                                   __nv_bfloat16* __restrict__ out) {
+  long long total = (long long)ks * ks * cout_pad * cin_pad;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int ci = (int)(i % cin_pad);
+    long long r = i / cin_pad;
+    int o = (int)(r % cout_pad);
+    int tap = (int)(r / cout_pad);
+    int ky = tap / ks, kx = tap - ky * ks;
+    float v = 0.f;
+    if (ci < cin && o < cout) {
+      // PixelShuffle layers are packed sub-pixel major (row s*q + c' holds conv channel 4c' + s) so a
+      // tile's accumulator columns of one sub-pixel are contiguous output channels
+      int oo = o;
+      if (store == OFA_STORE_PIXELSHUFFLE2) { int q = cout >> 2; oo = 4 * (o % q) + o / q; }
+      v = w[oo * w_so + ci * w_si + ky * w_sh + kx * w_sw];
+    }
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+int launch_pack_weight(const float* w, long long w_so, long long w_si, long long w_sh, long long w_sw,
+                       int cin, int cout, int ks, int cin_pad, int cout_pad, int store, void* out,
+                       cudaStream_t st) {
+  long long total = (long long)ks * ks * cout_pad * cin_pad;
+  if (total == 0) return OFA_OK;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 1184) blocks = 1184;
+  pack_weight_kernel<<<blocks, 256, 0, st>>>(w, w_so, w_si, w_sh, w_sw, cin, cout, ks, cin_pad, cout_pad, store,
+                                             reinterpret_cast<__nv_bfloat16*>(out));
+  return check_launch("pack_weight_kernel");
+}
+
+// =================================================================================================
+// elementwise: y = store(act(affine(x))) + residual
+// =================================================================================================
+__global__ void affine_act_kernel(TV x, TV y, Epi epi, int store, int c_is_inner) {
+  const long long total = (long long)x.n * x.c * x.h * x.w;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int n, c, h, w;
+    long long r = i;
+    if (c_is_inner) {
+      c = (int)(r % x.c); r /= x.c;
+      w = (int)(r % x.w); r /= x.w;
+      h = (int)(r % x.h); n = (int)(r / x.h);
+    } else {
+      w = (int)(r % x.w); r /= x.w;
+      h = (int)(r % x.h); r /= x.h;
+      c = (int)(r % x.c); n = (int)(r / x.c);
+    }
+    float scale, shift;
+    epi_scale_shift(epi, c, scale, shift);
+    float v = apply_act(fmaf(x.ld(x.off(n, c, h, w)), scale, shift), epi.act);
+    int oc, oh, ow;
+    store_coord(store, c, h, w, oc, oh, ow);
+    if (epi.res.ptr) v += epi.res.ld(epi.res.off(n, oc, oh, ow));
+    y.st(y.off(n, oc, oh, ow), v);
+  }
+}
+
+int launch_affine_act(const TV& x, const TV& y, const Epi& epi, int store, cudaStream_t st) {
+  long long total = (long long)x.n * x.c * x.h * x.w;
+  if (total == 0) return OFA_OK;
+  long long blocks = (total + 255) / 256;
+  long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  affine_act_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, y, epi, store, x.sc == 1);
+  return check_launch("affine_act_kernel");
+}
+
+// =================================================================================================
+// (a5) training BN: batch statistics.  One block per 32 channels, 8 pixel lanes; two passes
+// (mean, then centred second moment) so the variance matches F.batch_norm to fp32 rounding.
+// =================================================================================================
+constexpr int BN_CH = 32, BN_THREADS = 256, BN_PL = BN_THREADS / BN_CH;
+
+__device__ __forceinline__ void pix_decode(long long p, long long HW, int W, int& n, int& h, int& w) {
+  n = (int)(p / HW);
+  int rem = (int)(p - (long long)n * HW);
+  h = rem / W;
+  w = rem - h * W;
+}
+
+__global__ void __launch_bounds__(BN_THREADS)
+bn_stats_kernel(TV x, float* __restrict__ mean, float* __restrict__ var, int c_is_inner) {
+  __shared__ float red[BN_PL][BN_CH + 1];
+  __shared__ float smean[BN_CH];
+  int cl, pl;
+  if (c_is_inner) { cl = threadIdx.x % BN_CH; pl = threadIdx.x / BN_CH; }
+  else            { pl = threadIdx.x % BN_PL; cl = threadIdx.x / BN_PL; }
+  const int c = blockIdx.x * BN_CH + cl;
+  const long long HW = (long long)x.h * x.w;
+  const long long P = HW * x.n;
+  const bool ok = c < x.c;
+  float s = 0.f;
+  if (ok)
+    for (long long p = pl; p < P; p += BN_PL) {
+      int n, h, w;
+      pix_decode(p, HW, x.w, n, h, w);
+      s += x.ld(x.off(n, c, h, w));
+    }
+  red[pl][cl] = s;
+  __syncthreads();
+  if (threadIdx.x < BN_CH) {
+    double t = 0.0;
+    for (int i = 0; i < BN_PL; ++i) t += red[i][threadIdx.x];
+    smean[threadIdx.x] = (float)(t / (double)P);
+  }
+  __syncthreads();
+  const float m = smean[cl];
+  float q = 0.f;
+  if (ok)
+    for (long long p = pl; p < P; p += BN_PL) {
+      int n, h, w;
+      pix_decode(p, HW, x.w, n, h, w);
+      float d = x.ld(x.off(n, c, h, w)) - m;
+      q = fmaf(d, d, q);
+    }
+  red[pl][cl] = q;
+  __syncthreads();
+  if (threadIdx.x < BN_CH) {
+    int cc = blockIdx.x * BN_CH + threadIdx.x;
+    if (cc < x.c) {
+      double t = 0.0;
+      for (int i = 0; i < BN_PL; ++i) t += red[i][threadIdx.x];
+      mean[cc] = smean[threadIdx.x];
+      var[cc] = (float)(t / (double)P);
+    }
+  }
+}
+
+int launch_bn_stats(const TV& x, float* mean, float* var, cudaStream_t st) {
+  if (x.c == 0) return OFA_OK;
+  bn_stats_kernel<<<(x.c + BN_CH - 1) / BN_CH, BN_THREADS, 0, st>>>(x, mean, var, x.sc == 1);
+  return check_launch("bn_stats_kernel");
+}
+
+__global__ void bn_update_running_kernel(const float* __restrict__ mean, const float* __restrict__ var,
+                                         float unbias, float* __restrict__ rm, float* __restrict__ rv,
+                                         float momentum, int C) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  rm[c] = (1.f - momentum) * rm[c] + momentum * mean[c];
+  rv[c] = (1.f - momentum) * rv[c] + momentum * (var[c] * unbias);
+}
+
+int launch_bn_update_running(const float* mean, const float* var, long long count, float* rm, float* rv,
+                             float momentum, int C, cudaStream_t st) {
+  if (C == 0) return OFA_OK;
+  float unbias = count > 1 ? (float)((double)count / (double)(count - 1)) : 1.f;
+  bn_update_running_kernel<<<(C + 127) / 128, 128, 0, st>>>(mean, var, unbias, rm, rv, momentum, C);
+  return check_launch("bn_update_running_kernel");
+}
+
+// =================================================================================================
+// (a14) BN (+act) backward
+// =================================================================================================
+__global__ void __launch_bounds__(BN_THREADS)
+bn_bwd_reduce_kernel(TV x, TV dy, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     const float* __restrict__ mean, const float* __restrict__ var, float eps, int act,
+                     float* __restrict__ sum_dz, float* __restrict__ sum_dz_xhat, int c_is_inner) {
+  __shared__ float red0[BN_PL][BN_CH + 1];
+  __shared__ float red1[BN_PL][BN_CH + 1];
+  int cl, pl;
+  if (c_is_inner) { cl = threadIdx.x % BN_CH; pl = threadIdx.x / BN_CH; }
+  else            { pl = threadIdx.x % BN_PL; cl = threadIdx.x / BN_PL; }
+  const int c = blockIdx.x * BN_CH + cl;
+  const long long HW = (long long)x.h * x.w;
+  const long long P = HW * x.n;
+  float s0 = 0.f, s1 = 0.f;
+  if (c < x.c) {
+    const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+    const float m = mean[c], rstd = rsqrtf(var[c] + eps);
+    for (long long p = pl; p < P; p += BN_PL) {
+      int n, h, w;
+      pix_decode(p, HW, x.w, n, h, w);
+      float xhat = (x.ld(x.off(n, c, h, w)) - m) * rstd;
+      float z = fmaf(g, xhat, b);
+      float dz = dy.ld(dy.off(n, c, h, w)) * act_grad(z, act);
+      s0 += dz;
+      s1 = fmaf(dz, xhat, s1);
+    }
+  }
+  red0[pl][cl] = s0;
+  red1[pl][cl] = s1;
+  __syncthreads();
+  if (threadIdx.x < BN_CH) {
+    int cc = blockIdx.x * BN_CH + threadIdx.x;
+    if (cc < x.c) {
+      double t0 = 0.0, t1 = 0.0;
+      for (int i = 0; i < BN_PL; ++i) { t0 += red0[i][threadIdx.x]; t1 += red1[i][threadIdx.x]; }
+      sum_dz[cc] = (float)t0;
+      sum_dz_xhat[cc] = (float)t1;
+    }
+  }
+}
+
+int launch_bn_bwd_reduce(const TV& x, const TV& dy, const float* gamma, const float* beta,
+                         const float* mean, const float* var, float eps, int act, float* sum_dz,
+                         float* sum_dz_xhat, cudaStream_t st) {
+  if (x.c == 0) return OFA_OK;
+  bn_bwd_reduce_kernel<<<(x.c + BN_CH - 1) / BN_CH, BN_THREADS, 0, st>>>(x, dy, gamma, beta, mean, var, eps, act,
+                                                                      sum_dz, sum_dz_xhat, x.sc == 1);
+  return check_launch("bn_bwd_reduce_kernel");
+}
+
+__global__ void bn_bwd_apply_kernel(TV x, TV dy, TV dx, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, const float* __restrict__ mean,
+                                    const float* __restrict__ var, float eps, int act, int training,
+                                    const float* __restrict__ sum_dz,
+                                    const float* __restrict__ sum_dz_xhat, int c_is_inner) {
+  const long long total = (long long)x.n * x.c * x.h * x.w;
+  const float invP = 1.f / (float)((long long)x.n * x.h * x.w);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int n, c, h, w;
+    long long r = i;
+    if (c_is_inner) {
+      c = (int)(r % x.c); r /= x.c;
+      w = (int)(r % x.w); r /= x.w;
+      h = (int)(r % x.h); n = (int)(r / x.h);
+    } else {
+      w = (int)(r % x.w); r /= x.w;
+      h = (int)(r % x.h); r /= x.h;
+      c = (int)(r % x.c); n = (int)(r / x.c);
+    }
+    const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+    const float m = mean ? mean[c] : 0.f, rstd = var ? rsqrtf(var[c] + eps) : 1.f;
+    float xhat = (x.ld(x.off(n, c, h, w)) - m) * rstd;
+    float z = fmaf(g, xhat, b);
+    float dz = dy.ld(dy.off(n, c, h, w)) * act_grad(z, act);
+    float v;
+    if (training) v = g * rstd * (dz - sum_dz[c] * invP - xhat * sum_dz_xhat[c] * invP);
+    else v = g * rstd * dz;
+    dx.st(dx.off(n, c, h, w), v);
+  }
+}
+
+int launch_bn_bwd_apply(const TV& x, const TV& dy, const TV& dx, const float* gamma, const float* beta,
+                        const float* mean, const float* var, float eps, int act, int training,
+                        const float* sum_dz, const float* sum_dz_xhat, cudaStream_t st) {
+  long long total = (long long)x.n * x.c * x.h * x.w;
+  if (total == 0) return OFA_OK;
+  long long blocks = (total + 255) / 256;
+  long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  bn_bwd_apply_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, dy, dx, gamma, beta, mean, var, eps, act, training,
+                                                        sum_dz, sum_dz_xhat, x.sc == 1);
+  return check_launch("bn_bwd_apply_kernel");
+}
+
+// =================================================================================================
+// (a14) depthwise filter gradient: dW[c, tap] = sum_p x[p + tap] * dy[p]
+//   grid (C/32, pixel splits); each thread keeps KS*KS accumulators; block reduce; atomicAdd.
+// =================================================================================================
+template <int KS>
+__global__ void __launch_bounds__(BN_THREADS)
+dw_bwd_filter_kernel(TV x, TV dy, float* __restrict__ dw, long long pix_per_block, int c_is_inner) {
+  __shared__ float red[BN_PL][BN_CH + 1];
+  int cl, pl;
+  if (c_is_inner) { cl = threadIdx.x % BN_CH; pl = threadIdx.x / BN_CH; }
+  else            { pl = threadIdx.x % BN_PL; cl = threadIdx.x / BN_PL; }
+  const int c = blockIdx.x * BN_CH + cl;
+  const long long HW = (long long)x.h * x.w;
+  const long long P = HW * x.n;
+  const long long p_begin = (long long)blockIdx.y * pix_per_block;
+  long long p_end = p_begin + pix_per_block;
+  if (p_end > P) p_end = P;
+  constexpr int R = KS / 2;
+  float acc[KS * KS];
+#pragma unroll
+  for (int j = 0; j < KS * KS; ++j) acc[j] = 0.f;
+  if (c < x.c)
+    for (long long p = p_begin + pl; p < p_end; p += BN_PL) {
+      int n, h, w;
+      pix_decode(p, HW, x.w, n, h, w);
+      float g = dy.ld(dy.off(n, c, h, w));
+#pragma unroll
+      for (int ky = 0; ky < KS; ++ky) {
+        int ih = h + ky - R;
+        if (ih < 0 || ih >= x.h) continue;
+#pragma unroll
+        for (int kx = 0; kx < KS; ++kx) {
+          int iw = w + kx - R;
+          if (iw < 0 || iw >= x.w) continue;
+          acc[ky * KS + kx] = fmaf(x.ld(x.off(n, c, ih, iw)), g, acc[ky * KS + kx]);
+        }
+      }
+    }
+#pragma unroll
+  for (int j = 0; j < KS * KS; ++j) {
+    red[pl][cl] = acc[j];
+    __syncthreads();
+    if (threadIdx.x < BN_CH) {
+      int cc = blockIdx.x * BN_CH + threadIdx.x;
+      if (cc < x.c) {
+        float t = 0.f;
+        for (int i = 0; i < BN_PL; ++i) t += red[i][threadIdx.x];
+        atomicAdd(&dw[(size_t)cc * KS * KS + j], t);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+int launch_dw_bwd_filter(const TV& x, const TV& dy, int ks, float* dw, cudaStream_t st) {
+  if (x.c == 0) return OFA_OK;
+  cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)x.c * ks * ks, st);
+  if (e != cudaSuccess) return fail(OFA_ERR_CUDA, "memset dw: %s", cudaGetErrorString(e));
+  long long P = (long long)x.n * x.h * x.w;
+  if (P == 0) return OFA_OK;
+  int cb = (x.c + BN_CH - 1) / BN_CH;
+  long long splits = (long long)sm_count() * 4 / cb;
+  if (splits < 1) splits = 1;
+  long long ppb = (P + splits - 1) / splits;
+  if (ppb < 256) ppb = 256;
+  splits = (P + ppb - 1) / ppb;
+  dim3 grid(cb, (unsigned)splits);
+  int ci = x.sc == 1;
+  switch (ks) {
+    case 3: dw_bwd_filter_kernel<3><<<grid, BN_THREADS, 0, st>>>(x, dy, dw, ppb, ci); break;
+    case 5: dw_bwd_filter_kernel<5><<<grid, BN_THREADS, 0, st>>>(x, dy, dw, ppb, ci); break;
+    case 7: dw_bwd_filter_kernel<7><<<grid, BN_THREADS, 0, st>>>(x, dy, dw, ppb, ci); break;
+    default: return fail(OFA_ERR_UNSUPPORTED, "depthwise kernel size %d", ks);
+  }
+  return check_launch("dw_bwd_filter_kernel");
+}
+
+// chain rule through the filter transform (dynamic_op.py:46-71), one thread per channel, atomics
+// for the shared matrices.
+__global__ void active_filter_bwd_kernel(const float* __restrict__ w7, int kmax,
+                                         const float* __restrict__ m75, const float* __restrict__ m53,
+                                         int transform_on, int ks, int C,
+                                         const float* __restrict__ dwa, float* __restrict__ dw7,
+                                         float* __restrict__ dm75, float* __restrict__ dm53) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float* w = w7 + (size_t)c * kmax * kmax;
+  float* dw = dw7 + (size_t)c * kmax * kmax;
+  const float* g = dwa + (size_t)c * ks * ks;
+  if (!transform_on || ks == kmax) {
+    const int s = kmax / 2 - ks / 2;
+    for (int y = 0; y < ks; ++y)
+      for (int x = 0; x < ks; ++x) dw[(y + s) * kmax + (x + s)] += g[y * ks + x];
+    return;
+  }
+  // forward recompute of the intermediate 5x5 (when the 7->5 step exists)
+  float k5[25], g5[25];
+  const float* cur = w;
+  int kc = kmax;
+  const bool step75 = (kmax == 7 && m75 != nullptr);
+  if (step75) {
+    for (int j = 0; j < 25; ++j) {
+      float acc = 0.f;
+      for (int i = 0; i < 25; ++i) acc = fmaf(w[(i / 5 + 1) * 7 + (i % 5 + 1)], m75[j * 25 + i], acc);
+      k5[j] = acc;
+    }
+    cur = k5;
+    kc = 5;
+  }
+  // gradient w.r.t. `cur` (size kc*kc)
+  float gcur[49];
+  for (int j = 0; j < kc * kc; ++j) gcur[j] = 0.f;
+  if (ks == kc) {
+    for (int j = 0; j < kc * kc; ++j) gcur[j] = g[j];
+  } else {
+    const int s = kc / 2 - 1;
+    for (int j = 0; j < 9; ++j)
+      for (int i = 0; i < 9; ++i) {
+        int src = (i / 3 + s) * kc + (i % 3 + s);
+        atomicAdd(&dm53[j * 9 + i], g[j] * cur[src]);
+        gcur[src] = fmaf(g[j], m53[j * 9 + i], gcur[src]);
+      }
+  }
+  if (step75) {
+    for (int j = 0; j < 25; ++j) g5[j] = gcur[j];
+    for (int j = 0; j < 25; ++j)
+      for (int i = 0; i < 25; ++i) {
+        int src = (i / 5 + 1) * 7 + (i % 5 + 1);
+        atomicAdd(&dm75[j * 25 + i], g5[j] * w[src]);
+        dw[src] += g5[j] * m75[j * 25 + i];
+      }
+  } else {
+    for (int j = 0; j < kc * kc; ++j) dw[j] += gcur[j];
+  }
+}
+
+int launch_active_filter_bwd(const float* w7, int kmax, const float* m75, const float* m53,
+                             int transform_on, int ks, int C, const float* dwa, float* dw7, float* dm75,
+                             float* dm53, cudaStream_t st) {
+  if (C == 0) return OFA_OK;
+  active_filter_bwd_kernel<<<(C + 63) / 64, 64, 0, st>>>(w7, kmax, m75, m53, transform_on, ks, C, dwa, dw7,
+                                                         dm75, dm53);
+  return check_launch("active_filter_bwd_kernel");
+}
+
+// =================================================================================================
+// (a14) dense conv weight gradient: dW[o, i, ky, kx] += sum_p dy[p, o] * x[p + tap, i]
+//   GEMM with the reduction over pixels: tile 64 outputs x 64 (tap, ci) columns, split over pixels
+//   in grid.z, atomicAdd into the strided slice.
+// =================================================================================================
+__global__ void __launch_bounds__(CV_THREADS)
+conv_bwd_weight_kernel(TV x, TV dy, float* __restrict__ dw, long long w_so, long long w_si,
+                       long long w_sh, long long w_sw, int cin, int cout, int ks,
+                       long long pix_per_block) {
+  __shared__ float sA[CV_TK][CV_TO + 4];  // dy  [pixel kk][o]
+  __shared__ float sB[CV_TK][CV_TP + 4];  // x   [pixel kk][col]
+  const int H = x.h, W = x.w;
+  const long long HW = (long long)H * W;
+  const long long P = HW * x.n;
+  const int o0 = blockIdx.x * CV_TO;
+  const int col0 = blockIdx.y * CV_TP;
+  const int ncol = ks * ks * cin;
+  const int R = ks / 2;
+  const long long p_begin = (long long)blockIdx.z * pix_per_block;
+  long long p_end = p_begin + pix_per_block;
+  if (p_end > P) p_end = P;
+  const int tid = threadIdx.x;
+  const int to = (tid % 16) * 4;
+  const int tc = (tid / 16) * 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  // loaders: thread -> (e = tid % 64 (o or col), kk = tid / 64 + 4*r)
+  const int l_e = tid % 64;
+  const int l_k = tid / 64;
+  // column decode for the x loader
+  const int col = col0 + l_e;
+  const bool col_ok = col < ncol;
+  int ctap = col_ok ? col / cin : 0;
+  const int cci = col_ok ? col - ctap * cin : 0;
+  const int cky = ctap / ks, ckx = ctap - cky * ks;
+
+  for (long long pb = p_begin; pb < p_end; pb += CV_TK) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      int kk = l_k + 4 * r;
+      long long p = pb + kk;
+      float va = 0.f, vb = 0.f;
+      if (p < p_end) {
+        int n, h, w;
+        pix_decode(p, HW, W, n, h, w);
+        int o = o0 + l_e;
+        if (o < cout) va = dy.ld(dy.off(n, o, h, w));
+        int ih = h + cky - R, iw = w + ckx - R;
+        if (col_ok && ih >= 0 && ih < H && iw >= 0 && iw < W) vb = x.ld(x.off(n, cci, ih, iw));
+      }
+      sA[kk][l_e] = va;
+      sB[kk][l_e] = vb;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < CV_TK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = sA[kk][to + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = sB[kk][tc + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int o = o0 + to + i;
+    if (o >= cout) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int cc = col0 + tc + j;
+      if (cc >= ncol) continue;
+      int tap = cc / cin, ci = cc - tap * cin;
+      int ky = tap / ks, kx = tap - ky * ks;
+      atomicAdd(&dw[o * w_so + ci * w_si + ky * w_sh + kx * w_sw], acc[i][j]);
+    }
+  }
+}
+
+int launch_conv_bwd_weight(const TV& x, const TV& dy, float* dw, long long w_so, long long w_si,
+                           long long w_sh, long long w_sw, int cin, int cout, int ks, cudaStream_t st) {
+  long long P = (long long)x.n * x.h * x.w;
+  if (P == 0 || cin == 0 || cout == 0) return OFA_OK;
+  int gx = (cout + CV_TO - 1) / CV_TO;
+  int gy = (ks * ks * cin + CV_TP - 1) / CV_TP;
+  long long splits = (long long)sm_count() * 2 / ((long long)gx * gy);
+  if (splits < 1) splits = 1;
+  long long ppb = (P + splits - 1) / splits;
+  ppb = (ppb + CV_TK - 1) / CV_TK * CV_TK;
+  if (ppb < 256) ppb = 256;
+  splits = (P + ppb - 1) / ppb;
+  if (splits > 65535) return fail(OFA_ERR_UNSUPPORTED, "conv_bwd_weight: too many pixel splits");
+  dim3 grid(gx, gy, (unsigned)splits);
+  conv_bwd_weight_kernel<<<grid, CV_THREADS, 0, st>>>(x, dy, dw, w_so, w_si, w_sh, w_sw, cin, cout, ks, ppb);
+  return check_launch("conv_bwd_weight_kernel");
+}
+
+}  // namespace ofa

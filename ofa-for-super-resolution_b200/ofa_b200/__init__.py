@@ -1,0 +1,12 @@
+"""ofa_b200 — B200-native (sm_100a) implementation of the elastic-MBConv super-resolution hot path
+of twice154/ofa-for-super-resolution, behind the reference's own `ofa/elastic_nn` module API.
+
+    from ofa_b200.elastic_nn.networks import OFAMobileNetS4, OFAMobileNetX4
+    from ofa_b200.elastic_nn.modules import DynamicMBConvLayer, DynamicSeparableConv2d, ...
+
+All activation math runs in libofa_sr_b200.so (include/ofa_sr_b200.h); there is no CPU fallback.
+"""
+from . import backend, functional  # noqa: F401
+from .functional import set_compute_dtype, get_compute_dtype, set_impl  # noqa: F401
+
+__version__ = '0.1.0'

@@ -1,0 +1,391 @@
+"""Operator layer between the drop-in nn.Modules and the C-ABI library.
+
+Two families:
+  * autograd Functions (training / grad-enabled path): DwConvFn, ConvFn, BnActFn, ReorderFn — forward
+    and backward each call the library's kernels;
+  * fused inference calls (no grad, module.eval()): conv + folded BN + activation + residual /
+    long-skip + PixelShuffle / PixelUnshuffle store in ONE kernel, and the whole MBConv block.
+
+Tensors produced here are logical NCHW stored channels-last (NHWC memory); inputs may have any
+strides (the user's NCHW fp32 image is read in place).
+"""
+import ctypes
+from ctypes import byref
+
+import torch
+
+from . import backend as B
+
+_state = {'compute_dtype': torch.bfloat16, 'impl': B.IMPL_AUTO}
+
+
+def set_compute_dtype(dtype):
+    """Activation storage type of the fused inference path: torch.bfloat16 (tensor-core path,
+    default) or torch.float32 (exact CUDA-core path).  Accumulation is fp32 either way."""
+    assert dtype in (torch.bfloat16, torch.float32)
+    _state['compute_dtype'] = dtype
+
+
+def get_compute_dtype():
+    return _state['compute_dtype']
+
+
+def set_impl(impl):
+    """Testing / profiling: force B.IMPL_SIMT or B.IMPL_FAST (default B.IMPL_AUTO)."""
+    _state['impl'] = impl
+
+
+def _stream(t):
+    return B.stream_ptr(t.device)
+
+
+def _null_or(t):
+    return B.fptr(t) if t is not None else None
+
+
+# =================================================================================================
+# depthwise (a1, a2, a14)
+# =================================================================================================
+
+def _transform_ptrs(m75, m53):
+    return _null_or(m75), _null_or(m53)
+
+
+def dw_active_filter(w7, m75, m53, transform_on, ks, C):
+    """DynamicSeparableConv2d.get_active_filter (dynamic_op.py:46-71) -> [C,1,ks,ks] fp32."""
+    kmax = w7.shape[-1]
+    out = torch.empty((C, 1, ks, ks), dtype=torch.float32, device=w7.device)
+    p75, p53 = _transform_ptrs(m75, m53)
+    B.check(B.lib().ofa_dw_active_filter(B.fptr(w7), kmax, p75, p53, int(bool(transform_on)), ks, C,
+                                         out.data_ptr(), _stream(w7)))
+    return out
+
+
+class DwConvFn(torch.autograd.Function):
+    """y = depthwise_conv(x, active_filter(w7, m75, m53, ks)), stride 1, same padding."""
+
+    @staticmethod
+    def forward(ctx, x, w7, m75, m53, ks, transform_on):
+        n, c, h, w = x.shape
+        y = B.new_nhwc(n, c, h, w, x.dtype, x.device)
+        p75, p53 = _transform_ptrs(m75, m53)
+        tx, ty = B.t4(x), B.t4(y)
+        B.check(B.lib().ofa_dw_fwd(byref(tx), byref(ty), B.fptr(w7), w7.shape[-1], p75, p53,
+                                   int(bool(transform_on)), ks, None, _state['impl'], _stream(x)))
+        ctx.save_for_backward(x, w7, m75, m53)
+        ctx.ks, ctx.transform_on = ks, transform_on
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w7, m75, m53 = ctx.saved_tensors
+        ks, transform_on = ctx.ks, ctx.transform_on
+        n, c, h, w = x.shape
+        kmax = w7.shape[-1]
+        p75, p53 = _transform_ptrs(m75, m53)
+        L = B.lib()
+        st = _stream(x)
+        tdy = B.t4(dy)
+        dx = dw7 = dm75 = dm53 = None
+        if ctx.needs_input_grad[0]:
+            dx = B.new_nhwc(n, c, h, w, dy.dtype, dy.device)
+            tdx = B.t4(dx)
+            B.check(L.ofa_dw_bwd_data(byref(tdy), byref(tdx), B.fptr(w7), kmax, p75, p53,
+                                      int(bool(transform_on)), ks, st))
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
+            dwa = torch.empty((c, ks * ks), dtype=torch.float32, device=x.device)
+            tx = B.t4(x)
+            B.check(L.ofa_dw_bwd_filter(byref(tx), byref(tdy), ks, dwa.data_ptr(), st))
+            dw7 = torch.zeros_like(w7)
+            use75 = transform_on and ks < kmax and m75 is not None
+            use53 = transform_on and ks < kmax and ks == 3 and m53 is not None
+            dm75 = torch.zeros_like(m75) if m75 is not None else None
+            dm53 = torch.zeros_like(m53) if m53 is not None else None
+            B.check(L.ofa_dw_active_filter_bwd(B.fptr(w7), kmax, p75, p53, int(bool(transform_on)), ks, c,
+                                               dwa.data_ptr(), dw7.data_ptr(),
+                                               dm75.data_ptr() if dm75 is not None else None,
+                                               dm53.data_ptr() if dm53 is not None else None, st))
+            # matrices that did not take part get no gradient (autograd of the reference leaves them None)
+            if not use75:
+                dm75 = None
+            if not use53:
+                dm53 = None
+        return dx, dw7, dm75, dm53, None, None
+
+
+def dw_conv(x, w7, m75, m53, ks, transform_on):
+    return DwConvFn.apply(x, w7, m75, m53, ks, transform_on)
+
+
+# =================================================================================================
+# dense conv with an in-place weight slice (a3, a4, a9, a14)
+# =================================================================================================
+
+def _conv_args(x, y, w, cin, cout, ks, store=B.STORE_PLAIN, epi=None, w_bf16=None, cin_pad=0, cout_pad=0):
+    a = B.OfaConvArgs()
+    a.x, a.y = B.t4(x), B.t4(y)
+    a.w = B.fptr(w) if w is not None else None
+    if w is not None:
+        so, si, sh, sw = w.stride()
+        a.w_so, a.w_si, a.w_sh, a.w_sw = so, si, sh, sw
+    a.w_bf16 = w_bf16.data_ptr() if w_bf16 is not None else None
+    a.cin_pad, a.cout_pad = cin_pad, cout_pad
+    a.cin, a.cout, a.ks, a.flip, a.store = cin, cout, ks, 0, store
+    if epi is not None:
+        a.epi = epi
+    return a
+
+
+def _conv_out(x, cout, store, dtype, nchw=False):
+    n, _, h, w = x.shape
+    if store == B.STORE_PIXELSHUFFLE2:
+        shape = (n, cout // 4, 2 * h, 2 * w)
+    elif store == B.STORE_PIXELUNSHUFFLE2:
+        shape = (n, cout * 4, h // 2, w // 2)
+    else:
+        shape = (n, cout, h, w)
+    if nchw:
+        return torch.empty(shape, dtype=dtype, device=x.device)
+    return torch.empty(shape, dtype=dtype, device=x.device, memory_format=torch.channels_last)
+
+
+class ConvFn(torch.autograd.Function):
+    """y = conv2d(x, w[:cout, :cin]), stride 1, same padding; the slice is addressed in place."""
+
+    @staticmethod
+    def forward(ctx, x, w, cin, cout, ks):
+        y = _conv_out(x, cout, B.STORE_PLAIN, x.dtype)
+        a = _conv_args(x, y, w, cin, cout, ks)
+        B.check(B.lib().ofa_conv_fwd(byref(a), B.IMPL_SIMT, _stream(x)))
+        ctx.save_for_backward(x, w)
+        ctx.dims = (cin, cout, ks)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        cin, cout, ks = ctx.dims
+        L = B.lib()
+        st = _stream(x)
+        so, si, sh, sw = w.stride()
+        tdy = B.t4(dy)
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            n, _, h, wd = x.shape
+            dx = B.new_nhwc(n, cin, h, wd, dy.dtype, dy.device)
+            tdx = B.t4(dx)
+            B.check(L.ofa_conv_bwd_data(byref(tdy), byref(tdx), B.fptr(w), so, si, sh, sw, cin, cout, ks, st))
+        if ctx.needs_input_grad[1]:
+            dw = torch.zeros_like(w)
+            tx = B.t4(x)
+            B.check(L.ofa_conv_bwd_weight(byref(tx), byref(tdy), dw.data_ptr(), so, si, sh, sw, cin, cout, ks, st))
+        return dx, dw, None, None, None
+
+
+def conv2d(x, w, cin, cout, ks):
+    return ConvFn.apply(x, w, cin, cout, ks)
+
+
+# =================================================================================================
+# BatchNorm (+ activation, + residual) on the active channel prefix (a5, a6, a8, a14)
+# =================================================================================================
+
+class BnActFn(torch.autograd.Function):
+    """y = act(BN(x)) [+ residual].  Training: batch statistics (biased var for normalisation,
+    unbiased for the running update, momentum update of the [:C] slice in place).  Eval: running
+    statistics.  gamma / beta / running_* are the FULL-width tensors; the first C entries are used."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, residual, training, momentum, eps, act):
+        n, c, h, w = x.shape
+        L = B.lib()
+        st = _stream(x)
+        tx = B.t4(x)
+        if training:
+            mean = torch.empty(c, dtype=torch.float32, device=x.device)
+            var = torch.empty(c, dtype=torch.float32, device=x.device)
+            B.check(L.ofa_bn_stats(byref(tx), mean.data_ptr(), var.data_ptr(), st))
+            if running_mean is not None and momentum is not None and momentum != 0.0:
+                B.check(L.ofa_bn_update_running(mean.data_ptr(), var.data_ptr(), n * h * w,
+                                                B.fptr(running_mean), B.fptr(running_var), float(momentum), c, st))
+        else:
+            mean, var = running_mean, running_var
+        y = B.new_nhwc(n, c, h, w, x.dtype, x.device)
+        ty = B.t4(y)
+        e, keep = B.epilogue(gamma, beta, mean, var, eps, act, residual)
+        B.check(L.ofa_affine_act(byref(tx), byref(ty), byref(e), B.STORE_PLAIN, st))
+        ctx.save_for_backward(x, gamma, beta, mean, var)
+        ctx.cfg = (training, eps, act, residual is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, beta, mean, var = ctx.saved_tensors
+        training, eps, act, has_res = ctx.cfg
+        n, c, h, w = x.shape
+        L = B.lib()
+        st = _stream(x)
+        tx, tdy = B.t4(x), B.t4(dy)
+        s0 = torch.empty(c, dtype=torch.float32, device=x.device)
+        s1 = torch.empty(c, dtype=torch.float32, device=x.device)
+        B.check(L.ofa_bn_bwd_reduce(byref(tx), byref(tdy), _null_or(gamma), _null_or(beta), B.fptr(mean),
+                                    B.fptr(var), eps, act, s0.data_ptr(), s1.data_ptr(), st))
+        dx = dgamma = dbeta = None
+        if ctx.needs_input_grad[0]:
+            dx = B.new_nhwc(n, c, h, w, dy.dtype, dy.device)
+            tdx = B.t4(dx)
+            B.check(L.ofa_bn_bwd_apply(byref(tx), byref(tdy), byref(tdx), _null_or(gamma), _null_or(beta),
+                                       B.fptr(mean), B.fptr(var), eps, act, int(training), s0.data_ptr(),
+                                       s1.data_ptr(), st))
+        if gamma is not None and ctx.needs_input_grad[1]:
+            dgamma = torch.zeros_like(gamma)
+            dgamma[:c] = s1
+        if beta is not None and ctx.needs_input_grad[2]:
+            dbeta = torch.zeros_like(beta)
+            dbeta[:c] = s0
+        dres = dy if (has_res and ctx.needs_input_grad[5]) else None
+        return dx, dgamma, dbeta, None, None, dres, None, None, None, None
+
+
+def bn_act(x, bn, C, act=B.ACT_NONE, residual=None, full_width=False):
+    """DynamicBatchNorm2d.bn_forward semantics (dynamic_op.py:148-167) for an nn.BatchNorm2d `bn`
+    on the first C channels.  `full_width` = the reference's `bn(x)` branch, which also bumps
+    num_batches_tracked through nn.BatchNorm2d.forward."""
+    training = bn.training or not bn.track_running_stats
+    momentum = 0.0
+    if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked += 1
+        if bn.momentum is None:
+            momentum = 1.0 / float(bn.num_batches_tracked)
+        else:
+            momentum = bn.momentum
+    return BnActFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, residual, training,
+                         momentum, bn.eps, act)
+
+
+# =================================================================================================
+# PixelShuffle(2) / PixelUnshuffle(2) as a stand-alone reorder (training path; a10, a11)
+# =================================================================================================
+
+class ReorderFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, store):
+        n, c, h, w = x.shape
+        y = _conv_out(x, c, store, x.dtype)
+        tx, ty = B.t4(x), B.t4(y)
+        B.check(B.lib().ofa_affine_act(byref(tx), byref(ty), None, store, _stream(x)))
+        ctx.store = store
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        inv = B.STORE_PIXELUNSHUFFLE2 if ctx.store == B.STORE_PIXELSHUFFLE2 else B.STORE_PIXELSHUFFLE2
+        n, c, h, w = dy.shape
+        dx = _conv_out(dy, c, inv, dy.dtype)
+        tdy, tdx = B.t4(dy), B.t4(dx)
+        B.check(B.lib().ofa_affine_act(byref(tdy), byref(tdx), None, inv, _stream(dy)))
+        return dx, None
+
+
+def pixel_shuffle2(x):
+    return ReorderFn.apply(x, B.STORE_PIXELSHUFFLE2)
+
+
+def pixel_unshuffle2(x):
+    return ReorderFn.apply(x, B.STORE_PIXELUNSHUFFLE2)
+
+
+# =================================================================================================
+# fused inference calls
+# =================================================================================================
+
+class PackedWeightCache:
+    """bf16 [tap][cout_pad][cin_pad] copy of an active weight slice — a derived cache owned by the
+    module, rebuilt whenever the fp32 master changes (optimizer step / load_state_dict / re-sort)."""
+
+    def __init__(self):
+        self._key = None
+        self._buf = None
+        self.cin_pad = self.cout_pad = 0
+
+    def get(self, w, cin, cout, ks, store):
+        key = (w.data_ptr(), w._version, tuple(w.shape), cin, cout, ks, store, str(w.device))
+        if key != self._key:
+            cin_pad = (cin + 63) // 64 * 64
+            cout_pad = (cout + 15) // 16 * 16
+            buf = torch.empty((ks * ks, cout_pad, cin_pad), dtype=torch.bfloat16, device=w.device)
+            so, si, sh, sw = w.stride()
+            B.check(B.lib().ofa_pack_weight_bf16(B.fptr(w), so, si, sh, sw, cin, cout, ks, cin_pad, cout_pad,
+                                                 store, buf.data_ptr(), _stream(w)))
+            self._key, self._buf, self.cin_pad, self.cout_pad = key, buf, cin_pad, cout_pad
+        return self._buf
+
+
+def _bn_epilogue(bn, act, residual):
+    if bn is None:
+        return B.epilogue(act=act, residual=residual)
+    return B.epilogue(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, act, residual)
+
+
+def conv_bn_act_infer(x, w, cin, cout, ks, bn=None, act=B.ACT_NONE, store=B.STORE_PLAIN, residual=None,
+                      cache=None, out_dtype=None, out_nchw=False):
+    """ConvLayer / DynamicPointConv2d(+BN+act) in inference: one kernel."""
+    dtype = out_dtype or _state['compute_dtype']
+    y = _conv_out(x, cout, store, dtype, nchw=out_nchw)
+    e, keep = _bn_epilogue(bn, act, residual)
+    w_bf16, cin_pad, cout_pad = None, 0, 0
+    impl = _state['impl']
+    if x.dtype == torch.bfloat16 and cin % 64 == 0 and cache is not None and impl != B.IMPL_SIMT:
+        w_bf16 = cache.get(w, cin, cout, ks, store)
+        cin_pad, cout_pad = cache.cin_pad, cache.cout_pad
+    elif impl == B.IMPL_FAST:
+        impl = B.IMPL_AUTO  # layers the tensor-core kernel does not cover (thin stem) use the CUDA-core one
+    a = _conv_args(x, y, w, cin, cout, ks, store, e, w_bf16, cin_pad, cout_pad)
+    B.check(B.lib().ofa_conv_fwd(byref(a), impl, _stream(x)))
+    return y
+
+
+def dw_bn_act_infer(x, w7, m75, m53, ks, transform_on, bn, act):
+    n, c, h, w = x.shape
+    y = B.new_nhwc(n, c, h, w, x.dtype, x.device)
+    e, keep = _bn_epilogue(bn, act, None)
+    p75, p53 = _transform_ptrs(m75, m53)
+    tx, ty = B.t4(x), B.t4(y)
+    B.check(B.lib().ofa_dw_fwd(byref(tx), byref(ty), B.fptr(w7), w7.shape[-1], p75, p53,
+                               int(bool(transform_on)), ks, byref(e), _state['impl'], _stream(x)))
+    return y
+
+
+def _bn_struct(bn):
+    return B.OfaBn(B.fptr(bn.weight), B.fptr(bn.bias), B.fptr(bn.running_mean), B.fptr(bn.running_var), bn.eps)
+
+
+def mbconv_infer(x, w_exp, w_dw, m75, m53, w_proj, cin, mid, cout, ks, transform_on, act, bn_exp, bn_dw,
+                 bn_proj, add_residual):
+    """Whole inference MBConv block (expand -> dw -> project [+x]) through ofa_mbconv_fwd; needs
+    NHWC-dense bf16 x.  Returns NHWC bf16."""
+    n, _, h, w = x.shape
+    y = B.new_nhwc(n, cout, h, w, torch.bfloat16, x.device)
+    L = B.lib()
+    ws_bytes = L.ofa_mbconv_workspace_bytes(n, h, w, cin, mid, cout)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+    a = B.OfaMBConvArgs()
+    a.x, a.y = B.t4(x), B.t4(y)
+    a.w_exp = B.fptr(w_exp)
+    a.w_exp_so, a.w_exp_si = w_exp.stride(0), w_exp.stride(1)
+    a.w_dw, a.kmax = B.fptr(w_dw), w_dw.shape[-1]
+    a.m75, a.m53 = _transform_ptrs(m75, m53)
+    a.transform_on = int(bool(transform_on))
+    a.w_proj = B.fptr(w_proj)
+    a.w_proj_so, a.w_proj_si = w_proj.stride(0), w_proj.stride(1)
+    a.cin, a.mid, a.cout, a.ks, a.act = cin, mid, cout, ks, act
+    a.bn_exp, a.bn_dw, a.bn_proj = _bn_struct(bn_exp), _bn_struct(bn_dw), _bn_struct(bn_proj)
+    a.add_residual = int(bool(add_residual))
+    a.ws, a.ws_bytes = ws.data_ptr(), ws_bytes
+    B.check(L.ofa_mbconv_fwd(byref(a), _state['impl'], _stream(x)))
+    return y
+
+
+def inference_mode_active(module):
+    """The fused single-kernel path is taken when nothing needs autograd and BN uses running stats."""
+    return (not module.training) and (not torch.is_grad_enabled())

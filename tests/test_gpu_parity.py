@@ -1,0 +1,431 @@
+"""Parity of the CUDA path (called through the C ABI of libofa_sr_b200.so) with the CPU oracle and
+with the fixtures produced by the unmodified reference.  Needs a B200: `pytest -m gpu`.
+
+Tolerances (BASELINE.json north_star):
+  fp32 path : max |err| <= 1e-3 * max|ref|              (we assert 1e-4 where the math is short)
+  bf16 path : per-op   max |err| <= 2^-7 * max|ref| (one bf16 rounding of the output + bf16 inputs)
+              per-net  PSNR(ours, target) within 0.01 dB of PSNR(reference, target), reference metric
+  subnet selection / channel indexing: bit-exact
+"""
+import ctypes
+import random
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import ofa_sr_oracle as O
+
+FULL = dict(ks_list=[3, 5, 7], expand_ratio_list=[3, 4, 6], depth_list=[2, 3, 4])
+
+
+@pytest.fixture(scope='module')
+def dev():
+    assert torch.cuda.is_available(), 'GPU tests need a CUDA device'
+    return torch.device('cuda:0')
+
+
+@pytest.fixture(autouse=True)
+def _reset_policy():
+    import ofa_b200
+    from ofa_b200 import backend as B
+    from ofa_b200.elastic_nn.modules.dynamic_op import DynamicSeparableConv2d
+    DynamicSeparableConv2d.KERNEL_TRANSFORM_MODE = 1
+    ofa_b200.set_compute_dtype(torch.bfloat16)
+    ofa_b200.set_impl(B.IMPL_AUTO)
+    yield
+    ofa_b200.set_compute_dtype(torch.bfloat16)
+    ofa_b200.set_impl(B.IMPL_AUTO)
+
+
+def relerr(a, b):
+    a = a.detach().float().cpu().double()
+    b = b.detach().float().cpu().double()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return float((a - b).abs().max() / max(1e-12, float(b.abs().max())))
+
+
+def bf16r(t):
+    return t.to(torch.bfloat16).float()
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    return torch.from_numpy((np.random.RandomState(seed).randn(*shape) * scale).astype(np.float32))
+
+
+def bn_params(C, seed, dev):
+    rs = np.random.RandomState(seed)
+    mk = lambda a: torch.from_numpy(a.astype(np.float32)).to(dev)
+    return dict(gamma=mk(rs.uniform(0.5, 1.5, C)), beta=mk(0.1 * rs.randn(C)), mean=mk(0.1 * rs.randn(C)),
+                var=mk(rs.uniform(0.5, 1.5, C)))
+
+
+def ref_bn(y, bn, C, eps=1e-5):
+    g, b, m, v = (bn[k][:C].cpu() for k in ('gamma', 'beta', 'mean', 'var'))
+    return (y - m.view(1, -1, 1, 1)) / torch.sqrt(v.view(1, -1, 1, 1) + eps) * g.view(1, -1, 1, 1) + b.view(1, -1, 1, 1)
+
+
+def dw_weights(seed, dev, C=384):
+    rs = np.random.RandomState(seed)
+    w7 = torch.from_numpy((rs.randn(C, 1, 7, 7) * 0.2).astype(np.float32))
+    m75 = torch.from_numpy((np.eye(25) + 0.05 * rs.randn(25, 25)).astype(np.float32))
+    m53 = torch.from_numpy((np.eye(9) + 0.05 * rs.randn(9, 9)).astype(np.float32))
+    return w7, m75, m53
+
+
+# =================================================================================================
+# (a1) active filter
+# =================================================================================================
+@pytest.mark.parametrize('ks', [3, 5, 7])
+@pytest.mark.parametrize('transform', [True, False])
+def test_active_filter(dev, ks, transform):
+    from ofa_b200 import functional as OF
+    w7, m75, m53 = dw_weights(1, dev)
+    ref = O.active_filter(w7, {'7to5_matrix': m75, '5to3_matrix': m53}, [3, 5, 7], 200, ks, transform)
+    got = OF.dw_active_filter(w7.to(dev), m75.to(dev), m53.to(dev), transform, ks, 200)
+    assert relerr(got, ref) < 1e-5
+
+
+# =================================================================================================
+# (a2) depthwise forward — CUDA-core path, every layout / dtype; TMA path, bf16 NHWC
+# =================================================================================================
+@pytest.mark.parametrize('ks', [3, 5, 7])
+@pytest.mark.parametrize('layout', ['nchw', 'nhwc'])
+@pytest.mark.parametrize('C', [40, 192])
+def test_dw_simt_fp32(dev, ks, layout, C):
+    from ofa_b200 import functional as OF, backend as B
+    import ofa_b200
+    ofa_b200.set_impl(B.IMPL_SIMT)
+    w7, m75, m53 = dw_weights(2, dev)
+    x = rnd(2, C, 13, 9, seed=3)
+    filt = O.active_filter(w7, {'7to5_matrix': m75, '5to3_matrix': m53}, [3, 5, 7], C, ks)
+    ref = O.dw_conv(x, filt)
+    xd = x.to(dev)
+    if layout == 'nhwc':
+        xd = xd.contiguous(memory_format=torch.channels_last)
+    got = OF.dw_conv(xd, w7.to(dev), m75.to(dev), m53.to(dev), ks, True)
+    assert relerr(got, ref) < 1e-5
+    # fused BN + ReLU6 epilogue
+    bn = bn_params(384, 4, dev)
+
+    class _BN:  # duck-typed nn.BatchNorm2d for the fused call
+        weight, bias, running_mean, running_var, eps = bn['gamma'], bn['beta'], bn['mean'], bn['var'], 1e-5
+    got2 = OF.dw_bn_act_infer(xd, w7.to(dev), m75.to(dev), m53.to(dev), ks, True, _BN, B.ACT_RELU6)
+    ref2 = torch.clamp(ref_bn(ref, bn, C), 0, 6)
+    assert relerr(got2, ref2) < 1e-5
+
+
+@pytest.mark.parametrize('ks', [3, 5, 7])
+@pytest.mark.parametrize('shape', [(1, 64, 8, 32), (2, 192, 19, 45), (1, 384, 40, 70)])
+def test_dw_fast_bf16(dev, ks, shape):
+    from ofa_b200 import functional as OF, backend as B
+    import ofa_b200
+    ofa_b200.set_impl(B.IMPL_FAST)
+    n, C, H, W = shape
+    w7, m75, m53 = dw_weights(5, dev)
+    x = bf16r(rnd(n, C, H, W, seed=6))
+    filt = O.active_filter(w7, {'7to5_matrix': m75, '5to3_matrix': m53}, [3, 5, 7], C, ks)
+    bn = bn_params(384, 7, dev)
+    ref = torch.clamp(ref_bn(O.dw_conv(x, filt), bn, C), 0, 6)
+
+    class _BN:
+        weight, bias, running_mean, running_var, eps = bn['gamma'], bn['beta'], bn['mean'], bn['var'], 1e-5
+    xd = x.to(dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    got = OF.dw_bn_act_infer(xd, w7.to(dev), m75.to(dev), m53.to(dev), ks, True, _BN, B.ACT_RELU6)
+    assert got.dtype == torch.bfloat16
+    assert relerr(got, ref) < 2 ** -7
+    # and the two implementations agree with each other to one bf16 ulp of the output range
+    ofa_b200.set_impl(B.IMPL_SIMT)
+    got_s = OF.dw_bn_act_infer(xd, w7.to(dev), m75.to(dev), m53.to(dev), ks, True, _BN, B.ACT_RELU6)
+    assert relerr(got, got_s) < 2 ** -7
+
+
+# =================================================================================================
+# (a3, a4, a9-a11) dense conv — CUDA-core path and tcgen05 path
+# =================================================================================================
+def _conv_case(dev, ks, cin, cout, cmax_in, cmax_out, store, with_res, shape, dtype, impl, seed=0):
+    from ofa_b200 import functional as OF, backend as B
+    import ofa_b200
+    ofa_b200.set_impl(impl)
+    n, H, W = shape
+    w = rnd(cmax_out, cmax_in, ks, ks, seed=seed, scale=(2.0 / (ks * ks * cout)) ** 0.5)
+    x = rnd(n, cin, H, W, seed=seed + 1)
+    if dtype == torch.bfloat16:
+        x, wq = bf16r(x), bf16r(w)
+    else:
+        wq = w
+    bn = bn_params(cmax_out, seed + 2, dev)
+    ref = ref_bn(O.sliced_conv(x, wq, cout), bn, cout)
+    act = B.ACT_RELU6 if store == B.STORE_PLAIN else B.ACT_NONE
+    if act == B.ACT_RELU6:
+        ref = torch.clamp(ref, 0, 6)
+    if store == B.STORE_PIXELSHUFFLE2:
+        ref = O.pixel_shuffle2(ref)
+    elif store == B.STORE_PIXELUNSHUFFLE2:
+        ref = O.pixel_unshuffle2(ref)
+    res = None
+    if with_res:
+        res = rnd(*ref.shape, seed=seed + 3)
+        if dtype == torch.bfloat16:
+            res = bf16r(res)
+        ref = ref + res
+        res = res.to(dev).to(dtype).contiguous(memory_format=torch.channels_last)
+
+    class _BN:
+        weight, bias, running_mean, running_var, eps = bn['gamma'], bn['beta'], bn['mean'], bn['var'], 1e-5
+    xd = x.to(dev).to(dtype).contiguous(memory_format=torch.channels_last)
+    cache = OF.PackedWeightCache()
+    got = OF.conv_bn_act_infer(xd, w.to(dev), cin, cout, ks, _BN, act, store, res, cache, out_dtype=dtype)
+    return got, ref
+
+
+@pytest.mark.parametrize('ks,cin,cout', [(1, 64, 192), (1, 200, 64), (3, 3, 16), (5, 64, 3), (5, 16, 40), (7, 8, 8)])
+@pytest.mark.parametrize('store', [0, 1, 2])
+def test_conv_simt_fp32(dev, ks, cin, cout, store):
+    from ofa_b200 import backend as B
+    if store == B.STORE_PIXELSHUFFLE2 and cout % 4:
+        pytest.skip('pixelshuffle needs cout % 4 == 0')
+    got, ref = _conv_case(dev, ks, cin, cout, cin + 8, cout + 8, store, store == 0, (2, 10, 14), torch.float32, B.IMPL_SIMT)
+    assert relerr(got, ref) < 1e-4
+
+
+@pytest.mark.parametrize('ks,cin,cout,store,res', [
+    (1, 64, 384, 0, False), (1, 64, 192, 0, False), (1, 64, 256, 0, False),       # expand
+    (1, 384, 64, 0, True), (1, 192, 64, 0, True), (1, 256, 64, 0, True),          # project + residual
+    (5, 64, 64, 0, True), (3, 64, 64, 0, False),                                  # tail convs + long skip
+    (5, 64, 256, 1, False), (3, 64, 256, 1, False),                               # conv + BN + PixelShuffle
+    (3, 64, 16, 2, False),                                                        # conv + BN + PixelUnshuffle
+    (5, 64, 3, 0, False), (3, 64, 3, 0, False), (7, 128, 48, 0, False),           # thin outputs, generic
+])
+@pytest.mark.parametrize('shape', [(1, 8, 16), (2, 22, 38)])
+def test_conv_tc_bf16(dev, ks, cin, cout, store, res, shape):
+    from ofa_b200 import backend as B
+    got, ref = _conv_case(dev, ks, cin, cout, max(cin, 64) if ks > 1 else cin + 64, cout if ks > 1 else cout + 64,
+                          store, res, shape, torch.bfloat16, B.IMPL_FAST, seed=11)
+    assert got.dtype == torch.bfloat16
+    assert relerr(got, ref) < 2 ** -7
+
+
+def test_conv_tc_fp32_nchw_output(dev):
+    """last layer of the nets: bf16 NHWC in, fp32 NCHW out (what the caller receives)."""
+    from ofa_b200 import functional as OF, backend as B
+    import ofa_b200
+    ofa_b200.set_impl(B.IMPL_FAST)
+    w = rnd(3, 64, 5, 5, seed=1, scale=0.05)
+    x = bf16r(rnd(2, 64, 20, 33, seed=2))
+    ref = O.sliced_conv(x, bf16r(w), 3)
+    cache = OF.PackedWeightCache()
+    xd = x.to(dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    got = OF.conv_bn_act_infer(xd, w.to(dev), 64, 3, 5, None, B.ACT_NONE, B.STORE_PLAIN, None, cache,
+                               out_dtype=torch.float32, out_nchw=True)
+    assert got.dtype == torch.float32 and got.is_contiguous()
+    assert relerr(got, ref) < 1e-4
+
+
+# =================================================================================================
+# module level: DynamicMBConvLayer against fixtures of the unmodified reference
+# =================================================================================================
+def _block_layer(dev):
+    from ofa_b200.elastic_nn.modules import DynamicMBConvLayer
+    spec = O.SuperNetSpec('s4', FULL['ks_list'], FULL['expand_ratio_list'], FULL['depth_list'], [1])
+    pre = 'blocks.0.mobile_inverted_conv.'
+    short = {k[len(pre):]: v for k, v in spec.param_shapes().items() if k.startswith(pre)}
+    layer = DynamicMBConvLayer([64], [64], kernel_size_list=[3, 5, 7], expand_ratio_list=[3, 4, 6], stride=1,
+                               act_func='relu6', use_se=False)
+    layer.load_state_dict(O.synth_state_dict(short, 21))
+    return layer.to(dev)
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+def test_block_eval_golden(dev, golden, mode):
+    import ofa_b200
+    arrays, _ = golden
+    layer = _block_layer(dev).eval()
+    ofa_b200.set_compute_dtype(torch.float32 if mode == 'fp32' else torch.bfloat16)
+    x = torch.from_numpy(arrays['block/x']).to(dev)
+    for ks in (3, 5, 7):
+        f = layer.depth_conv.conv.get_active_filter(384, ks)
+        assert relerr(f, torch.from_numpy(arrays['block/filter_k%d' % ks])) < 1e-5
+        for e in (3, 4, 6):
+            layer.active_kernel_size, layer.active_expand_ratio = ks, e
+            with torch.no_grad():
+                xin = x if mode == 'fp32' else x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+                y = layer(xin)
+            ref = torch.from_numpy(arrays['block/eval_k%d_e%d' % (ks, e)])
+            assert relerr(y, ref) < (1e-4 if mode == 'fp32' else 2e-2)
+            # secondary oracle: the static twin built by get_active_subnet computes the same thing
+            sub = layer.get_active_subnet(64).eval()
+            with torch.no_grad():
+                ys = sub(xin)
+            assert relerr(ys, y) < (1e-5 if mode == 'fp32' else 2e-2)
+
+
+@pytest.mark.parametrize('ks,e', [(3, 4), (5, 6), (7, 3)])
+def test_block_training_golden(dev, golden, ks, e):
+    """a5 (training BN on the slice, running-stat update) + a14 (every gradient of the block)."""
+    arrays, _ = golden
+    tag = 'block/train_k%d_e%d/' % (ks, e)
+    layer = _block_layer(dev).train()
+    layer.active_kernel_size, layer.active_expand_ratio = ks, e
+    x = torch.from_numpy(arrays['block/x']).to(dev).requires_grad_(True)
+    y = layer(x)
+    tgt = torch.from_numpy(arrays[tag + 'target']).to(dev)
+    loss = torch.nn.functional.mse_loss(y, tgt)
+    loss.backward()
+    assert relerr(y, torch.from_numpy(arrays[tag + 'y'])) < 1e-4
+    assert abs(loss.item() - float(arrays[tag + 'loss'])) < 1e-4 * abs(float(arrays[tag + 'loss']))
+    assert relerr(x.grad, torch.from_numpy(arrays[tag + 'dx'])) < 1e-3
+    for pname, p in layer.named_parameters():
+        ref = arrays[tag + 'grad/' + pname]
+        if ref.size == 0:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, pname
+        else:
+            assert p.grad is not None, pname
+            assert relerr(p.grad, torch.from_numpy(ref)) < 1e-3, pname
+    for bname, b in layer.named_buffers():
+        ref = torch.from_numpy(arrays[tag + 'buf/' + bname])
+        if b.dtype == torch.int64:
+            assert int(b) == int(ref), bname
+        else:
+            assert relerr(b, ref) < 1e-4, bname
+
+
+# =================================================================================================
+# network level: S4 / X4 against the reference fixtures — fp32 exact path and bf16 fast path
+# =================================================================================================
+def _build_net(kind, pd, wseed, dev):
+    from ofa_b200.elastic_nn.networks import OFAMobileNetS4, OFAMobileNetX4
+    cls = OFAMobileNetS4 if kind == 's4' else OFAMobileNetX4
+    net = cls(ks_list=[3, 5, 7], expand_ratio_list=[3, 4, 6], depth_list=[2, 3, 4], pixelshuffle_depth_list=list(pd))
+    spec = O.SuperNetSpec(kind, FULL['ks_list'], FULL['expand_ratio_list'], FULL['depth_list'], pd)
+    net.load_state_dict(O.synth_state_dict(spec.param_shapes(), wseed))
+    return net.to(dev).eval()
+
+
+def _apply(net, request):
+    if isinstance(request, str):
+        random.seed(int(request.split(':')[1]))
+        return net.sample_active_subnet()
+    net.set_active_subnet(**request)
+    return dict(request)
+
+
+@pytest.mark.parametrize('name', ['s4_ps1', 's4_ps12', 'x4_ps12'])
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+def test_net_forward_golden(dev, golden, name, mode):
+    import ofa_b200
+    arrays, book = golden
+    meta = book[name]
+    net = _build_net(meta['kind'], meta['pd'], meta['wseed'], dev)
+    ofa_b200.set_compute_dtype(torch.float32 if mode == 'fp32' else torch.bfloat16)
+    x = torch.from_numpy(arrays[name + '/x']).to(dev)
+    target = torch.from_numpy(np.random.RandomState(9).rand(*meta['subnets'][0]['out_shape']).astype(np.float32))
+    for i, sub in enumerate(meta['subnets']):
+        setting = _apply(net, sub['request'])
+        assert setting == sub['setting'] and list(net.runtime_depth) == sub['runtime_depth']
+        with torch.no_grad():
+            y = net(x)
+        ref = torch.from_numpy(arrays['%s/y%d' % (name, i)])
+        assert list(y.shape) == sub['out_shape'] and y.dtype == torch.float32
+        if mode == 'fp32':
+            assert relerr(y, ref) < 1e-3
+        else:
+            assert relerr(y, ref) < 5e-2
+            if list(target.shape) == list(ref.shape):
+                for b in range(ref.shape[0]):
+                    t = O.tensor_to_y_uint8(target[b])
+                    p_ref = O.psnr_uint8(O.tensor_to_y_uint8(ref[b]), t)
+                    p_got = O.psnr_uint8(O.tensor_to_y_uint8(y[b].cpu()), t)
+                    assert abs(p_ref - p_got) < 0.01, (p_ref, p_got)
+
+
+def test_random_subnet_sweep_vs_oracle(dev):
+    """C5: sampled subnets (seeded through Python `random`) — product vs oracle, fp32 path."""
+    import ofa_b200
+    ofa_b200.set_compute_dtype(torch.float32)
+    for kind, pd, shape in (('s4', [1, 2], (1, 3, 10, 12)), ('x4', [1, 2], (1, 3, 16, 8))):
+        net = _build_net(kind, pd, 41, dev)
+        spec = O.SuperNetSpec(kind, FULL['ks_list'], FULL['expand_ratio_list'], FULL['depth_list'], pd)
+        sd = O.synth_state_dict(spec.param_shapes(), 41)
+        x = torch.from_numpy(np.random.RandomState(3).rand(*shape).astype(np.float32))
+        for seed in range(12):
+            random.seed(seed)
+            a = net.sample_active_subnet()
+            random.seed(seed)
+            b = spec.sample_active_subnet()
+            assert a == b and list(net.runtime_depth) == spec.runtime_depth
+            with torch.no_grad():
+                y = net(x.to(dev))
+                ref = O.supernet_forward(x, sd, spec)
+            assert relerr(y, ref) < 1e-3, (kind, seed)
+
+
+def test_s4_training_step_golden(dev, golden):
+    """C3 shape of work: two sampled subnets, gradients accumulate, BN in batch-stat mode."""
+    arrays, book = golden
+    net = _build_net('s4', [1, 2], 31, dev).train()
+    lr_img = torch.from_numpy(arrays['train_s4/lr']).to(dev)
+    hr_img = torch.from_numpy(arrays['train_s4/hr']).to(dev)
+    net.zero_grad()
+    losses = []
+    for j in range(2):
+        random.seed(int('%d%.3d%.3d' % (5, j, 0)))
+        net.sample_active_subnet()
+        y = net(lr_img)
+        loss = torch.nn.functional.mse_loss(y, hr_img)
+        loss.backward()
+        losses.append(loss.item())
+    assert list(net.runtime_depth) == book['train_s4_runtime_depth']
+    np.testing.assert_allclose(losses, arrays['train_s4/losses'], rtol=1e-3)
+    for pname, p in net.named_parameters():
+        ref = book['train_s4_grad_norms'][pname]
+        if ref is None:
+            assert p.grad is None or float(p.grad.norm()) == 0.0, pname   # inactive block / matrix
+        else:
+            assert p.grad is not None, pname
+            assert abs(float(p.grad.norm()) - ref) <= 2e-3 * max(ref, 1e-6), (pname, float(p.grad.norm()), ref)
+    for key in ('dec_first_conv_block.conv.weight', 'blocks.0.mobile_inverted_conv.depth_conv.conv.conv.weight'):
+        g = dict(net.named_parameters())[key].grad
+        assert relerr(g, torch.from_numpy(arrays['train_s4/grad/' + key])) < 2e-3, key
+    rv = net.blocks[0].mobile_inverted_conv.depth_conv.bn.bn.running_var
+    assert relerr(rv, torch.from_numpy(arrays['train_s4/buf/blocks.0.mobile_inverted_conv.depth_conv.bn.bn.running_var'])) < 1e-4
+
+
+# =================================================================================================
+# edge cases and error behaviour
+# =================================================================================================
+def test_ragged_and_tiny_images(dev):
+    import ofa_b200
+    net = _build_net('s4', [1, 2], 51, dev)
+    spec = O.SuperNetSpec('s4', FULL['ks_list'], FULL['expand_ratio_list'], FULL['depth_list'], [1, 2])
+    sd = O.synth_state_dict(spec.param_shapes(), 51)
+    net.set_active_subnet(ks=7, e=6, d=4, pixel_d=2)
+    spec.set_active_subnet(ks=7, e=6, d=4, pixel_d=2)
+    for shape in ((1, 3, 1, 1), (1, 3, 5, 3), (3, 3, 9, 17)):
+        x = torch.from_numpy(np.random.RandomState(1).rand(*shape).astype(np.float32))
+        ref = O.supernet_forward(x, sd, spec)
+        for dt, tol in ((torch.float32, 1e-3), (torch.bfloat16, 5e-2)):
+            ofa_b200.set_compute_dtype(dt)
+            with torch.no_grad():
+                y = net(x.to(dev))
+            assert relerr(y, ref) < tol, (shape, dt)
+
+
+def test_no_cpu_path(dev):
+    from ofa_b200 import functional as OF
+    w7, m75, m53 = dw_weights(1, dev)
+    with pytest.raises(RuntimeError):
+        OF.dw_conv(torch.randn(1, 64, 4, 4), w7, m75, m53, 3, True)
+
+
+def test_bad_arguments_are_reported(dev):
+    from ofa_b200 import backend as B
+    x = torch.randn(1, 64, 4, 4, device=dev)
+    tx = B.t4(x)
+    w = torch.randn(64, 49, device=dev)
+    rc = B.lib().ofa_dw_fwd(ctypes.byref(tx), ctypes.byref(tx), w.data_ptr(), 7, None, None, 1, 4, None, 0, None)
+    assert rc == 1 and b'kernel size' in B.lib().ofa_last_error()
+    with pytest.raises(RuntimeError):
+        B.check(rc)
