@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""Benchmark of the elastic-MBConv SR hot path on B200 (contract: see the task brief / DESIGN.md §6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm (CUDA library)
+    python bench.py --impl reference [...]                         # the reference's CPU path (oracle port)
+
+Workload (BASELINE.json configs[1]): OFAMobileNetS4 (2 shuffle stages), max sub-network
+set_active_subnet(ks=7, e=6, d=4, pixel_d=2), 4x SR of one synthetic LR frame 960x540 -> 3840x2160
+per step per GPU (frames are independent units: no data-path collective; "weak" scaling).
+Metric: SR output Mpix/s, whole job (all ranks).  One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, 'ofa-for-super-resolution_b200'), os.path.join(ROOT, 'oracle')):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np
+import torch
+
+METRIC = 'SR output Mpix/s (4x, max subnet ks=7 e=6 d=4)'
+UNIT = 'Mpix/s'
+NET_CFG = dict(ks_list=[3, 5, 7], expand_ratio_list=[3, 4, 6], depth_list=[2, 3, 4], pixelshuffle_depth_list=[1, 2])
+SUBNET = dict(ks=7, e=6, d=4, pixel_d=2)
+WEIGHT_SEED = 1234
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--lr-h', type=int, default=540)
+    ap.add_argument('--lr-w', type=int, default=960)
+    ap.add_argument('--cpu-tile', type=int, default=160, help='LR tile edge of the bounded CPU-baseline sample')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {'hbm': d['hbm_gbs'], 'tensor_burst': d['bf16_tflops'], 'tensor_sustained': d['bf16_tflops_sustained'],
+                'source': 'MEASURED_PEAKS.json'}
+    return {'hbm': 6650.0, 'tensor_burst': 1590.0, 'tensor_sustained': 1400.0, 'source': 'fallback (B200_PROFILING.md)'}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(',')])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def finish(self):
+        self._stop.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower() == 'active'})
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': reasons, 'samples': len(sm)}
+
+
+# =====================================================================================================
+# reference arm / cpu baseline: the oracle port on the host cores
+# =====================================================================================================
+def cpu_forward_sample(tile, iters, warm):
+    import ofa_sr_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    spec = O.SuperNetSpec('s4', NET_CFG['ks_list'], NET_CFG['expand_ratio_list'], NET_CFG['depth_list'],
+                          NET_CFG['pixelshuffle_depth_list'])
+    sd = O.synth_state_dict(spec.param_shapes(), WEIGHT_SEED)
+    spec.set_active_subnet(**SUBNET)
+    x = torch.from_numpy(np.random.RandomState(0).rand(1, 3, tile, tile).astype(np.float32))
+    times = []
+    with torch.no_grad():
+        for i in range(warm + iters):
+            t0 = time.perf_counter()
+            y = O.supernet_forward(x, sd, spec)
+            t1 = time.perf_counter()
+            if i >= warm:
+                times.append(t1 - t0)
+    out_pix = y.shape[0] * y.shape[2] * y.shape[3]
+    return out_pix, times
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    out_pix, times = cpu_forward_sample(args.cpu_tile, args.steps, args.warmup)
+    ms = 1e3 * float(np.mean(times))
+    val = out_pix / 1e6 / (ms / 1e3)
+    sample = ('oracle port (torch CPU fp32, same ops the reference calls) of the S4 max-subnet forward on one '
+              '%dx%d LR tile -> %dx%d per step; Mpix/s is size-normalised' % (args.cpu_tile, args.cpu_tile,
+                                                                               4 * args.cpu_tile, 4 * args.cpu_tile))
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'S4 max subnet (ks=7,e=6,d=4,pixel_d=2) 4x SR forward, bounded tile sample on host cores'},
+        'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port', 'sample': sample},
+        'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line))
+
+
+# =====================================================================================================
+# our arm
+# =====================================================================================================
+def build_net(dev):
+    import ofa_sr_oracle as O   # only for the machine-independent synthetic weight recipe
+    from ofa_b200.elastic_nn.modules.dynamic_op import DynamicSeparableConv2d
+    DynamicSeparableConv2d.KERNEL_TRANSFORM_MODE = 1
+    from ofa_b200.elastic_nn.networks import OFAMobileNetS4
+    net = OFAMobileNetS4(**{k: list(v) for k, v in NET_CFG.items()})
+    spec = O.SuperNetSpec('s4', NET_CFG['ks_list'], NET_CFG['expand_ratio_list'], NET_CFG['depth_list'],
+                          NET_CFG['pixelshuffle_depth_list'])
+    net.load_state_dict(O.synth_state_dict(spec.param_shapes(), WEIGHT_SEED))
+    net.set_active_subnet(**SUBNET)
+    return net.to(dev).eval()
+
+
+def run_ours(args):
+    import ofa_b200
+    from ofa_b200 import backend as B, functional as OF
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    assert torch.cuda.is_available(), 'bench.py (our arm) needs a CUDA device: there is no CPU path'
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+    B.lib()  # fail loudly if the extension is missing
+    ofa_b200.set_compute_dtype(torch.bfloat16 if args.dtype == 'bf16' else torch.float32)
+    net = build_net(dev)
+    H, W = args.lr_h, args.lr_w
+    out_pix = 16 * H * W
+    g = torch.Generator(device='cpu').manual_seed(rank)
+    x_host = torch.rand(1, 3, H, W, generator=g).pin_memory()
+    x_dev = x_host.to(dev)
+    y_host = torch.empty(1, 3, 4 * H, 4 * W, dtype=torch.float32).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        with torch.no_grad():
+            for _ in range(warmup):
+                fn()
+            barrier()
+            evs = []
+            for _ in range(steps):
+                flush.zero_()                       # L2 flush between timed iterations (not timed)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn()
+                e1.record()
+                evs.append((e0, e1))
+            barrier()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def step_resident():
+        return net(x_dev)
+
+    def step_e2e():
+        xd = x_host.to(dev, non_blocking=True)
+        y = net(xd)
+        y_host.copy_(y, non_blocking=True)
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    B.launch_count_reset()
+    total_ms = timed(step_resident, args.steps, args.warmup)
+    launches = B.launch_count() * args.steps // (args.steps + args.warmup)
+    clocks = sampler.finish() if sampler else None
+    e2e_ms = timed(step_e2e, args.steps, args.warmup)
+
+    ms_per_step = total_ms / args.steps
+    value = world * out_pix / 1e6 / (ms_per_step / 1e3)
+    e2e_val = world * out_pix / 1e6 / (e2e_ms / args.steps / 1e3)
+
+    # ---- live per-kernel timing over the same workload: pick the dominant kernel, roofline it ---------
+    roof = None
+    if rank == 0:
+        rec = []
+        OF.set_profiler(rec)
+        with torch.no_grad():
+            for _ in range(3):
+                flush.zero_()
+                net(x_dev)
+        torch.cuda.synchronize()
+        OF.set_profiler(None)
+        agg = {}
+        for tag, flops, nbytes, e0, e1 in rec:
+            a = agg.setdefault(tag, [0.0, 0, flops, nbytes])
+            a[0] += e0.elapsed_time(e1)
+            a[1] += 1
+        total = sum(a[0] for a in agg.values())
+        pk = peaks()
+        table = []
+        for tag, (ms, cnt, flops, nbytes) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+            avg_s = ms / cnt / 1e3
+            table.append({'kernel': tag, 'share': ms / total, 'launches_per_step': cnt // 3, 'avg_ms': ms / cnt,
+                          'GBps': nbytes / avg_s / 1e9, 'TFLOPs': flops / avg_s / 1e12})
+        top = table[0]
+        tag = top['kernel']
+        _, _, flops, nbytes = agg[tag]
+        tensor_bound = tag.startswith('conv') and tag.endswith('tc') and (flops / nbytes) > 247
+        if tensor_bound:
+            roof = {'bound': 'tensor', 'achieved': top['TFLOPs'], 'peak': pk['tensor_sustained'], 'unit': 'TFLOP/s',
+                    'frac': top['TFLOPs'] / pk['tensor_sustained'], 'traffic': None}
+        else:
+            roof = {'bound': 'hbm', 'achieved': top['GBps'], 'peak': pk['hbm'], 'unit': 'GB/s',
+                    'frac': top['GBps'] / pk['hbm'], 'traffic': None}
+        roof.update({'kernel': tag, 'share_of_step': top['share'], 'peak_source': pk['source'], 'kernels': table[:8]})
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        pix, times = cpu_forward_sample(args.cpu_tile, 2, 1)
+        v = pix / 1e6 / float(np.mean(times))
+        cpu = {'value': v, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port',
+               'sample': 'oracle port, S4 max subnet, one %dx%d LR tile -> 4x, 1 warm-up + 2 timed forwards, '
+                         'torch CPU fp32 on all host threads' % (args.cpu_tile, args.cpu_tile)}
+
+    if rank == 0:
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': args.dtype, 'data': 'synthetic',
+            'config': {'workload': 'OFAMobileNetS4 max subnet (ks=7,e=6,d=4,pixel_d=2 -> 14 MBConv blocks), 4x SR '
+                                   'forward, LR %dx%d -> %dx%d, 1 frame per step per GPU, frames sharded across ranks '
+                                   '(no collective)' % (W, H, 4 * W, 4 * H),
+                       'l2': 'flushed between timed iterations (256 MiB write); per-step activations are also >> L2',
+                       'timing': 'CUDA events per step on the launch stream, summed, max over ranks'},
+            'e2e': {'value': e2e_val, 'unit': UNIT, 'h2d_bytes_per_step': x_host.numel() * 4,
+                    'd2h_bytes_per_step': y_host.numel() * 4},
+            'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    a = parse()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -39,6 +39,30 @@ def _stream(t):
     return B.stream_ptr(t.device)
 
 
+# ---- optional per-call CUDA-event profiler (bench.py's live roofline measurement) -----------------
+_profiler = None
+
+
+def set_profiler(records):
+    """`records` = a list that receives (tag, flops, algorithmic_bytes, start_event, end_event) for
+    every fused inference call, or None to switch profiling off.  Events are recorded on the current
+    stream, which is the stream the library launches on."""
+    global _profiler
+    _profiler = records
+
+
+def _call(tag, flops, nbytes, fn):
+    if _profiler is None:
+        return fn()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = fn()
+    e1.record()
+    _profiler.append((tag, flops, nbytes, e0, e1))
+    return out
+
+
 def _null_or(t):
     return B.fptr(t) if t is not None else None
 
@@ -341,7 +365,13 @@ def conv_bn_act_infer(x, w, cin, cout, ks, bn=None, act=B.ACT_NONE, store=B.STOR
     elif impl == B.IMPL_FAST:
         impl = B.IMPL_AUTO  # layers the tensor-core kernel does not cover (thin stem) use the CUDA-core one
     a = _conv_args(x, y, w, cin, cout, ks, store, e, w_bf16, cin_pad, cout_pad)
-    B.check(B.lib().ofa_conv_fwd(byref(a), impl, _stream(x)))
+    P = x.shape[0] * x.shape[2] * x.shape[3]
+    nbytes = P * (cin * x.element_size() + cout * y.element_size()) + \
+        (y.numel() * residual.element_size() if residual is not None else 0)
+    tag = 'conv%dx%d %d->%d%s %s' % (ks, ks, cin, cout, {0: '', 1: '+ps', 2: '+pus'}[store],
+                                     'tc' if w_bf16 is not None else 'simt')
+    _call(tag, 2.0 * P * ks * ks * cin * cout, nbytes,
+          lambda: B.check(B.lib().ofa_conv_fwd(byref(a), impl, _stream(x))))
     return y
 
 
@@ -351,9 +381,13 @@ def dw_bn_act_infer(x, w7, m75, m53, ks, transform_on, bn, act):
     e, keep = _bn_epilogue(bn, act, None)
     p75, p53 = _transform_ptrs(m75, m53)
     tx, ty = B.t4(x), B.t4(y)
-    B.check(B.lib().ofa_dw_fwd(byref(tx), byref(ty), B.fptr(w7), w7.shape[-1], p75, p53,
-                               int(bool(transform_on)), ks, byref(e), _state['impl'], _stream(x)))
+    _call('dw%dx%d C%d' % (ks, ks, c), 2.0 * n * h * w * c * ks * ks, 2 * n * h * w * c * x.element_size(),
+          lambda: B.check(B.lib().ofa_dw_fwd(byref(tx), byref(ty), B.fptr(w7), w7.shape[-1], p75, p53,
+                                             int(bool(transform_on)), ks, byref(e), _state['impl'], _stream(x))))
     return y
+
+
+_prof_caches = {}
 
 
 def _bn_struct(bn):
@@ -365,6 +399,14 @@ def mbconv_infer(x, w_exp, w_dw, m75, m53, w_proj, cin, mid, cout, ks, transform
     """Whole inference MBConv block (expand -> dw -> project [+x]) through ofa_mbconv_fwd; needs
     NHWC-dense bf16 x.  Returns NHWC bf16."""
     n, _, h, w = x.shape
+    if _profiler is not None:
+        # same kernels, issued one by one so each gets its own event pair
+        c1 = _prof_caches.setdefault((w_exp.data_ptr(), 0), PackedWeightCache())
+        c2 = _prof_caches.setdefault((w_proj.data_ptr(), 1), PackedWeightCache())
+        t = conv_bn_act_infer(x, w_exp, cin, mid, 1, bn_exp, act, cache=c1)
+        t = dw_bn_act_infer(t, w_dw, m75, m53, ks, transform_on, bn_dw, act)
+        return conv_bn_act_infer(t, w_proj, mid, cout, 1, bn_proj, B.ACT_NONE, residual=x if add_residual else None,
+                                 cache=c2)
     y = B.new_nhwc(n, cout, h, w, torch.bfloat16, x.device)
     L = B.lib()
     ws_bytes = L.ofa_mbconv_workspace_bytes(n, h, w, cin, mid, cout)
