@@ -321,7 +321,6 @@ def test_net_forward_golden(dev, golden, name, mode):
     net = _build_net(meta['kind'], meta['pd'], meta['wseed'], dev)
     ofa_b200.set_compute_dtype(torch.float32 if mode == 'fp32' else torch.bfloat16)
     x = torch.from_numpy(arrays[name + '/x']).to(dev)
-    target = torch.from_numpy(np.random.RandomState(9).rand(*meta['subnets'][0]['out_shape']).astype(np.float32))
     for i, sub in enumerate(meta['subnets']):
         setting = _apply(net, sub['request'])
         assert setting == sub['setting'] and list(net.runtime_depth) == sub['runtime_depth']
@@ -333,12 +332,27 @@ def test_net_forward_golden(dev, golden, name, mode):
             assert relerr(y, ref) < 1e-3
         else:
             assert relerr(y, ref) < 5e-2
-            if list(target.shape) == list(ref.shape):
-                for b in range(ref.shape[0]):
-                    t = O.tensor_to_y_uint8(target[b])
-                    p_ref = O.psnr_uint8(O.tensor_to_y_uint8(ref[b]), t)
-                    p_got = O.psnr_uint8(O.tensor_to_y_uint8(y[b].cpu()), t)
-                    assert abs(p_ref - p_got) < 0.01, (p_ref, p_got)
+            d = psnr_delta_db(ref, y.cpu())
+            assert d < 0.01, (name, i, d)
+
+
+def psnr_delta_db(ref, got, target_psnr_db=31.0):
+    """|PSNR(got, T) - PSNR(ref, T)| with the reference's metric (clamp -> uint8 -> BT.601 Y -> PSNR,
+    sr_run_manager.py:567-597) in an SR-like operating point: random-weight outputs have no meaningful
+    range, so both images go through the SAME affine map that puts the reference's 1..99 percentile on
+    [0.1, 0.9], and the target T is the mapped reference plus Gaussian noise at `target_psnr_db`
+    (31 dB = the reference README's 4x Set14 figure)."""
+    lo, hi = np.percentile(ref.numpy(), [1, 99])
+    a = 0.8 / max(hi - lo, 1e-6)
+    f = lambda t: (t - lo) * a + 0.1
+    sigma = 1.0 / (10 ** (target_psnr_db / 20.0))
+    worst = 0.0
+    for b in range(ref.shape[0]):
+        r, g = f(ref[b]), f(got[b])
+        noise = torch.from_numpy(np.random.RandomState(17 + b).randn(*r.shape).astype(np.float32)) * sigma
+        t = O.tensor_to_y_uint8(r + noise)
+        worst = max(worst, abs(O.psnr_uint8(O.tensor_to_y_uint8(r), t) - O.psnr_uint8(O.tensor_to_y_uint8(g), t)))
+    return worst
 
 
 def test_random_subnet_sweep_vs_oracle(dev):
