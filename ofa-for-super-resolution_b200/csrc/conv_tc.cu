@@ -1,16 +1,24 @@
 // Dense convolution (1x1 channel-sliced point convs and k x k ConvLayers) as an implicit GEMM on the
 // 5th-gen tensor cores:  D[pixel, cout] = sum_{tap, cin} X[pixel + tap, cin] * W[tap][cout][cin].
 //
-//   * activations NHWC bf16; a CTA tile is TH x TW = 8 x 16 = 128 pixels (the UMMA M dimension);
-//   * per K block (one filter tap x 64 input channels) TMA loads the shifted 8x16x64 activation box
-//     (zero fill outside the image = the conv padding) and the [BN x 64] weight box, both with the
-//     128-byte swizzle, into a STAGES-deep mbarrier ring;
-//   * one elected thread issues tcgen05.mma (M=128, N=BN, K=16) x 4 per K block, accumulating in TMEM;
-//     two accumulator stages let the epilogue of tile i overlap the main loop of tile i+1;
-//   * 4 epilogue warps read TMEM (tcgen05.ld), apply the folded BatchNorm scale/shift, the
-//     activation and the residual / long skip, and store plain, PixelShuffle(2) or
-//     PixelUnshuffle(2) layouts (bf16 NHWC vectorised, or any strided fp32 / bf16 view);
-//   * persistent: grid = #SMs, tiles strided over CTAs.
+//   * activations NHWC bf16.  A CTA owns a 16 x 16 pixel tile = two UMMA M-tiles of 16 rows x 8 cols
+//     (an M-tile's 8-row group = one image row of 8 pixels).
+//   * HALO REUSE: per 64-channel chunk the (16+k-1) x (16+k-1) x 64 activation halo arrives with ONE TMA
+//     load (128-byte swizzle; out-of-bounds zero fill = the conv's padding) and every filter tap is fed
+//     from it: the tap's operand is the same shared-memory tile addressed through a UMMA descriptor
+//     whose start address is shifted by (ky * halo_w + kx) rows and whose 8-row-group stride is the
+//     halo row pitch.  (The swizzle XOR is a function of the absolute smem address, so TMA's write
+//     pattern and tcgen05's read pattern agree for any 128-byte-aligned start: probed in
+//     csrc/experiments/umma_probe.cu.)  L2 -> SM activation traffic drops k*k-fold.
+//   * weights [tap][cout][cin] bf16: resident in shared memory for the whole persistent CTA when they
+//     fit (all 1x1 convs, thin outputs), else streamed per tap through an mbarrier ring shared by both
+//     M-tiles.
+//   * one elected thread issues tcgen05.mma (M=128, N=BN<=128, K=16); accumulators live in TMEM, two
+//     stages, so the epilogue of one (tile, N-split) overlaps the MMAs of the next.  When Cin = 64 the
+//     N-splits of a tile are looped INSIDE the CTA, re-using the resident halo.
+//   * 8 epilogue warps: tcgen05.ld -> folded BatchNorm scale/shift -> activation -> + residual / long
+//     skip -> plain, PixelShuffle(2) or PixelUnshuffle(2) store (vectorised bf16 NHWC, or any view).
+//   * persistent: grid = #SMs.
 #include "ofa_common.cuh"
 #include "kernels.h"
 #include "sm100_ptx.cuh"
@@ -43,29 +51,37 @@ int encode_tmap(CUtensorMap* out, CUtensorMapDataType dt, uint32_t rank, void* b
 
 namespace {
 
-constexpr int TH = 8, TW = 16;         // spatial tile = 128 pixels = UMMA M
-constexpr int BK = 64;                 // channels per K block (128 bytes of bf16 = one swizzle row)
-constexpr int A_BYTES = TH * TW * BK * 2;  // 16 KiB
-constexpr int NUM_THREADS = 192;       // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr int MT_ROWS = 16, MT_COLS = 8;   // one UMMA M-tile: 16 image rows x 8 pixels
+constexpr int MTX = 2;                     // M-tiles side by side -> CTA tile 16 x 16 pixels
+constexpr int TILE_H = MT_ROWS, TILE_W = MT_COLS * MTX;
+constexpr int BK = 64;                     // channels per K chunk (128 bytes = one swizzle row)
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int MAX_COUT = 512;
+constexpr int MAX_A_STAGES = 4, MAX_B_STAGES = 8;
+constexpr int B_RESIDENT_LIMIT = 64 * 1024;
 
 struct ConvTcParams {
-  int N, H, W;          // input (= conv resolution) extents
+  int N, H, W;
   int cin, cout, ks;
-  int BN;               // output channels per CTA tile (multiple of 16, <= 256)
-  int n_splits;         // cout_pad / BN
+  int kcs;               // cin / 64
+  int BN;                // accumulator columns per M-tile (multiple of 16, <= 128)
+  int n_splits;          // cout_pad / BN
+  int inner_splits;      // splits looped inside a work item (kcs == 1), else 1
+  int cout_pad;
   int tiles_h, tiles_w;
-  int stages;
-  int tmem_cols;        // power of two >= 2*BN
-  int store;
-  int act;
-  int vec_store;        // 1: y is channel-innermost bf16 and 16-channel groups are 32-byte aligned
+  int halo_w, halo_h;
+  int a_bytes;           // one halo block (one 64-channel chunk)
+  int a_stages, b_stages;
+  int b_resident;
+  int bres_rows;         // weight rows per TMA box when resident
+  int tmem_cols;
+  int store, act, vec_store;
   const float* gamma; const float* beta; const float* mean; const float* var; float eps;
   TV y;
   TV res;
 };
 
-// packed-row index o' of the weight -> original conv output channel o (see pack order below)
 __device__ __forceinline__ int packed_to_conv_channel(int op, int cout, int store) {
   if (store == OFA_STORE_PIXELSHUFFLE2) {
     int q = cout >> 2;
@@ -74,28 +90,87 @@ __device__ __forceinline__ int packed_to_conv_channel(int op, int cout, int stor
   return op;
 }
 
+// folded BN + activation + residual + store of 16 consecutive (packed-order) output channels of one pixel
+__device__ __forceinline__ void emit16(const ConvTcParams& p, const float* s_scale, const float* s_shift,
+                                       const uint32_t* v, int op0, int n, int h, int w) {
+  if (op0 >= p.cout) return;
+  float f[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+    f[i] = apply_act(fmaf(__uint_as_float(v[i]), s_scale[op0 + i], s_shift[op0 + i]), p.act);
+  int oc0, oh, ow;
+  if (p.store == OFA_STORE_PIXELSHUFFLE2) {
+    int q = p.cout >> 2;
+    int sub = op0 / q;  // a 16-group never straddles sub-pixels (q % 16 == 0)
+    oc0 = op0 - sub * q; oh = 2 * h + (sub >> 1); ow = 2 * w + (sub & 1);
+  } else if (p.store == OFA_STORE_PIXELUNSHUFFLE2) {
+    oc0 = 4 * op0 + 2 * (h & 1) + (w & 1); oh = h >> 1; ow = w >> 1;
+  } else {
+    oc0 = op0; oh = h; ow = w;
+  }
+  const int cstep = (p.store == OFA_STORE_PIXELUNSHUFFLE2) ? 4 : 1;
+  const bool full16 = op0 + 16 <= p.cout;
+  if (p.vec_store && full16 && cstep == 1) {
+    const long long o = p.y.off(n, oc0, oh, ow);
+    if (p.res.ptr) {
+      const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.res.ptr) +
+                                                       p.res.off(n, oc0, oh, ow));
+      uint4 r0 = rp[0], r1 = rp[1];
+      const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        f[2 * i] += __uint_as_float(rr[i] << 16);
+        f[2 * i + 1] += __uint_as_float(rr[i] & 0xffff0000u);
+      }
+    }
+    uint32_t pk[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      __nv_bfloat162 b2 = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+      pk[i] = *reinterpret_cast<uint32_t*>(&b2);
+    }
+    uint4* yp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y.ptr) + o);
+    yp[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    yp[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      if (op0 + i < p.cout) {
+        int oc = oc0 + i * cstep;
+        float val = f[i];
+        if (p.res.ptr) val += p.res.ld(p.res.off(n, oc, oh, ow));
+        p.y.st(p.y.off(n, oc, oh, ow), val);
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                const ConvTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [stages x A][stages x B][scale MAX_COUT][shift MAX_COUT][barriers][tmem ptr]
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int taps = p.ks * p.ks;
   const int B_BYTES = p.BN * BK * 2;
+  const int a_stride = (p.a_bytes + 1023) & ~1023;
   uint8_t* sA = smem;
-  uint8_t* sB = smem + (size_t)p.stages * A_BYTES;
-  float* s_scale = reinterpret_cast<float*>(sB + (size_t)p.stages * B_BYTES);
+  uint8_t* sB = sA + (size_t)p.a_stages * a_stride;
+  const size_t b_total = p.b_resident ? (size_t)taps * p.kcs * p.cout_pad * 128 : (size_t)p.b_stages * B_BYTES;
+  float* s_scale = reinterpret_cast<float*>(sB + b_total);
   float* s_shift = s_scale + MAX_COUT;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_shift + MAX_COUT);
-  uint64_t* empty_bar = full_bar + 8;
-  uint64_t* tfull_bar = empty_bar + 8;
-  uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(s_shift + MAX_COUT);
+  uint64_t* a_empty = a_full + MAX_A_STAGES;
+  uint64_t* b_full = a_empty + MAX_A_STAGES;
+  uint64_t* b_empty = b_full + MAX_B_STAGES;
+  uint64_t* tfull = b_empty + MAX_B_STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* bres_bar = tempty + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bres_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // folded BN for all (packed-order) output channels of this layer
-  for (int op = threadIdx.x; op < p.n_splits * p.BN; op += NUM_THREADS) {
+  for (int op = threadIdx.x; op < p.cout_pad; op += NUM_THREADS) {
     float sc = 0.f, sh = 0.f;
     if (op < p.cout) {
       int o = packed_to_conv_channel(op, p.cout, p.store);
@@ -114,14 +189,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     ptx::prefetch_tmap(&tmap_w);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < p.stages; ++s) {
-      ptx::mbar_init(&full_bar[s], 1);
-      ptx::mbar_init(&empty_bar[s], 1);
-    }
-    for (int a = 0; a < 2; ++a) {
-      ptx::mbar_init(&tfull_bar[a], 1);
-      ptx::mbar_init(&tempty_bar[a], 4);
-    }
+    for (int s = 0; s < MAX_A_STAGES; ++s) { ptx::mbar_init(&a_full[s], 1); ptx::mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < MAX_B_STAGES; ++s) { ptx::mbar_init(&b_full[s], 1); ptx::mbar_init(&b_empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull[a], 1); ptx::mbar_init(&tempty[a], NUM_EPI_WARPS); }
+    ptx::mbar_init(bres_bar, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
@@ -134,32 +205,48 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   const uint32_t tmem_base = *tmem_ptr;
 
   const int tiles_per_img = p.tiles_h * p.tiles_w;
-  const int num_tiles = p.N * tiles_per_img * p.n_splits;
-  const int taps = p.ks * p.ks;
-  const int kcs = p.cin / BK;
-  const int num_k = taps * kcs;
+  const int outer_splits = p.n_splits / p.inner_splits;
+  const int num_work = p.N * tiles_per_img * outer_splits;
   const int R = p.ks / 2;
+  const int acc_cols = MTX * p.BN;   // TMEM columns of one accumulator stage
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        int split = t % p.n_splits;
-        int sp = t / p.n_splits;
-        int n = sp / tiles_per_img;
-        int r = sp - n * tiles_per_img;
-        int h0 = (r / p.tiles_w) * TH, w0 = (r % p.tiles_w) * TW;
-        for (int kb = 0; kb < num_k; ++kb) {
-          int tap = kb / kcs, kc = kb - tap * kcs;
-          int ky = tap / p.ks, kx = tap - ky * p.ks;
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(A_BYTES + B_BYTES));
-          ptx::tma_load_4d(sA + (size_t)stage * A_BYTES, &tmap_x, &full_bar[stage], kc * BK, w0 + kx - R,
-                           h0 + ky - R, n);
-          ptx::tma_load_3d(sB + (size_t)stage * B_BYTES, &tmap_w, &full_bar[stage], kc * BK, split * p.BN, tap);
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      if (p.b_resident) {
+        ptx::mbar_arrive_expect_tx(bres_bar, (uint32_t)(taps * p.kcs * p.cout_pad * 128));
+        for (int tk = 0; tk < taps * p.kcs; ++tk) {
+          int tap = tk / p.kcs, kc = tk - tap * p.kcs;
+          for (int r0 = 0; r0 < p.cout_pad; r0 += p.bres_rows)   // box rows divide cout_pad exactly
+            ptx::tma_load_3d(sB + ((size_t)tk * p.cout_pad + r0) * 128, &tmap_w, bres_bar, kc * BK, r0, tap);
+        }
+      }
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      for (int wi = blockIdx.x; wi < num_work; wi += gridDim.x) {
+        const int split0 = wi % outer_splits;
+        const int sp = wi / outer_splits;
+        const int n = sp / tiles_per_img;
+        const int r = sp - n * tiles_per_img;
+        const int h0 = (r / p.tiles_w) * TILE_H, w0 = (r % p.tiles_w) * TILE_W;
+        for (int s = 0; s < p.inner_splits; ++s) {
+          for (int kc = 0; kc < p.kcs; ++kc) {
+            if (s == 0) {
+              ptx::mbar_wait(&a_empty[as], aph ^ 1);
+              ptx::mbar_arrive_expect_tx(&a_full[as], (uint32_t)p.a_bytes);
+              ptx::tma_load_4d(sA + (size_t)as * a_stride, &tmap_x, &a_full[as], kc * BK, w0 - R, h0 - R, n);
+              if (++as == p.a_stages) { as = 0; aph ^= 1; }
+            }
+            if (!p.b_resident) {
+              const int row0 = (split0 * p.inner_splits + s) * p.BN;
+              for (int tap = 0; tap < taps; ++tap) {
+                ptx::mbar_wait(&b_empty[bs], bph ^ 1);
+                ptx::mbar_arrive_expect_tx(&b_full[bs], (uint32_t)B_BYTES);
+                ptx::tma_load_3d(sB + (size_t)bs * B_BYTES, &tmap_w, &b_full[bs], kc * BK, row0, tap);
+                if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
+              }
+            }
+          }
         }
       }
     }
@@ -167,109 +254,96 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc = ptx::umma_idesc_bf16(128, p.BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-        ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
-        for (int kb = 0; kb < num_k; ++kb) {
-          ptx::mbar_wait(&full_bar[stage], phase);
+      const uint32_t sbo_a = (uint32_t)p.halo_w * 128;
+      int as = 0, bs = 0, acc = 0;
+      uint32_t aph = 0, bph = 0, accph = 0;
+      if (p.b_resident) ptx::mbar_wait(bres_bar, 0);
+      for (int wi = blockIdx.x; wi < num_work; wi += gridDim.x) {
+        const int split0 = wi % outer_splits;
+        int as_item = as;           // first A stage of this work item
+        uint32_t aph_item = aph;
+        for (int s = 0; s < p.inner_splits; ++s) {
+          ptx::mbar_wait(&tempty[acc], accph ^ 1);
           ptx::tc_fence_after();
-          const uint64_t da = ptx::umma_desc_sw128(ptx::smem_u32(sA + (size_t)stage * A_BYTES), 1024);
-          const uint64_t db = ptx::umma_desc_sw128(ptx::smem_u32(sB + (size_t)stage * B_BYTES), 1024);
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_cols);
+          int a_cur = as_item;
+          uint32_t a_cur_ph = aph_item;
+          const int row0 = (split0 * p.inner_splits + s) * p.BN;
+          for (int kc = 0; kc < p.kcs; ++kc) {
+            if (s == 0) ptx::mbar_wait(&a_full[a_cur], a_cur_ph);
+            ptx::tc_fence_after();
+            const uint32_t a_base = ptx::smem_u32(sA + (size_t)a_cur * a_stride);
+            for (int tap = 0; tap < p.ks * p.ks; ++tap) {
+              const int ky = tap / p.ks, kx = tap - ky * p.ks;
+              uint32_t b_addr;
+              if (p.b_resident) {
+                b_addr = ptx::smem_u32(sB) + (uint32_t)(((tap * p.kcs + kc) * p.cout_pad + row0) * 128);
+              } else {
+                ptx::mbar_wait(&b_full[bs], bph);
+                ptx::tc_fence_after();
+                b_addr = ptx::smem_u32(sB + (size_t)bs * B_BYTES);
+              }
+              const uint64_t db = ptx::umma_desc_sw128(b_addr, 1024);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row
-            ptx::umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+              for (int m = 0; m < MTX; ++m) {
+                const uint32_t a_addr = a_base + (uint32_t)((ky * p.halo_w + kx + m * MT_COLS) * 128);
+                const uint64_t da = ptx::umma_desc_sw128(a_addr, sbo_a);
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k)
+                  ptx::umma_bf16(d_tmem + (uint32_t)(m * p.BN), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                                 (kc | tap | k) ? 1u : 0u);
+              }
+              if (!p.b_resident) {
+                ptx::umma_commit(&b_empty[bs]);
+                if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
+              }
+            }
+            if (s == p.inner_splits - 1) ptx::umma_commit(&a_empty[a_cur]);
+            if (++a_cur == p.a_stages) { a_cur = 0; a_cur_ph ^= 1; }
           }
-          ptx::umma_commit(&empty_bar[stage]);
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          if (s == p.inner_splits - 1) { as = a_cur; aph = a_cur_ph; }
+          ptx::umma_commit(&tfull[acc]);
+          if (++acc == 2) { acc = 0; accph ^= 1; }
         }
-        ptx::umma_commit(&tfull_bar[acc]);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int quarter = warp & 3;              // TMEM lane quarter this warp may read
-    const int row = quarter * 32 + lane;       // pixel index inside the tile
+    // ===================== epilogue (warps 2..9) =====================
+    const int ew = warp - 2;
+    const int quarter = warp & 3;               // TMEM lane quarter this warp may read
+    const int m = ew >> 2;                      // M-tile handled by this warp group (MTX == 2)
+    const int row = quarter * 32 + lane;        // row of the M-tile = pixel (row / 8, row % 8)
     int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      int split = t % p.n_splits;
-      int sp = t / p.n_splits;
-      int n = sp / tiles_per_img;
-      int r = sp - n * tiles_per_img;
-      int h = (r / p.tiles_w) * TH + row / TW, w = (r % p.tiles_w) * TW + row % TW;
+    uint32_t accph = 0;
+    for (int wi = blockIdx.x; wi < num_work; wi += gridDim.x) {
+      const int split0 = wi % outer_splits;
+      const int sp = wi / outer_splits;
+      const int n = sp / tiles_per_img;
+      const int r = sp - n * tiles_per_img;
+      const int h = (r / p.tiles_w) * TILE_H + row / MT_COLS;
+      const int w = (r % p.tiles_w) * TILE_W + m * MT_COLS + row % MT_COLS;
       const bool pix_ok = h < p.H && w < p.W;
-      ptx::mbar_wait(&tfull_bar[acc], acc_phase);
-      ptx::tc_fence_after();
-      const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.BN);
-      for (int j = 0; j < p.BN; j += 16) {
-        uint32_t v[16];
-        ptx::tmem_ld16(t_addr + (uint32_t)j, v);
-        ptx::tmem_ld_wait();
-        const int op0 = split * p.BN + j;  // packed-order channel of v[0]
-        if (pix_ok && op0 < p.cout) {
-          float f[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            f[i] = apply_act(fmaf(__uint_as_float(v[i]), s_scale[op0 + i], s_shift[op0 + i]), p.act);
-          // packed channel op -> stored (channel, h, w)
-          int oc0, oh, ow;
-          if (p.store == OFA_STORE_PIXELSHUFFLE2) {
-            int q = p.cout >> 2;
-            int s = op0 / q;  // sub-pixel; a 16-group never straddles sub-pixels (q % 16 == 0)
-            oc0 = op0 - s * q; oh = 2 * h + (s >> 1); ow = 2 * w + (s & 1);
-          } else if (p.store == OFA_STORE_PIXELUNSHUFFLE2) {
-            oc0 = 4 * op0 + 2 * (h & 1) + (w & 1); oh = h >> 1; ow = w >> 1;
-          } else {
-            oc0 = op0; oh = h; ow = w;
-          }
-          const int cstep = (p.store == OFA_STORE_PIXELUNSHUFFLE2) ? 4 : 1;
-          const bool full16 = op0 + 16 <= p.cout;
-          if (p.vec_store && full16 && cstep == 1) {
-            const long long o = p.y.off(n, oc0, oh, ow);
-            if (p.res.ptr) {
-              const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.res.ptr) +
-                                                               p.res.off(n, oc0, oh, ow));
-              uint4 r0 = rp[0], r1 = rp[1];
-              const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                f[2 * i] += __uint_as_float(rr[i] << 16);
-                f[2 * i + 1] += __uint_as_float(rr[i] & 0xffff0000u);
-              }
-            }
-            uint32_t pk[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              __nv_bfloat162 b2 = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-              pk[i] = *reinterpret_cast<uint32_t*>(&b2);
-            }
-            uint4* yp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y.ptr) + o);
-            yp[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            yp[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              if (op0 + i < p.cout) {
-                int oc = oc0 + i * cstep;
-                float val = f[i];
-                if (p.res.ptr) val += p.res.ld(p.res.off(n, oc, oh, ow));
-                p.y.st(p.y.off(n, oc, oh, ow), val);
-              }
-            }
+      for (int s = 0; s < p.inner_splits; ++s) {
+        const int col0 = (split0 * p.inner_splits + s) * p.BN;
+        ptx::mbar_wait(&tfull[acc], accph);
+        ptx::tc_fence_after();
+        const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * acc_cols + m * p.BN);
+        for (int j = 0; j < p.BN; j += 32) {
+          uint32_t v[32];
+          const bool two = j + 16 < p.BN;
+          ptx::tmem_ld16(t_addr + (uint32_t)j, v);
+          if (two) ptx::tmem_ld16(t_addr + (uint32_t)(j + 16), v + 16);
+          ptx::tmem_ld_wait();
+          if (pix_ok) {
+            emit16(p, s_scale, s_shift, v, col0 + j, n, h, w);
+            if (two) emit16(p, s_scale, s_shift, v + 16, col0 + j + 16, n, h, w);
           }
         }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
+        if (++acc == 2) { acc = 0; accph ^= 1; }
       }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
@@ -281,13 +355,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   }
 }
 
-int pick_bn(int cout) {
-  int cp = (cout + 15) / 16 * 16;
-  if (cp <= 256) return cp;
-  // split N over CTAs: largest divisor-friendly tile
-  if (cp % 192 == 0) return 192;
-  if (cp % 128 == 0) return 128;
-  if (cp % 256 == 0) return 256;
+// accumulator width per M-tile: largest multiple of 16 that is <= 128 and divides cout_pad
+int pick_bn(int cout_pad) {
+  for (int bn = 128; bn >= 16; bn -= 16)
+    if (cout_pad % bn == 0) return bn;
   return 0;
 }
 
@@ -299,11 +370,8 @@ bool conv_tc_supported(const OfaConvArgs* a) {
   if (a->x.dtype != OFA_BF16 || !is_nhwc_dense(&a->x)) return false;
   if ((reinterpret_cast<uintptr_t>(a->x.ptr) & 15) || (reinterpret_cast<uintptr_t>(a->w_bf16) & 15)) return false;
   if (a->cin % BK != 0 || a->cin_pad != a->cin) return false;
-  if (a->ks > 7) return false;
-  int bn = pick_bn(a->cout);
-  if (bn == 0) return false;
-  int cp = (a->cout + 15) / 16 * 16;
-  if (a->cout_pad < cp || a->cout_pad % bn != 0 || a->cout_pad > MAX_COUT) return false;
+  if (a->ks > 7 || !(a->ks & 1)) return false;
+  if (a->cout_pad % 16 != 0 || a->cout_pad < a->cout || a->cout_pad > MAX_COUT) return false;
   if (a->store == OFA_STORE_PIXELSHUFFLE2 && (a->cout % 64 != 0)) return false;
   if (a->x.n <= 0 || a->x.h <= 0 || a->x.w <= 0) return false;
   return true;
@@ -314,27 +382,51 @@ int launch_conv_tc(const OfaConvArgs* a, cudaStream_t st) {
   memset(&p, 0, sizeof(p));
   p.N = a->x.n; p.H = a->x.h; p.W = a->x.w;
   p.cin = a->cin; p.cout = a->cout; p.ks = a->ks;
-  p.BN = pick_bn(a->cout);
+  p.kcs = a->cin / BK;
+  p.cout_pad = a->cout_pad;
+  p.BN = pick_bn(a->cout_pad);
   p.n_splits = a->cout_pad / p.BN;
-  p.tiles_h = (p.H + TH - 1) / TH;
-  p.tiles_w = (p.W + TW - 1) / TW;
+  p.inner_splits = (p.kcs == 1) ? p.n_splits : 1;
+  p.tiles_h = (p.H + TILE_H - 1) / TILE_H;
+  p.tiles_w = (p.W + TILE_W - 1) / TILE_W;
+  p.halo_w = TILE_W + p.ks - 1;
+  p.halo_h = TILE_H + p.ks - 1;
+  p.a_bytes = p.halo_w * p.halo_h * 128;
   p.store = a->store;
   p.act = a->epi.act;
   p.gamma = a->epi.gamma; p.beta = a->epi.beta; p.mean = a->epi.mean; p.var = a->epi.var; p.eps = a->epi.eps;
   p.y = make_tv(&a->y);
   p.res = a->epi.residual ? make_tv(a->epi.residual) : null_tv();
   int cols = 32;
-  while (cols < 2 * p.BN) cols <<= 1;
+  while (cols < 2 * MTX * p.BN) cols <<= 1;
   p.tmem_cols = cols;
-  const int b_bytes = p.BN * BK * 2;
-  const int fixed = 1024 /*align slack*/ + 2 * MAX_COUT * 4 + 256;
-  int stages = (227 * 1024 - fixed) / (A_BYTES + b_bytes);
-  if (stages > 8) stages = 8;
-  if (stages < 2) return fail(OFA_ERR_UNSUPPORTED, "conv_tc: tile does not fit shared memory");
-  p.stages = stages;
-  const size_t smem = (size_t)fixed + (size_t)stages * (A_BYTES + b_bytes);
 
-  // vectorised bf16 store: channel-innermost y (and residual), 16-channel groups 32-byte aligned
+  const int taps = p.ks * p.ks;
+  const int b_bytes = p.BN * BK * 2;
+  const long long b_all = (long long)taps * p.kcs * p.cout_pad * 128;
+  p.b_resident = b_all <= B_RESIDENT_LIMIT ? 1 : 0;
+  const int a_stride = (p.a_bytes + 1023) & ~1023;
+  const int fixed = 1024 /*align slack*/ + 2 * MAX_COUT * 4 + 512;
+  const int budget = 227 * 1024 - fixed;
+  if (p.b_resident) {
+    p.b_stages = 0;
+    int as = (int)((budget - b_all) / a_stride);
+    if (as > MAX_A_STAGES) as = MAX_A_STAGES;
+    if (as < 1) return fail(OFA_ERR_UNSUPPORTED, "conv_tc: halo tile does not fit shared memory");
+    p.a_stages = as;
+  } else {
+    // at least 2 halo stages (prefetch the next tile), the rest to the weight ring
+    int as = (p.kcs > 1) ? 3 : 2;
+    int bs = (budget - as * a_stride) / b_bytes;
+    if (bs > MAX_B_STAGES) bs = MAX_B_STAGES;
+    if (bs < 2) { as = 1; bs = (budget - as * a_stride) / b_bytes; if (bs > MAX_B_STAGES) bs = MAX_B_STAGES; }
+    if (bs < 2) return fail(OFA_ERR_UNSUPPORTED, "conv_tc: tile does not fit shared memory");
+    p.a_stages = as;
+    p.b_stages = bs;
+  }
+  const size_t smem = (size_t)fixed + (size_t)p.a_stages * a_stride +
+                      (p.b_resident ? (size_t)b_all : (size_t)p.b_stages * b_bytes);
+
   bool vec = a->y.dtype == OFA_BF16 && a->y.sc == 1 && (reinterpret_cast<uintptr_t>(a->y.ptr) & 15) == 0 &&
              a->y.sw % 8 == 0 && a->y.sh % 8 == 0 && a->y.sn % 8 == 0 && a->store != OFA_STORE_PIXELUNSHUFFLE2;
   if (a->epi.residual) {
@@ -348,27 +440,25 @@ int launch_conv_tc(const OfaConvArgs* a, cudaStream_t st) {
   {
     uint64_t dims[4] = {(uint64_t)p.cin, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.N};
     uint64_t strides[3] = {(uint64_t)p.cin * 2, (uint64_t)p.W * p.cin * 2, (uint64_t)p.H * p.W * p.cin * 2};
-    uint32_t box[4] = {BK, TW, TH, 1};
+    uint32_t box[4] = {BK, (uint32_t)p.halo_w, (uint32_t)p.halo_h, 1};
     int rc = encode_tmap(&tx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a->x.ptr, dims, strides, box,
                          CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
   {
-    uint64_t dims[3] = {(uint64_t)a->cin_pad, (uint64_t)a->cout_pad, (uint64_t)(a->ks * a->ks)};
+    uint64_t dims[3] = {(uint64_t)a->cin_pad, (uint64_t)a->cout_pad, (uint64_t)taps};
     uint64_t strides[2] = {(uint64_t)a->cin_pad * 2, (uint64_t)a->cin_pad * a->cout_pad * 2};
-    uint32_t box[3] = {BK, (uint32_t)p.BN, 1};
+    p.bres_rows = a->cout_pad <= 256 ? a->cout_pad : p.BN;
+    uint32_t rows = p.b_resident ? (uint32_t)p.bres_rows : (uint32_t)p.BN;
+    uint32_t box[3] = {BK, rows, 1};
     int rc = encode_tmap(&tw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(a->w_bf16), dims, strides, box,
                          CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
-  static thread_local size_t smem_set = 0;
-  if (smem > smem_set) {
-    OFA_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    smem_set = 227 * 1024;
-  }
-  const int num_tiles = p.N * p.tiles_h * p.tiles_w * p.n_splits;
+  OFA_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  const int num_work = p.N * p.tiles_h * p.tiles_w * (p.n_splits / p.inner_splits);
   int grid = sm_count();
-  if (grid > num_tiles) grid = num_tiles;
+  if (grid > num_work) grid = num_work;
   conv_tc_kernel<<<grid, NUM_THREADS, smem, st>>>(tx, tw, p);
   return check_launch("conv_tc_kernel");
 }

@@ -125,13 +125,16 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
          | ((uint32_t)(M >> 4) << 24);   // m_dim
 }
 // shared-memory matrix descriptor, K-major, 128-byte swizzle, rows of exactly 128 bytes:
-// 8-row groups are 1024 bytes apart (SBO); LBO unused for a single swizzle atom along K.
+// 8-row groups are `sbo_bytes` apart; LBO unused for a single swizzle atom along K.  The hardware
+// applies the swizzle XOR to the ABSOLUTE shared-memory address (bits 7..9 -> bits 4..6), exactly as
+// TMA does when it writes the tile, so any 128-byte-aligned start address and any 128-byte-multiple
+// group stride address a valid (shifted) window of a swizzled tile; the base-offset field stays 0
+// (measured: csrc/experiments/umma_probe.cu — a non-zero base offset breaks shifted windows).
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);        // start address
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;   // stride byte offset
   d |= (uint64_t)1 << 46;                             // descriptor version (sm_100)
-  d |= (uint64_t)((smem_addr >> 7) & 0x7) << 49;      // base offset (0 for 1024-byte aligned tiles)
   d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
   return d;
 }

@@ -1,0 +1,114 @@
+"""Multi-GPU plumbing of the SR path: one process per GPU, torch.distributed (NCCL over NVLink on the
+GPU box, gloo in the CPU tests).
+
+Inference: frames — or spatial tiles with a halo that covers the network's receptive
+field — are independent units, so they are SHARDED across ranks with NO data-path collective.  In
+eval mode BatchNorm is a per-channel affine, so a tile computed with `halo` extra LR pixels on every
+interior side and cropped afterwards equals the same region of the whole-frame result exactly.
+
+Training (progressive shrinking): batch-sharded; every rank seeds Python `random` identically
+(progressive_shrinking.py:164) so all ranks sample the same sub-network; gradients accumulate over
+`dynamic_batch_size` sub-networks and are then summed across ranks ONCE per step through a flat,
+zero-filled buffer (inactive blocks have no .grad — a fixed-size buffer keeps the collective
+shape-stable), divided by the world size (Horovod semantics, distributed_run_manager.py:72-75).
+BatchNorm statistics stay per-rank, as under nn.DataParallel.
+"""
+import torch
+
+# receptive-field radius of the max S4 sub-network in LR pixels: stem 2 + 14 blocks x 3 (7x7) + tail
+# 2 + 2 + shuffle convs 2 + 1 + output conv 0.5  ->  51.5; 64 keeps tiles 16-aligned
+S4_HALO_LR = 64
+
+
+def shard_range(n_items, rank, world):
+    """Contiguous, balanced [lo, hi) slice of `n_items` units for `rank` (frames, tiles or samples)."""
+    base, extra = divmod(n_items, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def tile_grid(h, w, tiles_y, tiles_x, halo):
+    """Split an h x w LR frame into tiles_y x tiles_x tiles.  Returns a list of dicts with the input
+    window (with halo, clipped to the frame) and the crop that removes the halo again, both in LR
+    pixels: {'in': (y0, y1, x0, x1), 'core': (y0, y1, x0, x1), 'crop': (cy0, cy1, cx0, cx1)}."""
+    tiles = []
+    for ty in range(tiles_y):
+        cy0, cy1 = shard_range(h, ty, tiles_y)
+        for tx in range(tiles_x):
+            cx0, cx1 = shard_range(w, tx, tiles_x)
+            iy0, iy1 = max(0, cy0 - halo), min(h, cy1 + halo)
+            ix0, ix1 = max(0, cx0 - halo), min(w, cx1 + halo)
+            tiles.append({'in': (iy0, iy1, ix0, ix1), 'core': (cy0, cy1, cx0, cx1),
+                          'crop': (cy0 - iy0, cy1 - iy0, cx0 - ix0, cx1 - ix0)})
+    return tiles
+
+
+def tiled_forward(net, x, tiles_y, tiles_x, halo=S4_HALO_LR, scale=4, rank=0, world=1, out=None):
+    """Run `net` on this rank's share of the tile grid of frame batch `x` [N,3,h,w].  Returns
+    (out, my_tiles): `out` is an [N,3,scale*h,scale*w] tensor in which only this rank's core regions are
+    written (no collective — the caller owns assembly, e.g. each rank writes its region of a shared
+    file / display buffer)."""
+    n, _, h, w = x.shape
+    tiles = tile_grid(h, w, tiles_y, tiles_x, halo)
+    lo, hi = shard_range(len(tiles), rank, world)
+    if out is None:
+        out = torch.zeros((n, 3, scale * h, scale * w), dtype=torch.float32, device=x.device)
+    for t in tiles[lo:hi]:
+        iy0, iy1, ix0, ix1 = t['in']
+        y = net(x[:, :, iy0:iy1, ix0:ix1])
+        cy0, cy1, cx0, cx1 = (scale * v for v in t['crop'])
+        oy0, oy1, ox0, ox1 = (scale * v for v in t['core'])
+        out[:, :, oy0:oy1, ox0:ox1] = y[:, :, cy0:cy1, cx0:cx1]
+    return out, tiles[lo:hi]
+
+
+class FlatGradAllReduce:
+    """Gradient exchange of data-parallel progressive-shrinking training.
+
+    All parameters own a slot in one flat fp32 buffer (fixed layout, so every rank issues the same
+    collective whatever sub-network was sampled).  `reduce()` packs the available .grad tensors
+    (zeros elsewhere), all-reduces the buffer in `n_buckets` contiguous buckets (the tail of the net —
+    whose gradients are ready first in backward — goes first so the transfer overlaps the rest of the
+    pack), averages, and scatters the result back into .grad (creating it where a rank had none, so
+    the optimizer sees identical gradients everywhere)."""
+
+    def __init__(self, params, n_buckets=2, process_group=None):
+        self.params = [p for p in params if p.requires_grad]
+        self.group = process_group
+        self.offsets = []
+        total = 0
+        for p in self.params:
+            self.offsets.append(total)
+            total += p.numel()
+        self.total = total
+        dev = self.params[0].device if self.params else torch.device('cpu')
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        cuts = [round(total * i / n_buckets) for i in range(n_buckets + 1)]
+        self.buckets = [(cuts[i], cuts[i + 1]) for i in range(n_buckets) if cuts[i + 1] > cuts[i]]
+
+    def reduce(self):
+        import torch.distributed as dist
+        world = dist.get_world_size(self.group)
+        self.flat.zero_()
+        for p, off in zip(self.params, self.offsets):
+            if p.grad is not None:
+                self.flat[off:off + p.numel()].copy_(p.grad.reshape(-1))
+        handles = []
+        for lo, hi in reversed(self.buckets):
+            handles.append(dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        for h in handles:
+            h.wait()
+        self.flat.div_(world)
+        for p, off in zip(self.params, self.offsets):
+            g = self.flat[off:off + p.numel()].view_as(p)
+            if p.grad is None:
+                p.grad = g.clone()
+            else:
+                p.grad.copy_(g)
+
+
+def broadcast_parameters(module, src=0, process_group=None):
+    """One-time broadcast of parameters and buffers from rank `src` (distributed_run_manager.py:180-184)."""
+    import torch.distributed as dist
+    for t in list(module.parameters()) + list(module.buffers()):
+        dist.broadcast(t.data, src=src, group=process_group)

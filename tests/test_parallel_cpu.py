@@ -1,0 +1,98 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU plumbing: unit sharding, the halo tile grid and the
+flat gradient all-reduce of data-parallel progressive shrinking.  The kernels are not involved."""
+import os
+import random
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from ofa_b200 import parallel as P
+
+
+def test_shard_range_partitions_exactly():
+    for n in (0, 1, 7, 8, 64, 1001):
+        for world in (1, 2, 3, 8):
+            spans = [P.shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_tile_grid_covers_frame_once_and_halo_is_clipped():
+    h, w, halo = 540, 960, 64
+    tiles = P.tile_grid(h, w, 2, 4, halo)
+    cover = torch.zeros(h, w, dtype=torch.int32)
+    for t in tiles:
+        iy0, iy1, ix0, ix1 = t['in']
+        cy0, cy1, cx0, cx1 = t['core']
+        assert 0 <= iy0 <= cy0 < cy1 <= iy1 <= h and 0 <= ix0 <= cx0 < cx1 <= ix1 <= w
+        assert (cy0 - iy0 in (0, halo)) and (cx0 - ix0 in (0, halo))      # halo only on interior sides
+        assert t['crop'] == (cy0 - iy0, cy1 - iy0, cx0 - ix0, cx1 - ix0)
+        cover[cy0:cy1, cx0:cx1] += 1
+    assert int(cover.min()) == 1 and int(cover.max()) == 1
+
+
+def test_tiled_forward_equals_whole_frame_for_a_local_operator():
+    """A stand-in 'network' with a known receptive field (5 stacked 3x3 box filters + 4x nearest
+    upsampling): tiling with halo >= radius must reproduce the whole-frame result exactly."""
+    def net(x):
+        for _ in range(5):
+            x = torch.nn.functional.avg_pool2d(torch.nn.functional.pad(x, (1, 1, 1, 1)), 3, 1) * 9
+        return torch.nn.functional.interpolate(x, scale_factor=4, mode='nearest')
+    x = torch.rand(2, 3, 37, 53)
+    whole = net(x)
+    out = None
+    for rank in range(3):
+        out, mine = P.tiled_forward(net, x, 2, 3, halo=5, scale=4, rank=rank, world=3, out=out)
+        assert len(mine) == 2
+    assert torch.equal(out, whole)
+
+
+def _worker(rank, world, port, ret):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)                       # identical init on every rank
+        model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Linear(5, 4), torch.nn.Linear(4, 3))
+        if rank == 1:                              # diverge, then broadcast from rank 0 must repair it
+            for p in model.parameters():
+                p.data.add_(1.0)
+        P.broadcast_parameters(model, src=0)
+        sync = P.FlatGradAllReduce(model.parameters(), n_buckets=2)
+        # every rank seeds `random` identically -> same "sub-network" choice (progressive_shrinking.py:164)
+        random.seed(int('%d%.3d%.3d' % (7, 0, 0)))
+        skip_last = random.choice([True, False])
+        torch.manual_seed(100 + rank)              # different data shard per rank
+        x = torch.randn(8, 6)
+        h = model[1](model[0](x))
+        y = h.sum() if skip_last else model[2](h).sum()   # the skipped layer has NO .grad on any rank
+        y.backward()
+        local = [None if p.grad is None else p.grad.clone() for p in model.parameters()]
+        sync.reduce()
+        gathered = [None] * world
+        dist.all_gather_object(gathered, [None if g is None else g.tolist() for g in local])
+        ok = True
+        for i, p in enumerate(model.parameters()):
+            parts = [torch.tensor(g[i]) if g[i] is not None else torch.zeros_like(p) for g in gathered]
+            expect = sum(parts) / world
+            ok = ok and p.grad is not None and torch.allclose(p.grad, expect, atol=1e-6)
+        w0 = [p.detach().clone() for p in model.parameters()]
+        allw = [None] * world
+        dist.all_gather_object(allw, [w.tolist() for w in w0])
+        ok = ok and allw[0] == allw[1]
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_flat_grad_allreduce_world2_gloo():
+    world = 2
+    port = 29500 + (os.getpid() % 2000)
+    with mp.Manager() as m:
+        ret = m.dict()
+        mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+        assert dict(ret) == {0: True, 1: True}
