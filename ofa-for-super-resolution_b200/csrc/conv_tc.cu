@@ -60,6 +60,7 @@ constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;   // warp 0 TMA, warp 1 MMA
 constexpr int MAX_COUT = 512;
 constexpr int MAX_A_STAGES = 4, MAX_B_STAGES = 8;
 constexpr int B_RESIDENT_LIMIT = 64 * 1024;
+constexpr int STAGE_BYTES = 32 * 64;         // per epilogue warp: 32 pixel rows x 32 bf16 channels
 
 struct ConvTcParams {
   int N, H, W;
@@ -158,7 +159,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   const size_t b_total = p.b_resident ? (size_t)taps * p.kcs * p.cout_pad * 128 : (size_t)p.b_stages * B_BYTES;
   float* s_scale = reinterpret_cast<float*>(sB + b_total);
   float* s_shift = s_scale + MAX_COUT;
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(s_shift + MAX_COUT);
+  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_shift + MAX_COUT);   // NUM_EPI_WARPS x 2 KiB store staging
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(s_stage + NUM_EPI_WARPS * STAGE_BYTES);
   uint64_t* a_empty = a_full + MAX_A_STAGES;
   uint64_t* b_full = a_empty + MAX_A_STAGES;
   uint64_t* b_empty = b_full + MAX_B_STAGES;
@@ -167,7 +169,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   uint64_t* bres_bar = tempty + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bres_bar + 1);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform
   const int lane = threadIdx.x & 31;
 
   for (int op = threadIdx.x; op < p.cout_pad; op += NUM_THREADS) {
@@ -202,7 +204,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);   // warp-uniform by construction
 
   const int tiles_per_img = p.tiles_h * p.tiles_w;
   const int outer_splits = p.n_splits / p.inner_splits;
@@ -252,59 +254,64 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = ptx::umma_idesc_bf16(128, p.BN);
-      const uint32_t sbo_a = (uint32_t)p.halo_w * 128;
-      int as = 0, bs = 0, acc = 0;
-      uint32_t aph = 0, bph = 0, accph = 0;
-      if (p.b_resident) ptx::mbar_wait(bres_bar, 0);
-      for (int wi = blockIdx.x; wi < num_work; wi += gridDim.x) {
-        const int split0 = wi % outer_splits;
-        int as_item = as;           // first A stage of this work item
-        uint32_t aph_item = aph;
-        for (int s = 0; s < p.inner_splits; ++s) {
-          ptx::mbar_wait(&tempty[acc], accph ^ 1);
+    // The whole warp walks the loops (warp-uniform control flow, so descriptors live in uniform
+    // registers); only the tcgen05 instructions are predicated on one lane.
+    const uint32_t leader = (lane == 0) ? 1u : 0u;
+    const uint32_t idesc = ptx::umma_idesc_bf16(128, p.BN);
+    const uint32_t sbo_a = (uint32_t)p.halo_w * 128;
+    const uint32_t sB_addr = ptx::smem_u32(sB);
+    int as = 0, bs = 0, acc = 0;
+    uint32_t aph = 0, bph = 0, accph = 0;
+    if (p.b_resident) ptx::mbar_wait(bres_bar, 0);
+    for (int wi = blockIdx.x; wi < num_work; wi += gridDim.x) {
+      const int split0 = wi % outer_splits;
+      const int as_item = as;           // first A stage of this work item
+      const uint32_t aph_item = aph;
+      for (int s = 0; s < p.inner_splits; ++s) {
+        ptx::mbar_wait(&tempty[acc], accph ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_cols);
+        int a_cur = as_item;
+        uint32_t a_cur_ph = aph_item;
+        const int row0 = (split0 * p.inner_splits + s) * p.BN;
+        uint32_t first = 0;             // 0 until the first MMA of this accumulator has been issued
+        for (int kc = 0; kc < p.kcs; ++kc) {
+          if (s == 0) ptx::mbar_wait(&a_full[a_cur], a_cur_ph);
           ptx::tc_fence_after();
-          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_cols);
-          int a_cur = as_item;
-          uint32_t a_cur_ph = aph_item;
-          const int row0 = (split0 * p.inner_splits + s) * p.BN;
-          for (int kc = 0; kc < p.kcs; ++kc) {
-            if (s == 0) ptx::mbar_wait(&a_full[a_cur], a_cur_ph);
-            ptx::tc_fence_after();
-            const uint32_t a_base = ptx::smem_u32(sA + (size_t)a_cur * a_stride);
-            for (int tap = 0; tap < p.ks * p.ks; ++tap) {
-              const int ky = tap / p.ks, kx = tap - ky * p.ks;
-              uint32_t b_addr;
-              if (p.b_resident) {
-                b_addr = ptx::smem_u32(sB) + (uint32_t)(((tap * p.kcs + kc) * p.cout_pad + row0) * 128);
-              } else {
+          const uint32_t a_base = ptx::smem_u32(sA) + (uint32_t)(a_cur * a_stride);
+          uint32_t b_res = sB_addr + (uint32_t)((kc * p.cout_pad + row0) * 128);   // resident: tap-major blocks
+          const uint32_t b_res_step = (uint32_t)(p.kcs * p.cout_pad * 128);
+          for (int ky = 0; ky < p.ks; ++ky) {
+            uint32_t a_row = a_base + (uint32_t)(ky * p.halo_w * 128);
+            for (int kx = 0; kx < p.ks; ++kx, a_row += 128, b_res += b_res_step) {
+              uint32_t b_addr = b_res;
+              if (!p.b_resident) {
                 ptx::mbar_wait(&b_full[bs], bph);
                 ptx::tc_fence_after();
-                b_addr = ptx::smem_u32(sB + (size_t)bs * B_BYTES);
+                b_addr = sB_addr + (uint32_t)(bs * B_BYTES);
               }
               const uint64_t db = ptx::umma_desc_sw128(b_addr, 1024);
 #pragma unroll
               for (int m = 0; m < MTX; ++m) {
-                const uint32_t a_addr = a_base + (uint32_t)((ky * p.halo_w + kx + m * MT_COLS) * 128);
-                const uint64_t da = ptx::umma_desc_sw128(a_addr, sbo_a);
+                const uint64_t da = ptx::umma_desc_sw128(a_row + (uint32_t)(m * MT_COLS * 128), sbo_a);
 #pragma unroll
                 for (int k = 0; k < BK / 16; ++k)
-                  ptx::umma_bf16(d_tmem + (uint32_t)(m * p.BN), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
-                                 (kc | tap | k) ? 1u : 0u);
+                  ptx::umma_bf16_pred(d_tmem + (uint32_t)(m * p.BN), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2),
+                                      idesc, first | (uint32_t)k, leader);
               }
+              first = 1;
               if (!p.b_resident) {
-                ptx::umma_commit(&b_empty[bs]);
+                ptx::umma_commit_pred(&b_empty[bs], leader);
                 if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
               }
             }
-            if (s == p.inner_splits - 1) ptx::umma_commit(&a_empty[a_cur]);
-            if (++a_cur == p.a_stages) { a_cur = 0; a_cur_ph ^= 1; }
           }
-          if (s == p.inner_splits - 1) { as = a_cur; aph = a_cur_ph; }
-          ptx::umma_commit(&tfull[acc]);
-          if (++acc == 2) { acc = 0; accph ^= 1; }
+          if (s == p.inner_splits - 1) ptx::umma_commit_pred(&a_empty[a_cur], leader);
+          if (++a_cur == p.a_stages) { a_cur = 0; a_cur_ph ^= 1; }
         }
+        if (s == p.inner_splits - 1) { as = a_cur; aph = a_cur_ph; }
+        ptx::umma_commit_pred(&tfull[acc], leader);
+        if (++acc == 2) { acc = 0; accph ^= 1; }
       }
     }
   } else {
@@ -328,15 +335,68 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         ptx::mbar_wait(&tfull[acc], accph);
         ptx::tc_fence_after();
         const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * acc_cols + m * p.BN);
+        uint8_t* stage = s_stage + ew * STAGE_BYTES;
+        const int h_t0 = (r / p.tiles_w) * TILE_H, w_t0 = (r % p.tiles_w) * TILE_W + m * MT_COLS;
         for (int j = 0; j < p.BN; j += 32) {
           uint32_t v[32];
           const bool two = j + 16 < p.BN;
           ptx::tmem_ld16(t_addr + (uint32_t)j, v);
           if (two) ptx::tmem_ld16(t_addr + (uint32_t)(j + 16), v + 16);
           ptx::tmem_ld_wait();
-          if (pix_ok) {
-            emit16(p, s_scale, s_shift, v, col0 + j, n, h, w);
-            if (two) emit16(p, s_scale, s_shift, v + 16, col0 + j + 16, n, h, w);
+          const int op0 = col0 + j;
+          if (p.vec_store && j + 32 <= p.BN && op0 + 32 <= p.cout) {
+            // ---- coalesced path: thread = pixel row computes, then the warp re-reads the 32 x 64-byte
+            // block through a swizzled staging tile so each store instruction writes 8 x 64 contiguous bytes
+            int sub = 0, oc0 = op0;
+            if (p.store == OFA_STORE_PIXELSHUFFLE2) { const int q = p.cout >> 2; sub = op0 / q; oc0 = op0 - sub * q; }
+            float f[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              f[i] = apply_act(fmaf(__uint_as_float(v[i]), s_scale[op0 + i], s_shift[op0 + i]), p.act);
+            if (p.res.ptr && pix_ok) {
+              int oh = h, ow = w;
+              if (p.store == OFA_STORE_PIXELSHUFFLE2) { oh = 2 * h + (sub >> 1); ow = 2 * w + (sub & 1); }
+              const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.res.ptr) +
+                                                               p.res.off(n, oc0, oh, ow));
+#pragma unroll
+              for (int q4 = 0; q4 < 4; ++q4) {
+                const uint4 rv = rp[q4];
+                const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  f[q4 * 8 + 2 * i] += __uint_as_float(rr[i] << 16);
+                  f[q4 * 8 + 2 * i + 1] += __uint_as_float(rr[i] & 0xffff0000u);
+                }
+              }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                __nv_bfloat162 b2 = __floats2bfloat162_rn(f[k * 8 + 2 * i], f[k * 8 + 2 * i + 1]);
+                pk[i] = *reinterpret_cast<uint32_t*>(&b2);
+              }
+              *reinterpret_cast<uint4*>(stage + lane * 64 + ((k ^ ((lane >> 1) & 3)) << 4)) =
+                  make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const int rr = it * 8 + (lane >> 2), piece = lane & 3;
+              const uint4 val = *reinterpret_cast<const uint4*>(stage + rr * 64 + ((piece ^ ((rr >> 1) & 3)) << 4));
+              const int R2 = quarter * 32 + rr;
+              const int hh = h_t0 + R2 / MT_COLS, ww = w_t0 + R2 % MT_COLS;
+              if (hh < p.H && ww < p.W) {
+                int oh = hh, ow = ww;
+                if (p.store == OFA_STORE_PIXELSHUFFLE2) { oh = 2 * hh + (sub >> 1); ow = 2 * ww + (sub & 1); }
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y.ptr) + p.y.off(n, oc0 + piece * 8, oh, ow)) = val;
+              }
+            }
+            __syncwarp();
+          } else if (pix_ok) {
+            emit16(p, s_scale, s_shift, v, op0, n, h, w);
+            if (two) emit16(p, s_scale, s_shift, v + 16, op0 + 16, n, h, w);
           }
         }
         ptx::tc_fence_before();
@@ -406,7 +466,7 @@ int launch_conv_tc(const OfaConvArgs* a, cudaStream_t st) {
   const long long b_all = (long long)taps * p.kcs * p.cout_pad * 128;
   p.b_resident = b_all <= B_RESIDENT_LIMIT ? 1 : 0;
   const int a_stride = (p.a_bytes + 1023) & ~1023;
-  const int fixed = 1024 /*align slack*/ + 2 * MAX_COUT * 4 + 512;
+  const int fixed = 1024 /*align slack*/ + 2 * MAX_COUT * 4 + NUM_EPI_WARPS * STAGE_BYTES + 512;
   const int budget = 227 * 1024 - fixed;
   if (p.b_resident) {
     p.b_stages = 0;

@@ -92,9 +92,14 @@ class ConvLayer(MyModule):
         bn = self.bn if self.use_bn else None
         w = self.conv.weight
         if OF.inference_mode_active(self):
+            out_dtype = self.out_dtype
+            if out_dtype is None and self.out_channels < 16 and self._store == B.STORE_PLAIN:
+                # thin tensors (the 3-channel learned low-resolution image of X4) stay fp32: it costs
+                # nothing and a bf16 rounding at a 3-channel bottleneck perturbs the image directly
+                out_dtype = torch.float32
             return OF.conv_bn_act_infer(x, w, self.in_channels, self.out_channels, self.kernel_size, bn,
                                         self._act_code, self._store, residual, self._packed,
-                                        self.out_dtype, self.out_nchw)
+                                        out_dtype, self.out_nchw)
         y = OF.conv2d(x, w, self.in_channels, self.out_channels, self.kernel_size)
         if self._store == B.STORE_PLAIN:
             if bn is not None:
