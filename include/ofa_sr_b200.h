@@ -37,6 +37,7 @@ extern "C" {
 
 #define OFA_F32 0
 #define OFA_BF16 1
+#define OFA_F16 2 /* only as the storage type of the planar MBConv intermediates */
 
 /* activation codes (ofa/utils.py:242-314 build_activation) */
 #define OFA_ACT_NONE 0
@@ -53,6 +54,7 @@ extern "C" {
 #define OFA_IMPL_AUTO 0
 #define OFA_IMPL_SIMT 1 /* CUDA-core kernels: any layout, fp32 or bf16 I/O                      */
 #define OFA_IMPL_FAST 2 /* TMA halo tiles (depthwise) / tcgen05+TMEM implicit GEMM (dense conv)  */
+#define OFA_IMPL_NHWC 3 /* ofa_mbconv_fwd only: the three NHWC kernels instead of the planar path */
 
 /* A 4-D activation view: element (n, c, h, w) lives at ptr + n*sn + c*sc + h*sh + w*sw (elements). */
 typedef struct OfaTensor4 {
@@ -196,11 +198,32 @@ typedef struct OfaMBConvArgs {
   int32_t add_residual; /* 1: y = block(x) + x */
   void* ws;
   int64_t ws_bytes;
+  int32_t mid_dtype; /* storage of the two expanded intermediates on the planar tensor-core path:
+                        0 = default (OFA_F16: they are ReLU6-clamped, fp16 keeps 3 more mantissa bits),
+                        OFA_BF16 or OFA_F16 */
 } OfaMBConvArgs;
 
 int64_t ofa_mbconv_workspace_bytes(int32_t n, int32_t h, int32_t w, int32_t cin, int32_t mid,
                                    int32_t cout);
 int ofa_mbconv_fwd(const OfaMBConvArgs* a, int32_t impl, void* stream);
+
+/* The three stages of ofa_mbconv_fwd's planar tcgen05 path (cin = cout = 64, mid % 64 == 0, W % 8 == 0),
+ * exported so that tests and profilers can drive them one by one.  "planar" = [N][C][H*W] dense, 16-bit
+ * (`dtype` = OFA_BF16 | OFA_F16); "nhwc" = [N][H*W][64] dense bf16.
+ *   pack    : w_exp[:mid,:64] -> bf16 [ceil(mid/128)*128][64], w_proj[:64,:mid] -> `dtype` [64][mid]
+ *   expand  : (a3 + a5 + a6) 1x1 64 -> mid, folded BN, activation            nhwc   -> planar
+ *   dw      : (a1 + a2 + a5 + a6) elastic depthwise ks x ks, folded BN, act   planar -> planar
+ *   project : (a4 + a5 + a8) 1x1 mid -> 64, folded BN, + residual (or NULL)   planar -> nhwc            */
+int ofa_mbconv_pack_weights(const float* w_exp, int64_t w_exp_so, int64_t w_exp_si, const float* w_proj,
+                            int64_t w_proj_so, int64_t w_proj_si, int32_t mid, int32_t dtype,
+                            void* wexp_packed, void* wproj_packed, void* stream);
+int ofa_expand_planar_fwd(const void* x_nhwc, void* y_planar, const void* wexp_packed, int32_t n, int32_t hw,
+                          int32_t mid, int32_t dtype, const OfaBn* bn, int32_t act, void* stream);
+int ofa_dw_planar_fwd(const void* x_planar, void* y_planar, int32_t n, int32_t c, int32_t h, int32_t w,
+                      const float* w7, int32_t kmax, const float* m75, const float* m53, int32_t transform_on,
+                      int32_t ks, int32_t dtype, const OfaBn* bn, int32_t act, void* stream);
+int ofa_project_planar_fwd(const void* x_planar, const void* res_nhwc, void* y_nhwc, const void* wproj_packed,
+                           int32_t n, int32_t hw, int32_t mid, int32_t dtype, const OfaBn* bn, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (a14) backward of the path — autograd of dynamic_op.py:73-84,104-112,148-167

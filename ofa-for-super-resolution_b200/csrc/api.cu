@@ -260,7 +260,6 @@ int ofa_mbconv_fwd(const OfaMBConvArgs* a, int32_t impl, void* stream) {
   OFA_REQUIRE(a->ws && a->ws_bytes >= need, "ofa_mbconv_fwd: workspace too small (%lld < %lld)",
               (long long)a->ws_bytes, (long long)need);
   if ((rc = check_transform_args(a->kmax, a->m75, a->m53, a->transform_on, a->ks))) return rc;
-  (void)impl;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t P = (int64_t)a->x.n * a->x.h * a->x.w;
   char* ws = reinterpret_cast<char*>(a->ws);
@@ -268,6 +267,23 @@ int ofa_mbconv_fwd(const OfaMBConvArgs* a, int32_t impl, void* stream) {
   void* t2 = ws + P * a->mid * 2;
   void* wexp_p = ws + 2 * P * a->mid * 2;
   void* wproj_p = reinterpret_cast<char*>(wexp_p) + (int64_t)384 * 384 * 2;
+  OFA_REQUIRE(a->mid_dtype == 0 || a->mid_dtype == OFA_BF16 || a->mid_dtype == OFA_F16, "bad mid_dtype %d",
+              a->mid_dtype);
+
+  // ---- planar tcgen05 path: expand -> Toeplitz depthwise -> project around channel-planar intermediates
+  if (impl != OFA_IMPL_SIMT && impl != OFA_IMPL_NHWC && mbconv_planar_supported(a)) {
+    const int f16 = (a->mid_dtype == OFA_BF16) ? 0 : 1;
+    const int HW = a->x.h * a->x.w;
+    const int mid_pad = (a->mid + 127) / 128 * 128;
+    if ((rc = launch_pack_block_weights(a->w_exp, a->w_exp_so, a->w_exp_si, a->w_proj, a->w_proj_so, a->w_proj_si,
+                                        a->cin, a->mid, a->cout, mid_pad, f16, wexp_p, wproj_p, st))) return rc;
+    if ((rc = launch_expand_planar(a->x.ptr, t1, wexp_p, a->x.n, HW, a->mid, f16, &a->bn_exp, a->act, st))) return rc;
+    if ((rc = launch_dw_planar(t1, t2, a->x.n, a->mid, a->x.h, a->x.w, a->w_dw, a->kmax, a->m75, a->m53,
+                               a->transform_on, a->ks, f16, &a->bn_dw, a->act, st))) return rc;
+    return launch_project_planar(t2, a->add_residual ? a->x.ptr : nullptr, a->y.ptr, wproj_p, a->x.n, HW, a->mid, f16,
+                                 &a->bn_proj, st);
+  }
+  if (impl == OFA_IMPL_NHWC) impl = OFA_IMPL_AUTO;
   // pack the active weight slices (tiny) — the slice W[:mid,:cin] is read in place from the full parameter
   if ((rc = launch_pack_weight(a->w_exp, a->w_exp_so, a->w_exp_si, 0, 0, a->cin, a->mid, 1, a->cin, a->mid, OFA_STORE_PLAIN, wexp_p, st))) return rc;
   if ((rc = launch_pack_weight(a->w_proj, a->w_proj_so, a->w_proj_si, 0, 0, a->mid, a->cout, 1, a->mid, a->cout, OFA_STORE_PLAIN, wproj_p, st))) return rc;
@@ -303,6 +319,68 @@ int ofa_mbconv_fwd(const OfaMBConvArgs* a, int32_t impl, void* stream) {
   c3.epi.var = a->bn_proj.var; c3.epi.eps = a->bn_proj.eps; c3.epi.act = OFA_ACT_NONE;
   c3.epi.residual = a->add_residual ? &a->x : nullptr;
   return ofa_conv_fwd(&c3, impl, stream);
+}
+
+static int dtype16_flag(int32_t dtype, int* f16) {
+  OFA_REQUIRE(dtype == OFA_BF16 || dtype == OFA_F16, "planar stages store OFA_BF16 or OFA_F16 (got %d)", dtype);
+  *f16 = dtype == OFA_F16 ? 1 : 0;
+  return OFA_OK;
+}
+
+int ofa_mbconv_pack_weights(const float* w_exp, int64_t e_so, int64_t e_si, const float* w_proj, int64_t p_so,
+                            int64_t p_si, int32_t mid, int32_t dtype, void* wexp_packed, void* wproj_packed,
+                            void* stream) {
+  int rc = require_device(), f16 = 0;
+  if (rc) return rc;
+  if ((rc = dtype16_flag(dtype, &f16))) return rc;
+  OFA_REQUIRE(w_exp && w_proj && wexp_packed && wproj_packed, "ofa_mbconv_pack_weights: null pointer");
+  OFA_REQUIRE(mid % 64 == 0 && mid >= 64 && mid <= 384, "mid must be a multiple of 64 in [64, 384]");
+  return launch_pack_block_weights(w_exp, e_so, e_si, w_proj, p_so, p_si, 64, mid, 64, (mid + 127) / 128 * 128, f16,
+                                   wexp_packed, wproj_packed, (cudaStream_t)stream);
+}
+
+static int planar_dims_ok(int32_t n, int64_t hw, int32_t mid) {
+  OFA_REQUIRE(n > 0 && hw > 0 && hw % 8 == 0 && hw < (1ll << 31), "planar stages need N > 0 and H*W %% 8 == 0");
+  OFA_REQUIRE(mid % 64 == 0 && mid >= 64 && mid <= 384, "mid must be a multiple of 64 in [64, 384]");
+  return OFA_OK;
+}
+
+int ofa_expand_planar_fwd(const void* x_nhwc, void* y_planar, const void* wexp_packed, int32_t n, int32_t hw,
+                          int32_t mid, int32_t dtype, const OfaBn* bn, int32_t act, void* stream) {
+  int rc = require_device(), f16 = 0;
+  if (rc) return rc;
+  if ((rc = dtype16_flag(dtype, &f16))) return rc;
+  if ((rc = planar_dims_ok(n, hw, mid))) return rc;
+  OFA_REQUIRE(x_nhwc && y_planar && wexp_packed && bn, "ofa_expand_planar_fwd: null pointer");
+  OFA_REQUIRE(((uintptr_t)x_nhwc & 15) == 0 && ((uintptr_t)y_planar & 15) == 0 && ((uintptr_t)wexp_packed & 15) == 0,
+              "ofa_expand_planar_fwd: pointers must be 16-byte aligned");
+  return launch_expand_planar(x_nhwc, y_planar, wexp_packed, n, hw, mid, f16, bn, act, (cudaStream_t)stream);
+}
+
+int ofa_dw_planar_fwd(const void* x_planar, void* y_planar, int32_t n, int32_t c, int32_t h, int32_t w,
+                      const float* w7, int32_t kmax, const float* m75, const float* m53, int32_t transform_on,
+                      int32_t ks, int32_t dtype, const OfaBn* bn, int32_t act, void* stream) {
+  int rc = require_device(), f16 = 0;
+  if (rc) return rc;
+  if ((rc = dtype16_flag(dtype, &f16))) return rc;
+  OFA_REQUIRE(x_planar && y_planar && w7, "ofa_dw_planar_fwd: null pointer");
+  OFA_REQUIRE(n > 0 && c > 0 && h > 0 && w > 0 && w % 8 == 0, "ofa_dw_planar_fwd: needs W %% 8 == 0");
+  OFA_REQUIRE(((uintptr_t)x_planar & 15) == 0 && ((uintptr_t)y_planar & 15) == 0, "pointers must be 16-byte aligned");
+  if ((rc = check_transform_args(kmax, m75, m53, transform_on, ks))) return rc;
+  return launch_dw_planar(x_planar, y_planar, n, c, h, w, w7, kmax, m75, m53, transform_on, ks, f16, bn, act,
+                          (cudaStream_t)stream);
+}
+
+int ofa_project_planar_fwd(const void* x_planar, const void* res_nhwc, void* y_nhwc, const void* wproj_packed,
+                           int32_t n, int32_t hw, int32_t mid, int32_t dtype, const OfaBn* bn, void* stream) {
+  int rc = require_device(), f16 = 0;
+  if (rc) return rc;
+  if ((rc = dtype16_flag(dtype, &f16))) return rc;
+  if ((rc = planar_dims_ok(n, hw, mid))) return rc;
+  OFA_REQUIRE(x_planar && y_nhwc && wproj_packed && bn, "ofa_project_planar_fwd: null pointer");
+  OFA_REQUIRE(((uintptr_t)x_planar & 15) == 0 && ((uintptr_t)y_nhwc & 15) == 0 && ((uintptr_t)res_nhwc & 15) == 0 &&
+                  ((uintptr_t)wproj_packed & 15) == 0, "pointers must be 16-byte aligned");
+  return launch_project_planar(x_planar, res_nhwc, y_nhwc, wproj_packed, n, hw, mid, f16, bn, (cudaStream_t)stream);
 }
 
 int ofa_dw_bwd_filter(const OfaTensor4* x, const OfaTensor4* dy, int32_t ks, float* dw_active, void* stream) {

@@ -40,4 +40,16 @@ int launch_dw_fast(const OfaTensor4* x, const OfaTensor4* y, const float* w7, in
 bool conv_tc_supported(const OfaConvArgs* a);
 int launch_conv_tc(const OfaConvArgs* a, cudaStream_t st);
 
+// ---- mbconv_planar.cu : MBConv block on channel-planar 16-bit intermediates (tcgen05) ---------------
+bool mbconv_planar_supported(const OfaMBConvArgs* a);
+int launch_pack_block_weights(const float* w_exp, long long e_so, long long e_si, const float* w_proj,
+                              long long p_so, long long p_si, int cin, int mid, int cout, int mid_pad, int f16,
+                              void* wexp_p, void* wproj_p, cudaStream_t st);
+int launch_expand_planar(const void* x, void* y, const void* wexp_p, int N, int HW, int mid, int f16,
+                         const OfaBn* bn, int act, cudaStream_t st);
+int launch_dw_planar(const void* x, void* y, int N, int C, int H, int W, const float* w7, int kmax, const float* m75,
+                     const float* m53, int transform_on, int ks, int f16, const OfaBn* bn, int act, cudaStream_t st);
+int launch_project_planar(const void* x, const void* res, void* y, const void* wproj_p, int N, int HW, int mid,
+                          int f16, const OfaBn* bn, cudaStream_t st);
+
 }  // namespace ofa

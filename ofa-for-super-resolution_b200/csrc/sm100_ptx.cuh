@@ -45,10 +45,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+#ifdef OFA_MBAR_SOFT_TIMEOUT
+    if (++spins > (1u << 22)) {   // bring-up aid: report and run on so that the message is flushed
+      printf("ofa: mbarrier wait timed out (block %d thread %d bar@%u parity %u)\n", (int)blockIdx.x,
+             (int)threadIdx.x, smem_u32(bar), parity);
+      return;
+    }
+#else
     if (++spins > (1u << 28)) {
       printf("ofa: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
       __trap();
     }
+#endif
   }
 }
 
@@ -70,6 +78,28 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uin
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
+}
+
+
+// TMA store (shared -> global), bulk-group completion
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until at most N of this thread's bulk groups still READ their shared-memory source
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait_all() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+// named barrier over `nthreads` threads (ids 1..15; 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 // ---- tcgen05 ------------------------------------------------------------------------------------
@@ -134,6 +164,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
       : "r"(taddr)
       : "memory");
 }
+
+// 32 lanes x 8 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // instruction descriptor for kind::f16: bf16 x bf16 -> fp32, both operands K-major
@@ -156,6 +194,27 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;   // stride byte offset
   d |= (uint64_t)1 << 46;                             // descriptor version (sm_100)
   d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
+  return d;
+}
+
+
+// general kind::f16 instruction descriptor: formats 0 = f16, 1 = bf16; majors 0 = K-major, 1 = MN-major
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N, int a_fmt, int b_fmt, int a_mn_major,
+                                                      int b_mn_major) {
+  return (1u << 4) | ((uint32_t)a_fmt << 7) | ((uint32_t)b_fmt << 10) | ((uint32_t)a_mn_major << 15) |
+         ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// generic shared-memory matrix descriptor: layout 0 = no swizzle, 2 = 128-byte swizzle
+//   K-major, no swizzle : 8x16-byte core matrices; K-halves `lbo` apart, 8-row groups `sbo` apart
+//   MN-major, 128B swz  : 64-element (128-byte) MN atoms `lbo` apart, 8-deep K groups `sbo` apart
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout << 61;
   return d;
 }
 

@@ -14,10 +14,10 @@ import torch
 _LIB_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'lib')
 LIB_PATH = os.path.join(_LIB_DIR, 'libofa_sr_b200.so')
 
-OFA_F32, OFA_BF16 = 0, 1
+OFA_F32, OFA_BF16, OFA_F16 = 0, 1, 2
 ACT_NONE, ACT_RELU6, ACT_HSWISH, ACT_RELU = 0, 1, 2, 3
 STORE_PLAIN, STORE_PIXELSHUFFLE2, STORE_PIXELUNSHUFFLE2 = 0, 1, 2
-IMPL_AUTO, IMPL_SIMT, IMPL_FAST = 0, 1, 2
+IMPL_AUTO, IMPL_SIMT, IMPL_FAST, IMPL_NHWC = 0, 1, 2, 3
 
 ACT_CODES = {None: ACT_NONE, 'relu6': ACT_RELU6, 'h_swish': ACT_HSWISH, 'relu': ACT_RELU}
 
@@ -53,7 +53,7 @@ class OfaMBConvArgs(Structure):
                 ('w_proj', c_void_p), ('w_proj_so', c_int64), ('w_proj_si', c_int64),
                 ('cin', c_int32), ('mid', c_int32), ('cout', c_int32), ('ks', c_int32), ('act', c_int32),
                 ('bn_exp', OfaBn), ('bn_dw', OfaBn), ('bn_proj', OfaBn),
-                ('add_residual', c_int32), ('ws', c_void_p), ('ws_bytes', c_int64)]
+                ('add_residual', c_int32), ('ws', c_void_p), ('ws_bytes', c_int64), ('mid_dtype', c_int32)]
 
 
 # every symbol include/ofa_sr_b200.h declares: name -> (restype, argtypes)
@@ -80,6 +80,14 @@ SYMBOLS = {
     'ofa_affine_act': (c_int32, [_T4, _T4, _EP, c_int32, c_void_p]),
     'ofa_mbconv_workspace_bytes': (c_int64, [c_int32] * 6),
     'ofa_mbconv_fwd': (c_int32, [POINTER(OfaMBConvArgs), c_int32, c_void_p]),
+    'ofa_mbconv_pack_weights': (c_int32, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int32, c_int32,
+                                          c_void_p, c_void_p, c_void_p]),
+    'ofa_expand_planar_fwd': (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                                        POINTER(OfaBn), c_int32, c_void_p]),
+    'ofa_dw_planar_fwd': (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32,
+                                    c_void_p, c_void_p, c_int32, c_int32, c_int32, POINTER(OfaBn), c_int32, c_void_p]),
+    'ofa_project_planar_fwd': (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                                         POINTER(OfaBn), c_void_p]),
     'ofa_dw_bwd_data': (c_int32, [_T4, _T4, c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_int32,
                                   c_void_p]),
     'ofa_dw_bwd_filter': (c_int32, [_T4, _T4, c_int32, c_void_p, c_void_p]),

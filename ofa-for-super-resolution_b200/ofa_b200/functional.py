@@ -16,7 +16,7 @@ import torch
 
 from . import backend as B
 
-_state = {'compute_dtype': torch.bfloat16, 'impl': B.IMPL_AUTO}
+_state = {'compute_dtype': torch.bfloat16, 'impl': B.IMPL_AUTO, 'mid_dtype': B.OFA_F16}
 
 
 def set_compute_dtype(dtype):
@@ -24,6 +24,13 @@ def set_compute_dtype(dtype):
     default) or torch.float32 (exact CUDA-core path).  Accumulation is fp32 either way."""
     assert dtype in (torch.bfloat16, torch.float32)
     _state['compute_dtype'] = dtype
+
+
+def set_mid_dtype(dtype):
+    """Storage type of the two expanded (ReLU6-clamped) intermediates of the planar MBConv path:
+    torch.float16 (default: 3 more mantissa bits than bf16 on [0, 6]) or torch.bfloat16."""
+    assert dtype in (torch.float16, torch.bfloat16)
+    _state['mid_dtype'] = B.OFA_F16 if dtype == torch.float16 else B.OFA_BF16
 
 
 def get_compute_dtype():
@@ -399,6 +406,10 @@ def mbconv_infer(x, w_exp, w_dw, m75, m53, w_proj, cin, mid, cout, ks, transform
     """Whole inference MBConv block (expand -> dw -> project [+x]) through ofa_mbconv_fwd; needs
     NHWC-dense bf16 x.  Returns NHWC bf16."""
     n, _, h, w = x.shape
+    planar = planar_supported(x, cin, mid, cout) and _state['impl'] not in (B.IMPL_SIMT, B.IMPL_NHWC)
+    if _profiler is not None and planar:
+        return _mbconv_planar_staged(x, w_exp, w_dw, m75, m53, w_proj, mid, ks, transform_on, act, bn_exp, bn_dw,
+                                     bn_proj, add_residual)
     if _profiler is not None:
         # same kernels, issued one by one so each gets its own event pair
         c1 = _prof_caches.setdefault((w_exp.data_ptr(), 0), PackedWeightCache())
@@ -424,7 +435,46 @@ def mbconv_infer(x, w_exp, w_dw, m75, m53, w_proj, cin, mid, cout, ks, transform
     a.bn_exp, a.bn_dw, a.bn_proj = _bn_struct(bn_exp), _bn_struct(bn_dw), _bn_struct(bn_proj)
     a.add_residual = int(bool(add_residual))
     a.ws, a.ws_bytes = ws.data_ptr(), ws_bytes
+    a.mid_dtype = _state['mid_dtype']
     B.check(L.ofa_mbconv_fwd(byref(a), _state['impl'], _stream(x)))
+    return y
+
+
+def planar_supported(x, cin, mid, cout):
+    """Shapes the planar tcgen05 MBConv path takes (mirrors mbconv_planar_supported in the library)."""
+    return (x.dtype == torch.bfloat16 and cin == 64 and cout == 64 and mid % 64 == 0 and 64 <= mid <= 384
+            and x.shape[3] % 8 == 0)
+
+
+def _mbconv_planar_staged(x, w_exp, w_dw, m75, m53, w_proj, mid, ks, transform_on, act, bn_exp, bn_dw, bn_proj,
+                          add_residual):
+    """The planar path stage by stage through the exported stage entry points (what ofa_mbconv_fwd runs
+    internally), so that the profiler gets one event pair per kernel."""
+    n, _, h, w = x.shape
+    hw = h * w
+    L = B.lib()
+    st = _stream(x)
+    dt = _state['mid_dtype']
+    tdt = torch.float16 if dt == B.OFA_F16 else torch.bfloat16
+    we = torch.empty(((mid + 127) // 128 * 128, 64), dtype=torch.bfloat16, device=x.device)
+    wp = torch.empty((64, mid), dtype=tdt, device=x.device)
+    B.check(L.ofa_mbconv_pack_weights(B.fptr(w_exp), w_exp.stride(0), w_exp.stride(1), B.fptr(w_proj),
+                                      w_proj.stride(0), w_proj.stride(1), mid, dt, we.data_ptr(), wp.data_ptr(), st))
+    t1 = torch.empty((n, mid, hw), dtype=tdt, device=x.device)
+    t2 = torch.empty((n, mid, hw), dtype=tdt, device=x.device)
+    y = B.new_nhwc(n, 64, h, w, torch.bfloat16, x.device)
+    b1, b2, b3 = _bn_struct(bn_exp), _bn_struct(bn_dw), _bn_struct(bn_proj)
+    p75, p53 = _transform_ptrs(m75, m53)
+    P = n * hw
+    _call('mbconv expand 64->%d planar' % mid, 2.0 * P * 64 * mid, P * (64 + mid) * 2,
+          lambda: B.check(L.ofa_expand_planar_fwd(x.data_ptr(), t1.data_ptr(), we.data_ptr(), n, hw, mid, dt,
+                                                  byref(b1), act, st)))
+    _call('dw%dx%d C%d planar' % (ks, ks, mid), 2.0 * P * mid * ks * ks, 2 * P * mid * 2,
+          lambda: B.check(L.ofa_dw_planar_fwd(t1.data_ptr(), t2.data_ptr(), n, mid, h, w, B.fptr(w_dw), w_dw.shape[-1],
+                                              p75, p53, int(bool(transform_on)), ks, dt, byref(b2), act, st)))
+    _call('mbconv project %d->64 planar' % mid, 2.0 * P * 64 * mid, P * (mid + 64 + (64 if add_residual else 0)) * 2,
+          lambda: B.check(L.ofa_project_planar_fwd(t2.data_ptr(), x.data_ptr() if add_residual else None, y.data_ptr(),
+                                                   wp.data_ptr(), n, hw, mid, dt, byref(b3), st)))
     return y
 
 
