@@ -11,8 +11,8 @@
  *   - plain pointers and sizes only; all pointers are DEVICE pointers unless a name says host;
  *   - activations are addressed through explicit element strides (sn, sc, sh, sw), so NCHW,
  *     NHWC (torch channels_last) and channel-sliced views all work without copies; the tensor-core
- *     paths additionally require NHWC-dense bf16 and say so;
- *   - dtype codes: OFA_F32 = 0, OFA_BF16 = 1 (accumulation is always fp32);
+ *     paths additionally require NHWC-dense 16-bit (bf16 or fp16) and say so;
+ *   - dtype codes: OFA_F32 = 0, OFA_BF16 = 1, OFA_F16 = 2 (accumulation is always fp32);
  *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant, and
  *     keeps no global mutable state besides a per-thread error string / launch counter and a
  *     per-device cache of device attributes (nn.DataParallel calls in from one thread per GPU);
@@ -37,7 +37,7 @@ extern "C" {
 
 #define OFA_F32 0
 #define OFA_BF16 1
-#define OFA_F16 2 /* only as the storage type of the planar MBConv intermediates */
+#define OFA_F16 2 /* IEEE half: 16-bit activation storage with 3 more mantissa bits than bf16 */
 
 /* activation codes (ofa/utils.py:242-314 build_activation) */
 #define OFA_ACT_NONE 0
@@ -52,7 +52,7 @@ extern "C" {
 
 /* implementation selectors (testing / profiling); 0 picks the fastest valid one */
 #define OFA_IMPL_AUTO 0
-#define OFA_IMPL_SIMT 1 /* CUDA-core kernels: any layout, fp32 or bf16 I/O                      */
+#define OFA_IMPL_SIMT 1 /* CUDA-core kernels: any layout, fp32 / bf16 / fp16 I/O                */
 #define OFA_IMPL_FAST 2 /* TMA halo tiles (depthwise) / tcgen05+TMEM implicit GEMM (dense conv)  */
 #define OFA_IMPL_NHWC 3 /* ofa_mbconv_fwd only: the three NHWC kernels instead of the planar path */
 
@@ -105,7 +105,8 @@ int ofa_dw_active_filter(const float* w7, int32_t kmax, const float* m75, const 
  * (a2 [+a5 eval, +a6]) DynamicSeparableConv2d.forward — dynamic_op.py:73-84
  *   depthwise ks x ks, stride 1, dilation 1, pad ks/2, groups = C, filter derived on the fly from
  *   (w7, m75, m53) exactly as (a1).  x and y have C channels, same N/H/W.  epi may be NULL.
- *   OFA_IMPL_FAST requires NHWC-dense bf16 x and y and C % 64 == 0.
+ *   OFA_IMPL_FAST requires NHWC-dense bf16 x and y and C % 64 == 0 (the planar tensor-core depthwise
+ *   is ofa_dw_planar_fwd below).
  * ------------------------------------------------------------------------------------------- */
 int ofa_dw_fwd(const OfaTensor4* x, const OfaTensor4* y, const float* w7, int32_t kmax,
                const float* m75, const float* m53, int32_t transform_on, int32_t ks,
@@ -117,7 +118,8 @@ int ofa_dw_fwd(const OfaTensor4* x, const OfaTensor4* y, const float* w7, int32_
  *            — layers.py:94-98,120-151; utils.py:259-260,383-410
  *   w      fp32 weight addressed as w[o*w_so + i*w_si + ky*w_sh + kx*w_sw]: pass the FULL supernet
  *          parameter with its strides and the active Cin/Cout — the slice W[:Cout,:Cin] is never copied
- *   w_bf16 optional packed copy [ks*ks][cout_pad][cin_pad] bf16 made by ofa_pack_weight_bf16
+ *   w_bf16 optional packed 16-bit copy [ks*ks][cout_pad][cin_pad] in the SAME format as x (bf16 or fp16),
+ *          made by ofa_pack_weight_bf16 / ofa_pack_weight_16
  *          (required by OFA_IMPL_FAST; a derived cache owned by the caller)
  *   y      describes the tensor actually written: for PIXELSHUFFLE2 it has c = Cout/4, h = 2H, w = 2W;
  *          for PIXELUNSHUFFLE2 c = 4*Cout, h = H/2, w = W/2.  epi.residual is indexed like y.
@@ -148,6 +150,11 @@ int ofa_conv_kxk_fwd(const OfaConvArgs* a, int32_t impl, void* stream); /* any o
 int ofa_pack_weight_bf16(const float* w, int64_t w_so, int64_t w_si, int64_t w_sh, int64_t w_sw,
                          int32_t cin, int32_t cout, int32_t ks, int32_t cin_pad, int32_t cout_pad,
                          int32_t store, void* out_bf16, void* stream);
+/* same, into `dtype` = OFA_BF16 | OFA_F16: the packed copy handed to OFA_IMPL_FAST must have the 16-bit
+ * format of the activation tensor x (tcgen05 kind::f16 multiplies like formats) */
+int ofa_pack_weight_16(const float* w, int64_t w_so, int64_t w_si, int64_t w_sh, int64_t w_sw,
+                       int32_t cin, int32_t cout, int32_t ks, int32_t cin_pad, int32_t cout_pad,
+                       int32_t store, int32_t dtype, void* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (a5) DynamicBatchNorm2d.bn_forward in TRAINING mode — dynamic_op.py:148-167
@@ -167,7 +174,8 @@ int ofa_affine_act(const OfaTensor4* x, const OfaTensor4* y, const OfaEpilogue* 
 /* ---------------------------------------------------------------------------------------------
  * (a7 + a8) DynamicMBConvLayer.forward + MobileInvertedResidualBlock — dynamic_layers.py:70-84,
  * proxyless_nets.py:44-51, inference mode (BN folded): expand 1x1 -> BN -> ReLU6 -> elastic
- * depthwise -> BN -> ReLU6 -> project 1x1 -> BN (+ x).  NHWC-dense bf16 x / y with `cin` channels.
+ * depthwise -> BN -> ReLU6 -> project 1x1 -> BN (+ x).  NHWC-dense x / y with `cin` channels, both bf16
+ * or both fp16.
  *   w_exp  [Mmax, cin_max] fp32 (full), w_proj [cout_max, Mmax] fp32 (full); `mid` active channels
  *   bn_*   the three BatchNorm parameter sets (full width; prefixes are used)
  *   ws     caller-owned scratch of ofa_mbconv_workspace_bytes(...) bytes
@@ -209,21 +217,23 @@ int ofa_mbconv_fwd(const OfaMBConvArgs* a, int32_t impl, void* stream);
 
 /* The three stages of ofa_mbconv_fwd's planar tcgen05 path (cin = cout = 64, mid % 64 == 0, W % 8 == 0),
  * exported so that tests and profilers can drive them one by one.  "planar" = [N][C][H*W] dense, 16-bit
- * (`dtype` = OFA_BF16 | OFA_F16); "nhwc" = [N][H*W][64] dense bf16.
- *   pack    : w_exp[:mid,:64] -> bf16 [ceil(mid/128)*128][64], w_proj[:64,:mid] -> `dtype` [64][mid]
+ * (`dtype` = OFA_BF16 | OFA_F16); "nhwc" = [N][H*W][64] dense 16-bit (`trunk_dtype` = OFA_BF16 | OFA_F16).
+ *   pack    : w_exp[:mid,:64] -> `trunk_dtype` [ceil(mid/128)*128][64], w_proj[:64,:mid] -> `dtype` [64][mid]
  *   expand  : (a3 + a5 + a6) 1x1 64 -> mid, folded BN, activation            nhwc   -> planar
  *   dw      : (a1 + a2 + a5 + a6) elastic depthwise ks x ks, folded BN, act   planar -> planar
  *   project : (a4 + a5 + a8) 1x1 mid -> 64, folded BN, + residual (or NULL)   planar -> nhwc            */
 int ofa_mbconv_pack_weights(const float* w_exp, int64_t w_exp_so, int64_t w_exp_si, const float* w_proj,
-                            int64_t w_proj_so, int64_t w_proj_si, int32_t mid, int32_t dtype,
-                            void* wexp_packed, void* wproj_packed, void* stream);
+                            int64_t w_proj_so, int64_t w_proj_si, int32_t mid, int32_t trunk_dtype,
+                            int32_t dtype, void* wexp_packed, void* wproj_packed, void* stream);
 int ofa_expand_planar_fwd(const void* x_nhwc, void* y_planar, const void* wexp_packed, int32_t n, int32_t hw,
-                          int32_t mid, int32_t dtype, const OfaBn* bn, int32_t act, void* stream);
+                          int32_t mid, int32_t trunk_dtype, int32_t dtype, const OfaBn* bn, int32_t act,
+                          void* stream);
 int ofa_dw_planar_fwd(const void* x_planar, void* y_planar, int32_t n, int32_t c, int32_t h, int32_t w,
                       const float* w7, int32_t kmax, const float* m75, const float* m53, int32_t transform_on,
                       int32_t ks, int32_t dtype, const OfaBn* bn, int32_t act, void* stream);
 int ofa_project_planar_fwd(const void* x_planar, const void* res_nhwc, void* y_nhwc, const void* wproj_packed,
-                           int32_t n, int32_t hw, int32_t mid, int32_t dtype, const OfaBn* bn, void* stream);
+                           int32_t n, int32_t hw, int32_t mid, int32_t trunk_dtype, int32_t dtype,
+                           const OfaBn* bn, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (a14) backward of the path — autograd of dynamic_op.py:73-84,104-112,148-167

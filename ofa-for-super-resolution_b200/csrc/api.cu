@@ -196,13 +196,20 @@ int ofa_conv_kxk_fwd(const OfaConvArgs* a, int32_t impl, void* stream) { return 
 int ofa_pack_weight_bf16(const float* w, int64_t w_so, int64_t w_si, int64_t w_sh, int64_t w_sw, int32_t cin,
                          int32_t cout, int32_t ks, int32_t cin_pad, int32_t cout_pad, int32_t store, void* out,
                          void* stream) {
+  return ofa_pack_weight_16(w, w_so, w_si, w_sh, w_sw, cin, cout, ks, cin_pad, cout_pad, store, OFA_BF16, out, stream);
+}
+
+int ofa_pack_weight_16(const float* w, int64_t w_so, int64_t w_si, int64_t w_sh, int64_t w_sw, int32_t cin,
+                       int32_t cout, int32_t ks, int32_t cin_pad, int32_t cout_pad, int32_t store, int32_t dtype,
+                       void* out, void* stream) {
   int rc = require_device();
   if (rc) return rc;
-  OFA_REQUIRE(w && out, "ofa_pack_weight_bf16: null pointer");
+  OFA_REQUIRE(w && out, "ofa_pack_weight_16: null pointer");
+  OFA_REQUIRE(dtype == OFA_BF16 || dtype == OFA_F16, "ofa_pack_weight_16: dtype must be OFA_BF16 or OFA_F16");
   OFA_REQUIRE(cin_pad >= cin && cout_pad >= cout && cin >= 0 && cout >= 0 && ks >= 1, "bad pack dims");
   OFA_REQUIRE(store != OFA_STORE_PIXELSHUFFLE2 || cout % 4 == 0, "pixelshuffle pack needs cout %% 4 == 0");
-  return launch_pack_weight(w, w_so, w_si, w_sh, w_sw, cin, cout, ks, cin_pad, cout_pad, store, out,
-                            (cudaStream_t)stream);
+  return launch_pack_weight(w, w_so, w_si, w_sh, w_sw, cin, cout, ks, cin_pad, cout_pad, store,
+                            dtype == OFA_F16 ? 1 : 0, out, (cudaStream_t)stream);
 }
 
 int ofa_bn_stats(const OfaTensor4* x, float* mean, float* var, void* stream) {
@@ -249,8 +256,8 @@ int ofa_mbconv_fwd(const OfaMBConvArgs* a, int32_t impl, void* stream) {
   OFA_REQUIRE(a != nullptr, "ofa_mbconv_fwd: null args");
   if ((rc = check_tensor(&a->x, "x"))) return rc;
   if ((rc = check_tensor(&a->y, "y"))) return rc;
-  OFA_REQUIRE(is_nhwc_dense(&a->x) && is_nhwc_dense(&a->y) && a->x.dtype == OFA_BF16 && a->y.dtype == OFA_BF16,
-              "ofa_mbconv_fwd: x and y must be NHWC-dense bf16");
+  OFA_REQUIRE(is_nhwc_dense(&a->x) && is_nhwc_dense(&a->y) && is_16bit(a->x.dtype) && a->y.dtype == a->x.dtype,
+              "ofa_mbconv_fwd: x and y must be NHWC-dense and both bf16 or both fp16");
   OFA_REQUIRE(a->x.c == a->cin && a->y.c == a->cout, "ofa_mbconv_fwd: channel mismatch");
   OFA_REQUIRE(a->cin % 64 == 0 && a->mid % 64 == 0 && a->cout % 64 == 0 && a->mid <= 384 && a->cin <= 384 && a->cout <= 256,
               "ofa_mbconv_fwd: cin/mid/cout must be multiples of 64 (cin,mid <= 384, cout <= 256)");
@@ -273,20 +280,23 @@ int ofa_mbconv_fwd(const OfaMBConvArgs* a, int32_t impl, void* stream) {
   // ---- planar tcgen05 path: expand -> Toeplitz depthwise -> project around channel-planar intermediates
   if (impl != OFA_IMPL_SIMT && impl != OFA_IMPL_NHWC && mbconv_planar_supported(a)) {
     const int f16 = (a->mid_dtype == OFA_BF16) ? 0 : 1;
+    const int tf16 = a->x.dtype == OFA_F16 ? 1 : 0;
     const int HW = a->x.h * a->x.w;
     const int mid_pad = (a->mid + 127) / 128 * 128;
     if ((rc = launch_pack_block_weights(a->w_exp, a->w_exp_so, a->w_exp_si, a->w_proj, a->w_proj_so, a->w_proj_si,
-                                        a->cin, a->mid, a->cout, mid_pad, f16, wexp_p, wproj_p, st))) return rc;
-    if ((rc = launch_expand_planar(a->x.ptr, t1, wexp_p, a->x.n, HW, a->mid, f16, &a->bn_exp, a->act, st))) return rc;
+                                        a->cin, a->mid, a->cout, mid_pad, tf16, f16, wexp_p, wproj_p, st))) return rc;
+    if ((rc = launch_expand_planar(a->x.ptr, t1, wexp_p, a->x.n, HW, a->mid, tf16, f16, &a->bn_exp, a->act, st)))
+      return rc;
     if ((rc = launch_dw_planar(t1, t2, a->x.n, a->mid, a->x.h, a->x.w, a->w_dw, a->kmax, a->m75, a->m53,
                                a->transform_on, a->ks, f16, &a->bn_dw, a->act, st))) return rc;
-    return launch_project_planar(t2, a->add_residual ? a->x.ptr : nullptr, a->y.ptr, wproj_p, a->x.n, HW, a->mid, f16,
-                                 &a->bn_proj, st);
+    return launch_project_planar(t2, a->add_residual ? a->x.ptr : nullptr, a->y.ptr, wproj_p, a->x.n, HW, a->mid, tf16,
+                                 f16, &a->bn_proj, st);
   }
   if (impl == OFA_IMPL_NHWC) impl = OFA_IMPL_AUTO;
   // pack the active weight slices (tiny) — the slice W[:mid,:cin] is read in place from the full parameter
-  if ((rc = launch_pack_weight(a->w_exp, a->w_exp_so, a->w_exp_si, 0, 0, a->cin, a->mid, 1, a->cin, a->mid, OFA_STORE_PLAIN, wexp_p, st))) return rc;
-  if ((rc = launch_pack_weight(a->w_proj, a->w_proj_so, a->w_proj_si, 0, 0, a->mid, a->cout, 1, a->mid, a->cout, OFA_STORE_PLAIN, wproj_p, st))) return rc;
+  const int xf16 = a->x.dtype == OFA_F16 ? 1 : 0;
+  if ((rc = launch_pack_weight(a->w_exp, a->w_exp_so, a->w_exp_si, 0, 0, a->cin, a->mid, 1, a->cin, a->mid, OFA_STORE_PLAIN, xf16, wexp_p, st))) return rc;
+  if ((rc = launch_pack_weight(a->w_proj, a->w_proj_so, a->w_proj_si, 0, 0, a->mid, a->cout, 1, a->mid, a->cout, OFA_STORE_PLAIN, xf16, wproj_p, st))) return rc;
 
   OfaTensor4 mid1 = a->x, mid2 = a->x;
   mid1.ptr = t1; mid2.ptr = t2;
@@ -295,7 +305,7 @@ int ofa_mbconv_fwd(const OfaMBConvArgs* a, int32_t impl, void* stream) {
   mid1.sw = mid2.sw = a->mid;
   mid1.sh = mid2.sh = (int64_t)a->x.w * a->mid;
   mid1.sn = mid2.sn = (int64_t)a->x.h * a->x.w * a->mid;
-  mid1.dtype = mid2.dtype = OFA_BF16;
+  mid1.dtype = mid2.dtype = a->x.dtype;
 
   OfaConvArgs c1;
   memset(&c1, 0, sizeof(c1));
@@ -328,15 +338,16 @@ static int dtype16_flag(int32_t dtype, int* f16) {
 }
 
 int ofa_mbconv_pack_weights(const float* w_exp, int64_t e_so, int64_t e_si, const float* w_proj, int64_t p_so,
-                            int64_t p_si, int32_t mid, int32_t dtype, void* wexp_packed, void* wproj_packed,
-                            void* stream) {
-  int rc = require_device(), f16 = 0;
+                            int64_t p_si, int32_t mid, int32_t trunk_dtype, int32_t dtype, void* wexp_packed,
+                            void* wproj_packed, void* stream) {
+  int rc = require_device(), f16 = 0, tf16 = 0;
   if (rc) return rc;
   if ((rc = dtype16_flag(dtype, &f16))) return rc;
+  if ((rc = dtype16_flag(trunk_dtype, &tf16))) return rc;
   OFA_REQUIRE(w_exp && w_proj && wexp_packed && wproj_packed, "ofa_mbconv_pack_weights: null pointer");
   OFA_REQUIRE(mid % 64 == 0 && mid >= 64 && mid <= 384, "mid must be a multiple of 64 in [64, 384]");
-  return launch_pack_block_weights(w_exp, e_so, e_si, w_proj, p_so, p_si, 64, mid, 64, (mid + 127) / 128 * 128, f16,
-                                   wexp_packed, wproj_packed, (cudaStream_t)stream);
+  return launch_pack_block_weights(w_exp, e_so, e_si, w_proj, p_so, p_si, 64, mid, 64, (mid + 127) / 128 * 128, tf16,
+                                   f16, wexp_packed, wproj_packed, (cudaStream_t)stream);
 }
 
 static int planar_dims_ok(int32_t n, int64_t hw, int32_t mid) {
@@ -346,15 +357,17 @@ static int planar_dims_ok(int32_t n, int64_t hw, int32_t mid) {
 }
 
 int ofa_expand_planar_fwd(const void* x_nhwc, void* y_planar, const void* wexp_packed, int32_t n, int32_t hw,
-                          int32_t mid, int32_t dtype, const OfaBn* bn, int32_t act, void* stream) {
-  int rc = require_device(), f16 = 0;
+                          int32_t mid, int32_t trunk_dtype, int32_t dtype, const OfaBn* bn, int32_t act,
+                          void* stream) {
+  int rc = require_device(), f16 = 0, tf16 = 0;
   if (rc) return rc;
   if ((rc = dtype16_flag(dtype, &f16))) return rc;
+  if ((rc = dtype16_flag(trunk_dtype, &tf16))) return rc;
   if ((rc = planar_dims_ok(n, hw, mid))) return rc;
   OFA_REQUIRE(x_nhwc && y_planar && wexp_packed && bn, "ofa_expand_planar_fwd: null pointer");
   OFA_REQUIRE(((uintptr_t)x_nhwc & 15) == 0 && ((uintptr_t)y_planar & 15) == 0 && ((uintptr_t)wexp_packed & 15) == 0,
               "ofa_expand_planar_fwd: pointers must be 16-byte aligned");
-  return launch_expand_planar(x_nhwc, y_planar, wexp_packed, n, hw, mid, f16, bn, act, (cudaStream_t)stream);
+  return launch_expand_planar(x_nhwc, y_planar, wexp_packed, n, hw, mid, tf16, f16, bn, act, (cudaStream_t)stream);
 }
 
 int ofa_dw_planar_fwd(const void* x_planar, void* y_planar, int32_t n, int32_t c, int32_t h, int32_t w,
@@ -372,15 +385,18 @@ int ofa_dw_planar_fwd(const void* x_planar, void* y_planar, int32_t n, int32_t c
 }
 
 int ofa_project_planar_fwd(const void* x_planar, const void* res_nhwc, void* y_nhwc, const void* wproj_packed,
-                           int32_t n, int32_t hw, int32_t mid, int32_t dtype, const OfaBn* bn, void* stream) {
-  int rc = require_device(), f16 = 0;
+                           int32_t n, int32_t hw, int32_t mid, int32_t trunk_dtype, int32_t dtype, const OfaBn* bn,
+                           void* stream) {
+  int rc = require_device(), f16 = 0, tf16 = 0;
   if (rc) return rc;
   if ((rc = dtype16_flag(dtype, &f16))) return rc;
+  if ((rc = dtype16_flag(trunk_dtype, &tf16))) return rc;
   if ((rc = planar_dims_ok(n, hw, mid))) return rc;
   OFA_REQUIRE(x_planar && y_nhwc && wproj_packed && bn, "ofa_project_planar_fwd: null pointer");
   OFA_REQUIRE(((uintptr_t)x_planar & 15) == 0 && ((uintptr_t)y_nhwc & 15) == 0 && ((uintptr_t)res_nhwc & 15) == 0 &&
                   ((uintptr_t)wproj_packed & 15) == 0, "pointers must be 16-byte aligned");
-  return launch_project_planar(x_planar, res_nhwc, y_nhwc, wproj_packed, n, hw, mid, f16, bn, (cudaStream_t)stream);
+  return launch_project_planar(x_planar, res_nhwc, y_nhwc, wproj_packed, n, hw, mid, tf16, f16, bn,
+                               (cudaStream_t)stream);
 }
 
 int ofa_dw_bwd_filter(const OfaTensor4* x, const OfaTensor4* dy, int32_t ks, float* dw_active, void* stream) {

@@ -78,6 +78,7 @@ struct ConvTcParams {
   int bres_rows;         // weight rows per TMA box when resident
   int tmem_cols;
   int store, act, vec_store;
+  int f16;               // 16-bit storage format of x, the packed weights, y and the residual: 1 = fp16, 0 = bf16
   const float* gamma; const float* beta; const float* mean; const float* var; float eps;
   TV y;
   TV res;
@@ -120,16 +121,14 @@ __device__ __forceinline__ void emit16(const ConvTcParams& p, const float* s_sca
       const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        f[2 * i] += __uint_as_float(rr[i] << 16);
-        f[2 * i + 1] += __uint_as_float(rr[i] & 0xffff0000u);
+        const float2 r2 = unpack16(rr[i], p.f16);
+        f[2 * i] += r2.x;
+        f[2 * i + 1] += r2.y;
       }
     }
     uint32_t pk[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      __nv_bfloat162 b2 = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-      pk[i] = *reinterpret_cast<uint32_t*>(&b2);
-    }
+    for (int i = 0; i < 8; ++i) pk[i] = pack16(f[2 * i], f[2 * i + 1], p.f16);
     uint4* yp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y.ptr) + o);
     yp[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     yp[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
@@ -257,7 +256,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     // The whole warp walks the loops (warp-uniform control flow, so descriptors live in uniform
     // registers); only the tcgen05 instructions are predicated on one lane.
     const uint32_t leader = (lane == 0) ? 1u : 0u;
-    const uint32_t idesc = ptx::umma_idesc_bf16(128, p.BN);
+    const uint32_t idesc = ptx::umma_idesc_f16(128, p.BN, p.f16 ? 0 : 1, p.f16 ? 0 : 1, 0, 0);
     const uint32_t sbo_a = (uint32_t)p.halo_w * 128;
     const uint32_t sB_addr = ptx::smem_u32(sB);
     int as = 0, bs = 0, acc = 0;
@@ -364,8 +363,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                 const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                  f[q4 * 8 + 2 * i] += __uint_as_float(rr[i] << 16);
-                  f[q4 * 8 + 2 * i + 1] += __uint_as_float(rr[i] & 0xffff0000u);
+                  const float2 r2 = unpack16(rr[i], p.f16);
+                  f[q4 * 8 + 2 * i] += r2.x;
+                  f[q4 * 8 + 2 * i + 1] += r2.y;
                 }
               }
             }
@@ -373,10 +373,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             for (int k = 0; k < 4; ++k) {
               uint32_t pk[4];
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                __nv_bfloat162 b2 = __floats2bfloat162_rn(f[k * 8 + 2 * i], f[k * 8 + 2 * i + 1]);
-                pk[i] = *reinterpret_cast<uint32_t*>(&b2);
-              }
+              for (int i = 0; i < 4; ++i) pk[i] = pack16(f[k * 8 + 2 * i], f[k * 8 + 2 * i + 1], p.f16);
               *reinterpret_cast<uint4*>(stage + lane * 64 + ((k ^ ((lane >> 1) & 3)) << 4)) =
                   make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
@@ -427,7 +424,7 @@ int pick_bn(int cout_pad) {
 bool conv_tc_supported(const OfaConvArgs* a) {
   if (!a->w_bf16) return false;
   if (a->flip) return false;
-  if (a->x.dtype != OFA_BF16 || !is_nhwc_dense(&a->x)) return false;
+  if (!is_16bit(a->x.dtype) || !is_nhwc_dense(&a->x)) return false;
   if ((reinterpret_cast<uintptr_t>(a->x.ptr) & 15) || (reinterpret_cast<uintptr_t>(a->w_bf16) & 15)) return false;
   if (a->cin % BK != 0 || a->cin_pad != a->cin) return false;
   if (a->ks > 7 || !(a->ks & 1)) return false;
@@ -454,6 +451,7 @@ int launch_conv_tc(const OfaConvArgs* a, cudaStream_t st) {
   p.a_bytes = p.halo_w * p.halo_h * 128;
   p.store = a->store;
   p.act = a->epi.act;
+  p.f16 = a->x.dtype == OFA_F16 ? 1 : 0;
   p.gamma = a->epi.gamma; p.beta = a->epi.beta; p.mean = a->epi.mean; p.var = a->epi.var; p.eps = a->epi.eps;
   p.y = make_tv(&a->y);
   p.res = a->epi.residual ? make_tv(a->epi.residual) : null_tv();
@@ -487,11 +485,11 @@ int launch_conv_tc(const OfaConvArgs* a, cudaStream_t st) {
   const size_t smem = (size_t)fixed + (size_t)p.a_stages * a_stride +
                       (p.b_resident ? (size_t)b_all : (size_t)p.b_stages * b_bytes);
 
-  bool vec = a->y.dtype == OFA_BF16 && a->y.sc == 1 && (reinterpret_cast<uintptr_t>(a->y.ptr) & 15) == 0 &&
+  bool vec = a->y.dtype == a->x.dtype && a->y.sc == 1 && (reinterpret_cast<uintptr_t>(a->y.ptr) & 15) == 0 &&
              a->y.sw % 8 == 0 && a->y.sh % 8 == 0 && a->y.sn % 8 == 0 && a->store != OFA_STORE_PIXELUNSHUFFLE2;
   if (a->epi.residual) {
     const OfaTensor4* r = a->epi.residual;
-    vec = vec && r->dtype == OFA_BF16 && r->sc == 1 && (reinterpret_cast<uintptr_t>(r->ptr) & 15) == 0 &&
+    vec = vec && r->dtype == a->x.dtype && r->sc == 1 && (reinterpret_cast<uintptr_t>(r->ptr) & 15) == 0 &&
           r->sw % 8 == 0 && r->sh % 8 == 0 && r->sn % 8 == 0;
   }
   p.vec_store = vec ? 1 : 0;
@@ -501,8 +499,8 @@ int launch_conv_tc(const OfaConvArgs* a, cudaStream_t st) {
     uint64_t dims[4] = {(uint64_t)p.cin, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.N};
     uint64_t strides[3] = {(uint64_t)p.cin * 2, (uint64_t)p.W * p.cin * 2, (uint64_t)p.H * p.W * p.cin * 2};
     uint32_t box[4] = {BK, (uint32_t)p.halo_w, (uint32_t)p.halo_h, 1};
-    int rc = encode_tmap(&tx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a->x.ptr, dims, strides, box,
-                         CU_TENSOR_MAP_SWIZZLE_128B);
+    int rc = encode_tmap(&tx, p.f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a->x.ptr,
+                         dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
   {
@@ -511,8 +509,8 @@ int launch_conv_tc(const OfaConvArgs* a, cudaStream_t st) {
     p.bres_rows = a->cout_pad <= 256 ? a->cout_pad : p.BN;
     uint32_t rows = p.b_resident ? (uint32_t)p.bres_rows : (uint32_t)p.BN;
     uint32_t box[3] = {BK, rows, 1};
-    int rc = encode_tmap(&tw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(a->w_bf16), dims, strides, box,
-                         CU_TENSOR_MAP_SWIZZLE_128B);
+    int rc = encode_tmap(&tw, p.f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                         const_cast<void*>(a->w_bf16), dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
   OFA_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

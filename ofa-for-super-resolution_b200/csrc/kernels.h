@@ -13,7 +13,8 @@ int launch_conv_simt(const TV& x, const TV& y, const float* w, long long w_so, l
                      long long w_sh, long long w_sw, int cin, int cout, int ks, int flip, int store,
                      const Epi& epi, cudaStream_t st);
 int launch_pack_weight(const float* w, long long w_so, long long w_si, long long w_sh, long long w_sw,
-                       int cin, int cout, int ks, int cin_pad, int cout_pad, int store, void* out, cudaStream_t st);
+                       int cin, int cout, int ks, int cin_pad, int cout_pad, int store, int f16, void* out,
+                       cudaStream_t st);
 int launch_affine_act(const TV& x, const TV& y, const Epi& epi, int store, cudaStream_t st);
 int launch_bn_stats(const TV& x, float* mean, float* var, cudaStream_t st);
 int launch_bn_update_running(const float* mean, const float* var, long long count, float* rm, float* rv,
@@ -43,13 +44,13 @@ int launch_conv_tc(const OfaConvArgs* a, cudaStream_t st);
 // ---- mbconv_planar.cu : MBConv block on channel-planar 16-bit intermediates (tcgen05) ---------------
 bool mbconv_planar_supported(const OfaMBConvArgs* a);
 int launch_pack_block_weights(const float* w_exp, long long e_so, long long e_si, const float* w_proj,
-                              long long p_so, long long p_si, int cin, int mid, int cout, int mid_pad, int f16,
-                              void* wexp_p, void* wproj_p, cudaStream_t st);
-int launch_expand_planar(const void* x, void* y, const void* wexp_p, int N, int HW, int mid, int f16,
+                              long long p_so, long long p_si, int cin, int mid, int cout, int mid_pad, int trunk_f16,
+                              int f16, void* wexp_p, void* wproj_p, cudaStream_t st);
+int launch_expand_planar(const void* x, void* y, const void* wexp_p, int N, int HW, int mid, int trunk_f16, int f16,
                          const OfaBn* bn, int act, cudaStream_t st);
 int launch_dw_planar(const void* x, void* y, int N, int C, int H, int W, const float* w7, int kmax, const float* m75,
                      const float* m53, int transform_on, int ks, int f16, const OfaBn* bn, int act, cudaStream_t st);
 int launch_project_planar(const void* x, const void* res, void* y, const void* wproj_p, int N, int HW, int mid,
-                          int f16, const OfaBn* bn, cudaStream_t st);
+                          int trunk_f16, int f16, const OfaBn* bn, cudaStream_t st);
 
 }  // namespace ofa

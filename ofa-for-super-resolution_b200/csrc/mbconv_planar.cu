@@ -25,28 +25,11 @@
 #include "kernels.h"
 #include "sm100_ptx.cuh"
 
-#include <cuda_fp16.h>
 #include <string.h>
 
 namespace ofa {
 namespace {
 
-__device__ __forceinline__ uint32_t pack16(float a, float b, int f16) {
-  if (f16) {
-    __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
-  }
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
-__device__ __forceinline__ uint16_t cvt16(float a, int f16) {
-  if (f16) {
-    __half h = __float2half_rn(a);
-    return *reinterpret_cast<uint16_t*>(&h);
-  }
-  __nv_bfloat16 h = __float2bfloat16_rn(a);
-  return *reinterpret_cast<uint16_t*>(&h);
-}
 __device__ __forceinline__ void bn_fold(const float* gamma, const float* beta, const float* mean, const float* var,
                                         float eps, int c, float& scale, float& shift) {
   const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
@@ -60,13 +43,13 @@ __device__ __forceinline__ void bn_fold(const float* gamma, const float* beta, c
 // ==================================================================================================
 __global__ void pack_block_weights_kernel(const float* __restrict__ w_exp, long long e_so, long long e_si,
                                           const float* __restrict__ w_proj, long long p_so, long long p_si,
-                                          int cin, int mid, int cout, int mid_pad, int f16,
-                                          __nv_bfloat16* __restrict__ out_exp, uint16_t* __restrict__ out_proj) {
+                                          int cin, int mid, int cout, int mid_pad, int trunk_f16, int f16,
+                                          uint16_t* __restrict__ out_exp, uint16_t* __restrict__ out_proj) {
   const int n_exp = mid_pad * cin, n_proj = cout * mid;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_exp + n_proj; i += gridDim.x * blockDim.x) {
     if (i < n_exp) {
       const int o = i / cin, ci = i - o * cin;
-      out_exp[i] = __float2bfloat16_rn(o < mid ? w_exp[o * e_so + ci * e_si] : 0.f);
+      out_exp[i] = cvt16(o < mid ? w_exp[o * e_so + ci * e_si] : 0.f, trunk_f16);
     } else {
       const int j = i - n_exp;
       const int o = j / mid, ci = j - o * mid;
@@ -87,7 +70,7 @@ constexpr int EX_SBUF_BYTES = 32 * 128;      // per-warp store staging: 32 chann
 constexpr int EX_MAX_MT = 3;
 
 struct ExpandParams {
-  int N, HW, mid, mt, f16, act;
+  int N, HW, mid, mt, f16, xf16, act;
   const float* gamma; const float* beta; const float* mean; const float* var; float eps;
   int tiles_per_img;
 };
@@ -140,7 +123,8 @@ expand_planar_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     }
   } else if (warp == 1) {
     const uint32_t leader = (lane == 0) ? 1u : 0u;
-    const uint32_t idesc = ptx::umma_idesc_f16(128, EX_NPIX, 1, 1, 0, 0);
+    const int xfmt = p.xf16 ? 0 : 1;
+    const uint32_t idesc = ptx::umma_idesc_f16(128, EX_NPIX, xfmt, xfmt, 0, 0);
     const uint32_t sW_addr = ptx::smem_u32(sW), sX_addr = ptx::smem_u32(sX);
     int s = 0, acc = 0; uint32_t ph = 0, accph = 0;
     ptx::mbar_wait(w_bar, 0);
@@ -472,7 +456,7 @@ constexpr int PJ_R_BYTES = PJ_MPIX * 128;     // residual / output staging tile
 constexpr int PJ_THREADS = 6 * 32;            // TMA, MMA, 4 epilogue warps
 
 struct ProjectParams {
-  int N, HW, mid, kcs, f16, has_res;
+  int N, HW, mid, kcs, f16, yf16, has_res;
   const float* gamma; const float* beta; const float* mean; const float* var; float eps;
   int tiles_per_img;
 };
@@ -606,10 +590,10 @@ project_planar_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int ch = j * 8 + 2 * i;
-          const float a = fmaf(__uint_as_float(v[ch]), s_scale[ch], s_shift[ch]) + __uint_as_float(rr[i] << 16);
-          const float b = fmaf(__uint_as_float(v[ch + 1]), s_scale[ch + 1], s_shift[ch + 1]) +
-                          __uint_as_float(rr[i] & 0xffff0000u);
-          pk[i] = pack16(a, b, 0);
+          const float2 r2 = unpack16(rr[i], p.yf16);   // rr == 0 -> (0, 0) in either format
+          const float a = fmaf(__uint_as_float(v[ch]), s_scale[ch], s_shift[ch]) + r2.x;
+          const float b = fmaf(__uint_as_float(v[ch + 1]), s_scale[ch + 1], s_shift[ch + 1]) + r2.y;
+          pk[i] = pack16(a, b, p.yf16);
         }
         *q = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
@@ -652,21 +636,21 @@ static CUtensorMapDataType dt16(int f16) {
 }
 
 int launch_pack_block_weights(const float* w_exp, long long e_so, long long e_si, const float* w_proj,
-                              long long p_so, long long p_si, int cin, int mid, int cout, int mid_pad, int f16,
-                              void* wexp_p, void* wproj_p, cudaStream_t st) {
+                              long long p_so, long long p_si, int cin, int mid, int cout, int mid_pad, int trunk_f16,
+                              int f16, void* wexp_p, void* wproj_p, cudaStream_t st) {
   const int total = mid_pad * cin + cout * mid;
   pack_block_weights_kernel<<<(total + 255) / 256, 256, 0, st>>>(
-      w_exp, e_so, e_si, w_proj, p_so, p_si, cin, mid, cout, mid_pad, f16,
-      reinterpret_cast<__nv_bfloat16*>(wexp_p), reinterpret_cast<uint16_t*>(wproj_p));
+      w_exp, e_so, e_si, w_proj, p_so, p_si, cin, mid, cout, mid_pad, trunk_f16, f16,
+      reinterpret_cast<uint16_t*>(wexp_p), reinterpret_cast<uint16_t*>(wproj_p));
   return check_launch("pack_block_weights_kernel");
 }
 
 // x: NHWC bf16 [N,H,W,64];  y: planar [N][mid][H*W] 16-bit
-int launch_expand_planar(const void* x, void* y, const void* wexp_p, int N, int HW, int mid, int f16,
+int launch_expand_planar(const void* x, void* y, const void* wexp_p, int N, int HW, int mid, int trunk_f16, int f16,
                          const OfaBn* bn, int act, cudaStream_t st) {
   ExpandParams p;
   memset(&p, 0, sizeof(p));
-  p.N = N; p.HW = HW; p.mid = mid; p.mt = (mid + 127) / 128; p.f16 = f16; p.act = act;
+  p.N = N; p.HW = HW; p.mid = mid; p.mt = (mid + 127) / 128; p.f16 = f16; p.xf16 = trunk_f16; p.act = act;
   p.gamma = bn->gamma; p.beta = bn->beta; p.mean = bn->mean; p.var = bn->var; p.eps = bn->eps;
   p.tiles_per_img = (HW + EX_NPIX - 1) / EX_NPIX;
   CUtensorMap tx, tw, ty;
@@ -675,14 +659,14 @@ int launch_expand_planar(const void* x, void* y, const void* wexp_p, int N, int 
     uint64_t dims[3] = {64, (uint64_t)HW, (uint64_t)N};
     uint64_t str[2] = {128, (uint64_t)HW * 128};
     uint32_t box[3] = {64, EX_NPIX, 1};
-    if ((rc = encode_tmap(&tx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(x), dims, str, box,
+    if ((rc = encode_tmap(&tx, dt16(trunk_f16), 3, const_cast<void*>(x), dims, str, box,
                           CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   }
   {
     uint64_t dims[3] = {64, (uint64_t)p.mt * 128, 1};
     uint64_t str[2] = {128, (uint64_t)p.mt * 128 * 128};
     uint32_t box[3] = {64, 128, 1};
-    if ((rc = encode_tmap(&tw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(wexp_p), dims, str, box,
+    if ((rc = encode_tmap(&tw, dt16(trunk_f16), 3, const_cast<void*>(wexp_p), dims, str, box,
                           CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   }
   {
@@ -752,10 +736,10 @@ int launch_dw_planar(const void* x, void* y, int N, int C, int H, int W, const f
 
 // x: planar [N][mid][H*W] 16-bit; res / y: NHWC bf16 [N,H*W,64]
 int launch_project_planar(const void* x, const void* res, void* y, const void* wproj_p, int N, int HW, int mid,
-                          int f16, const OfaBn* bn, cudaStream_t st) {
+                          int trunk_f16, int f16, const OfaBn* bn, cudaStream_t st) {
   ProjectParams p;
   memset(&p, 0, sizeof(p));
-  p.N = N; p.HW = HW; p.mid = mid; p.kcs = mid / 64; p.f16 = f16; p.has_res = res ? 1 : 0;
+  p.N = N; p.HW = HW; p.mid = mid; p.kcs = mid / 64; p.f16 = f16; p.yf16 = trunk_f16; p.has_res = res ? 1 : 0;
   p.gamma = bn->gamma; p.beta = bn->beta; p.mean = bn->mean; p.var = bn->var; p.eps = bn->eps;
   p.tiles_per_img = (HW + PJ_MPIX - 1) / PJ_MPIX;
   CUtensorMap ta, tw, tr, ty;
@@ -778,10 +762,9 @@ int launch_project_planar(const void* x, const void* res, void* y, const void* w
     uint64_t dims[3] = {64, (uint64_t)HW, (uint64_t)N};
     uint64_t str[2] = {128, (uint64_t)HW * 128};
     uint32_t box[3] = {64, PJ_MPIX, 1};
-    if ((rc = encode_tmap(&tr, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(res ? res : y), dims, str, box,
+    if ((rc = encode_tmap(&tr, dt16(trunk_f16), 3, const_cast<void*>(res ? res : y), dims, str, box,
                           CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-    if ((rc = encode_tmap(&ty, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, y, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)))
-      return rc;
+    if ((rc = encode_tmap(&ty, dt16(trunk_f16), 3, y, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   }
   const size_t smem = 1024 + PJ_A_STAGES * PJ_A_BYTES + PJ_MAX_KC * 8192 + 2 * PJ_R_BYTES + 128 * 4 + 256;
   OFA_CUDA(cudaFuncSetAttribute(project_planar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

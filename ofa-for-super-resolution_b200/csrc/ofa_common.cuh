@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
@@ -45,11 +46,14 @@ struct TV {
   }
   __device__ __forceinline__ float ld(long long o) const {
     if (dtype == OFA_F32) return reinterpret_cast<const float*>(ptr)[o];
+    if (dtype == OFA_F16) return __half2float(reinterpret_cast<const __half*>(ptr)[o]);
     return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(ptr)[o]);
   }
   __device__ __forceinline__ void st(long long o, float v) const {
     if (dtype == OFA_F32)
       reinterpret_cast<float*>(ptr)[o] = v;
+    else if (dtype == OFA_F16)
+      reinterpret_cast<__half*>(ptr)[o] = __float2half_rn(v);
     else
       reinterpret_cast<__nv_bfloat16*>(ptr)[o] = __float2bfloat16_rn(v);
   }
@@ -76,11 +80,36 @@ inline bool c_inner(const OfaTensor4* t) { return t->sc == 1; }
 inline int check_tensor(const OfaTensor4* t, const char* name) {
   if (!t) return fail(OFA_ERR_ARG, "%s: null tensor", name);
   if (!t->ptr) return fail(OFA_ERR_ARG, "%s: null data pointer", name);
-  if (t->dtype != OFA_F32 && t->dtype != OFA_BF16) return fail(OFA_ERR_ARG, "%s: bad dtype %d", name, t->dtype);
+  if (t->dtype != OFA_F32 && t->dtype != OFA_BF16 && t->dtype != OFA_F16)
+    return fail(OFA_ERR_ARG, "%s: bad dtype %d", name, t->dtype);
   if (t->n < 0 || t->c < 0 || t->h < 0 || t->w < 0) return fail(OFA_ERR_ARG, "%s: negative extent", name);
   return OFA_OK;
 }
 inline long long numel(const OfaTensor4* t) { return (long long)t->n * t->c * t->h * t->w; }
+
+inline bool is_16bit(int dtype) { return dtype == OFA_BF16 || dtype == OFA_F16; }
+
+// two packed 16-bit floats (bf16 or fp16) <-> two fp32
+__device__ __forceinline__ uint32_t pack16(float a, float b, int f16) {
+  if (f16) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack16(uint32_t u, int f16) {
+  if (f16) return __half22float2(*reinterpret_cast<const __half2*>(&u));
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+__device__ __forceinline__ uint16_t cvt16(float a, int f16) {
+  if (f16) {
+    __half h = __float2half_rn(a);
+    return *reinterpret_cast<uint16_t*>(&h);
+  }
+  __nv_bfloat16 h = __float2bfloat16_rn(a);
+  return *reinterpret_cast<uint16_t*>(&h);
+}
 
 // ------------------------------------------------------------------------------------------------
 // epilogue on the device: per-channel affine (BN fold) + activation + residual

@@ -234,8 +234,8 @@ int launch_conv_simt(const TV& x, const TV& y, const float* w, long long w_so, l
 // =================================================================================================
 __global__ void pack_weight_kernel(const float* __restrict__ w, long long w_so, long long w_si,
                                    long long w_sh, long long w_sw, int cin, int cout, int ks,
-                                   int cin_pad, int cout_pad, int store,
-                                   __nv_bfloat16* __restrict__ out) {
+                                   int cin_pad, int cout_pad, int store, int f16,
+                                   uint16_t* __restrict__ out) {
   long long total = (long long)ks * ks * cout_pad * cin_pad;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -252,19 +252,19 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, long long w_so, 
       if (store == OFA_STORE_PIXELSHUFFLE2) { int q = cout >> 2; oo = 4 * (o % q) + o / q; }
       v = w[oo * w_so + ci * w_si + ky * w_sh + kx * w_sw];
     }
-    out[i] = __float2bfloat16_rn(v);
+    out[i] = cvt16(v, f16);
   }
 }
 
 int launch_pack_weight(const float* w, long long w_so, long long w_si, long long w_sh, long long w_sw,
-                       int cin, int cout, int ks, int cin_pad, int cout_pad, int store, void* out,
+                       int cin, int cout, int ks, int cin_pad, int cout_pad, int store, int f16, void* out,
                        cudaStream_t st) {
   long long total = (long long)ks * ks * cout_pad * cin_pad;
   if (total == 0) return OFA_OK;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 1184) blocks = 1184;
-  pack_weight_kernel<<<blocks, 256, 0, st>>>(w, w_so, w_si, w_sh, w_sw, cin, cout, ks, cin_pad, cout_pad, store,
-                                             reinterpret_cast<__nv_bfloat16*>(out));
+  pack_weight_kernel<<<blocks, 256, 0, st>>>(w, w_so, w_si, w_sh, w_sw, cin, cout, ks, cin_pad, cout_pad, store, f16,
+                                             reinterpret_cast<uint16_t*>(out));
   return check_launch("pack_weight_kernel");
 }
 

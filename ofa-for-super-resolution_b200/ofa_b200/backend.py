@@ -74,6 +74,8 @@ SYMBOLS = {
     'ofa_conv_kxk_fwd': (c_int32, [POINTER(OfaConvArgs), c_int32, c_void_p]),
     'ofa_pack_weight_bf16': (c_int32, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int32, c_int32,
                                        c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    'ofa_pack_weight_16': (c_int32, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int32, c_int32,
+                                     c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     'ofa_bn_stats': (c_int32, [_T4, c_void_p, c_void_p, c_void_p]),
     'ofa_bn_update_running': (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_float, c_int32,
                                         c_void_p]),
@@ -81,13 +83,13 @@ SYMBOLS = {
     'ofa_mbconv_workspace_bytes': (c_int64, [c_int32] * 6),
     'ofa_mbconv_fwd': (c_int32, [POINTER(OfaMBConvArgs), c_int32, c_void_p]),
     'ofa_mbconv_pack_weights': (c_int32, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int32, c_int32,
-                                          c_void_p, c_void_p, c_void_p]),
-    'ofa_expand_planar_fwd': (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                                          c_int32, c_void_p, c_void_p, c_void_p]),
+    'ofa_expand_planar_fwd': (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
                                         POINTER(OfaBn), c_int32, c_void_p]),
     'ofa_dw_planar_fwd': (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32,
                                     c_void_p, c_void_p, c_int32, c_int32, c_int32, POINTER(OfaBn), c_int32, c_void_p]),
     'ofa_project_planar_fwd': (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
-                                         POINTER(OfaBn), c_void_p]),
+                                         c_int32, POINTER(OfaBn), c_void_p]),
     'ofa_dw_bwd_data': (c_int32, [_T4, _T4, c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_int32,
                                   c_void_p]),
     'ofa_dw_bwd_filter': (c_int32, [_T4, _T4, c_int32, c_void_p, c_void_p]),
@@ -134,7 +136,13 @@ def _dtype_code(t):
         return OFA_F32
     if t.dtype == torch.bfloat16:
         return OFA_BF16
-    raise RuntimeError('libofa_sr_b200 supports float32 and bfloat16 activations, got %s' % t.dtype)
+    if t.dtype == torch.float16:
+        return OFA_F16
+    raise RuntimeError('libofa_sr_b200 supports float32, bfloat16 and float16 activations, got %s' % t.dtype)
+
+
+def dtype_code(dtype):
+    return {torch.float32: OFA_F32, torch.bfloat16: OFA_BF16, torch.float16: OFA_F16}[dtype]
 
 
 def t4(t):

@@ -92,7 +92,7 @@ class DynamicMBConvLayer(MyModule):
                 mid = self.inverted_bottleneck.conv.active_out_channel
                 exp = self.inverted_bottleneck.conv
                 bn_exp = self.inverted_bottleneck.bn.bn
-                fused_ok = (x.dtype == torch.bfloat16 and x.is_contiguous(memory_format=torch.channels_last)
+                fused_ok = (x.dtype in (torch.bfloat16, torch.float16) and x.is_contiguous(memory_format=torch.channels_last)
                             and in_channel % 64 == 0 and mid % 64 == 0 and cout % 64 == 0
                             and (residual is None or residual is x) and OF._state['impl'] != B.IMPL_SIMT)
                 if fused_ok:

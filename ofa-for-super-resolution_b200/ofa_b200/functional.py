@@ -16,13 +16,15 @@ import torch
 
 from . import backend as B
 
-_state = {'compute_dtype': torch.bfloat16, 'impl': B.IMPL_AUTO, 'mid_dtype': B.OFA_F16}
+_state = {'compute_dtype': torch.float16, 'impl': B.IMPL_AUTO, 'mid_dtype': B.OFA_F16}
 
 
 def set_compute_dtype(dtype):
-    """Activation storage type of the fused inference path: torch.bfloat16 (tensor-core path,
-    default) or torch.float32 (exact CUDA-core path).  Accumulation is fp32 either way."""
-    assert dtype in (torch.bfloat16, torch.float32)
+    """Activation storage type of the fused inference path: torch.float16 (tensor-core path, default:
+    meets the 0.01 dB PSNR criterion; |activation| must stay below 65504), torch.bfloat16 (same
+    kernels and speed, 3 fewer mantissa bits, fp32 range) or torch.float32 (exact CUDA-core path).
+    Accumulation is fp32 in every mode."""
+    assert dtype in (torch.bfloat16, torch.float16, torch.float32)
     _state['compute_dtype'] = dtype
 
 
@@ -331,7 +333,7 @@ def pixel_unshuffle2(x):
 # =================================================================================================
 
 class PackedWeightCache:
-    """bf16 [tap][cout_pad][cin_pad] copy of an active weight slice — a derived cache owned by the
+    """16-bit [tap][cout_pad][cin_pad] copy (in the activation's format) of an active weight slice — a derived cache owned by the
     module, rebuilt whenever the fp32 master changes (optimizer step / load_state_dict / re-sort)."""
 
     def __init__(self):
@@ -339,15 +341,15 @@ class PackedWeightCache:
         self._buf = None
         self.cin_pad = self.cout_pad = 0
 
-    def get(self, w, cin, cout, ks, store):
-        key = (w.data_ptr(), w._version, tuple(w.shape), cin, cout, ks, store, str(w.device))
+    def get(self, w, cin, cout, ks, store, dtype=torch.bfloat16):
+        key = (w.data_ptr(), w._version, tuple(w.shape), cin, cout, ks, store, str(w.device), dtype)
         if key != self._key:
             cin_pad = (cin + 63) // 64 * 64
             cout_pad = (cout + 15) // 16 * 16
-            buf = torch.empty((ks * ks, cout_pad, cin_pad), dtype=torch.bfloat16, device=w.device)
+            buf = torch.empty((ks * ks, cout_pad, cin_pad), dtype=dtype, device=w.device)
             so, si, sh, sw = w.stride()
-            B.check(B.lib().ofa_pack_weight_bf16(B.fptr(w), so, si, sh, sw, cin, cout, ks, cin_pad, cout_pad,
-                                                 store, buf.data_ptr(), _stream(w)))
+            B.check(B.lib().ofa_pack_weight_16(B.fptr(w), so, si, sh, sw, cin, cout, ks, cin_pad, cout_pad,
+                                               store, B.dtype_code(dtype), buf.data_ptr(), _stream(w)))
             self._key, self._buf, self.cin_pad, self.cout_pad = key, buf, cin_pad, cout_pad
         return self._buf
 
@@ -366,8 +368,8 @@ def conv_bn_act_infer(x, w, cin, cout, ks, bn=None, act=B.ACT_NONE, store=B.STOR
     e, keep = _bn_epilogue(bn, act, residual)
     w_bf16, cin_pad, cout_pad = None, 0, 0
     impl = _state['impl']
-    if x.dtype == torch.bfloat16 and cin % 64 == 0 and cache is not None and impl != B.IMPL_SIMT:
-        w_bf16 = cache.get(w, cin, cout, ks, store)
+    if x.dtype in (torch.bfloat16, torch.float16) and cin % 64 == 0 and cache is not None and impl != B.IMPL_SIMT:
+        w_bf16 = cache.get(w, cin, cout, ks, store, x.dtype)
         cin_pad, cout_pad = cache.cin_pad, cache.cout_pad
     elif impl == B.IMPL_FAST:
         impl = B.IMPL_AUTO  # layers the tensor-core kernel does not cover (thin stem) use the CUDA-core one
@@ -418,7 +420,7 @@ def mbconv_infer(x, w_exp, w_dw, m75, m53, w_proj, cin, mid, cout, ks, transform
         t = dw_bn_act_infer(t, w_dw, m75, m53, ks, transform_on, bn_dw, act)
         return conv_bn_act_infer(t, w_proj, mid, cout, 1, bn_proj, B.ACT_NONE, residual=x if add_residual else None,
                                  cache=c2)
-    y = B.new_nhwc(n, cout, h, w, torch.bfloat16, x.device)
+    y = B.new_nhwc(n, cout, h, w, x.dtype, x.device)
     L = B.lib()
     ws_bytes = L.ofa_mbconv_workspace_bytes(n, h, w, cin, mid, cout)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
@@ -442,7 +444,7 @@ def mbconv_infer(x, w_exp, w_dw, m75, m53, w_proj, cin, mid, cout, ks, transform
 
 def planar_supported(x, cin, mid, cout):
     """Shapes the planar tcgen05 MBConv path takes (mirrors mbconv_planar_supported in the library)."""
-    return (x.dtype == torch.bfloat16 and cin == 64 and cout == 64 and mid % 64 == 0 and 64 <= mid <= 384
+    return (x.dtype in (torch.bfloat16, torch.float16) and cin == 64 and cout == 64 and mid % 64 == 0 and 64 <= mid <= 384
             and x.shape[3] % 8 == 0)
 
 
@@ -456,25 +458,27 @@ def _mbconv_planar_staged(x, w_exp, w_dw, m75, m53, w_proj, mid, ks, transform_o
     st = _stream(x)
     dt = _state['mid_dtype']
     tdt = torch.float16 if dt == B.OFA_F16 else torch.bfloat16
-    we = torch.empty(((mid + 127) // 128 * 128, 64), dtype=torch.bfloat16, device=x.device)
+    xdt = B.dtype_code(x.dtype)
+    we = torch.empty(((mid + 127) // 128 * 128, 64), dtype=x.dtype, device=x.device)
     wp = torch.empty((64, mid), dtype=tdt, device=x.device)
     B.check(L.ofa_mbconv_pack_weights(B.fptr(w_exp), w_exp.stride(0), w_exp.stride(1), B.fptr(w_proj),
-                                      w_proj.stride(0), w_proj.stride(1), mid, dt, we.data_ptr(), wp.data_ptr(), st))
+                                      w_proj.stride(0), w_proj.stride(1), mid, xdt, dt, we.data_ptr(), wp.data_ptr(),
+                                      st))
     t1 = torch.empty((n, mid, hw), dtype=tdt, device=x.device)
     t2 = torch.empty((n, mid, hw), dtype=tdt, device=x.device)
-    y = B.new_nhwc(n, 64, h, w, torch.bfloat16, x.device)
+    y = B.new_nhwc(n, 64, h, w, x.dtype, x.device)
     b1, b2, b3 = _bn_struct(bn_exp), _bn_struct(bn_dw), _bn_struct(bn_proj)
     p75, p53 = _transform_ptrs(m75, m53)
     P = n * hw
     _call('mbconv expand 64->%d planar' % mid, 2.0 * P * 64 * mid, P * (64 + mid) * 2,
-          lambda: B.check(L.ofa_expand_planar_fwd(x.data_ptr(), t1.data_ptr(), we.data_ptr(), n, hw, mid, dt,
+          lambda: B.check(L.ofa_expand_planar_fwd(x.data_ptr(), t1.data_ptr(), we.data_ptr(), n, hw, mid, xdt, dt,
                                                   byref(b1), act, st)))
     _call('dw%dx%d C%d planar' % (ks, ks, mid), 2.0 * P * mid * ks * ks, 2 * P * mid * 2,
           lambda: B.check(L.ofa_dw_planar_fwd(t1.data_ptr(), t2.data_ptr(), n, mid, h, w, B.fptr(w_dw), w_dw.shape[-1],
                                               p75, p53, int(bool(transform_on)), ks, dt, byref(b2), act, st)))
     _call('mbconv project %d->64 planar' % mid, 2.0 * P * 64 * mid, P * (mid + 64 + (64 if add_residual else 0)) * 2,
           lambda: B.check(L.ofa_project_planar_fwd(t2.data_ptr(), x.data_ptr() if add_residual else None, y.data_ptr(),
-                                                   wp.data_ptr(), n, hw, mid, dt, byref(b3), st)))
+                                                   wp.data_ptr(), n, hw, mid, xdt, dt, byref(b3), st)))
     return y
 
 

@@ -82,53 +82,55 @@ def run_dw(dtype, ks, N, C, H, W, timing=False):
     return report('dw ks=%d %s N%d C%d %dx%d' % (ks, str(dt)[6:], N, C, H, W), y, ref, 6e-3 if dtype == B.OFA_F16 else 1.2e-2)
 
 
-def pack(w_exp, w_proj, mid, dtype):
+def pack(w_exp, w_proj, mid, dtype, trunk=None):
+    trunk = trunk or B.OFA_BF16
     mt = (mid + 127) // 128
-    we = torch.empty(mt * 128, 64, dtype=torch.bfloat16, device=dev)
+    we = torch.empty(mt * 128, 64, dtype=tdt(trunk), device=dev)
     wp = torch.empty(64, mid, dtype=tdt(dtype), device=dev)
     B.check(L.ofa_mbconv_pack_weights(w_exp.data_ptr(), w_exp.stride(0), w_exp.stride(1), w_proj.data_ptr(),
-                                      w_proj.stride(0), w_proj.stride(1), mid, dtype, we.data_ptr(), wp.data_ptr(), st()))
+                                      w_proj.stride(0), w_proj.stride(1), mid, trunk, dtype, we.data_ptr(), wp.data_ptr(),
+                                      st()))
     return we, wp
 
 
-def run_expand(dtype, mid, N, HW, timing=False):
+def run_expand(dtype, mid, N, HW, timing=False, trunk=B.OFA_BF16):
     dt = tdt(dtype)
-    x = torch.randn(N, HW, 64, device=dev).to(torch.bfloat16)
+    x = torch.randn(N, HW, 64, device=dev).to(tdt(trunk))
     w_exp = torch.randn(384, 64, 1, 1, device=dev) * 0.2
     w_proj = torch.randn(64, 384, 1, 1, device=dev) * 0.1
-    we, _ = pack(w_exp, w_proj, mid, dtype)
+    we, _ = pack(w_exp, w_proj, mid, dtype, trunk)
     bn = BN(384)
     y = torch.full((N, mid, HW), 7.0, device=dev).to(dt)
     bs = bn.s()
 
     def call():
-        B.check(L.ofa_expand_planar_fwd(x.data_ptr(), y.data_ptr(), we.data_ptr(), N, HW, mid, dtype, byref(bs),
+        B.check(L.ofa_expand_planar_fwd(x.data_ptr(), y.data_ptr(), we.data_ptr(), N, HW, mid, trunk, dtype, byref(bs),
                                         B.ACT_RELU6, st()))
     call()
     torch.cuda.synchronize()
     if timing:
         return call
-    wr = w_exp[:mid, :, 0, 0].to(torch.bfloat16).float()
+    wr = w_exp[:mid, :, 0, 0].to(tdt(trunk)).float()
     ref = torch.einsum('npk,mk->nmp', x.float(), wr)
     sc, sh = bn.fold(mid)
     ref = torch.clamp(ref * sc.view(1, -1, 1) + sh.view(1, -1, 1), 0, 6)
-    return report('expand mid=%d %s N%d HW%d' % (mid, str(dt)[6:], N, HW), y, ref, 3e-3 if dtype == B.OFA_F16 else 1e-2)
+    return report('expand mid=%d %s trunk %s N%d HW%d' % (mid, str(dt)[6:], str(tdt(trunk))[6:], N, HW), y, ref, 3e-3 if dtype == B.OFA_F16 else 1e-2)
 
 
-def run_project(dtype, mid, N, HW, res=True, timing=False):
+def run_project(dtype, mid, N, HW, res=True, timing=False, trunk=B.OFA_BF16):
     dt = tdt(dtype)
     x = (torch.rand(N, mid, HW, device=dev) * 6).to(dt)
     w_exp = torch.randn(384, 64, 1, 1, device=dev) * 0.2
     w_proj = torch.randn(64, 384, 1, 1, device=dev) * 0.1
-    _, wp = pack(w_exp, w_proj, mid, dtype)
+    _, wp = pack(w_exp, w_proj, mid, dtype, trunk)
     bn = BN(64)
-    r = torch.randn(N, HW, 64, device=dev).to(torch.bfloat16)
-    y = torch.full((N, HW, 64), 7.0, device=dev).to(torch.bfloat16)
+    r = torch.randn(N, HW, 64, device=dev).to(tdt(trunk))
+    y = torch.full((N, HW, 64), 7.0, device=dev).to(tdt(trunk))
     bs = bn.s()
 
     def call():
         B.check(L.ofa_project_planar_fwd(x.data_ptr(), r.data_ptr() if res else None, y.data_ptr(), wp.data_ptr(), N,
-                                         HW, mid, dtype, byref(bs), st()))
+                                         HW, mid, trunk, dtype, byref(bs), st()))
     call()
     torch.cuda.synchronize()
     if timing:
@@ -139,7 +141,8 @@ def run_project(dtype, mid, N, HW, res=True, timing=False):
     ref = ref * sc.view(1, 1, -1) + sh.view(1, 1, -1)
     if res:
         ref = ref + r.float()
-    return report('project mid=%d %s N%d HW%d res=%d' % (mid, str(dt)[6:], N, HW, res), y, ref, 1e-2)
+    return report('project mid=%d %s trunk %s N%d HW%d res=%d' % (mid, str(dt)[6:], str(tdt(trunk))[6:], N, HW, res), y, ref,
+                  1e-2 if trunk == B.OFA_BF16 else 2e-3)
 
 
 def timeit(name, call, nbytes, iters=10):
@@ -172,12 +175,14 @@ if 'expand' in which:
             ok &= run_expand(dtype, mid, 1, 1000)
     ok &= run_expand(B.OFA_F16, 384, 3, 40 * 56)
     ok &= run_expand(B.OFA_F16, 192, 1, 540 * 960)
+    ok &= run_expand(B.OFA_F16, 384, 2, 1000, trunk=B.OFA_F16)
 if 'project' in which:
     for dtype in (B.OFA_F16, B.OFA_BF16):
         for mid in (384, 256, 192):
             ok &= run_project(dtype, mid, 1, 1000)
     ok &= run_project(B.OFA_F16, 384, 3, 40 * 56, res=False)
     ok &= run_project(B.OFA_F16, 192, 1, 540 * 960)
+    ok &= run_project(B.OFA_F16, 384, 2, 1000, trunk=B.OFA_F16)
 if 'time' in which:
     H, W = 540, 960
     P = H * W
