@@ -178,6 +178,8 @@ int ofa_conv_fwd(const OfaConvArgs* a, int32_t impl, void* stream) {
   if ((rc = store_shape_ok(a))) return rc;
   if ((rc = check_epi(&a->epi, &a->y))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  if (impl != OFA_IMPL_SIMT && conv_out_rows_supported(a)) return launch_conv_out_rows(a, st);
+  if (impl != OFA_IMPL_SIMT && conv_stem_supported(a)) return launch_conv_stem(a, st);
   bool tc_ok = conv_tc_supported(a);
   if (impl == OFA_IMPL_FAST && !tc_ok)
     return fail(OFA_ERR_UNSUPPORTED, "conv FAST path: needs NHWC-dense bf16 x, packed bf16 weights, cin %% 64 == 0, cout <= 256 (or a multiple of 128/192)");

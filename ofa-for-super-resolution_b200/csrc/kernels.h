@@ -41,6 +41,12 @@ int launch_dw_fast(const OfaTensor4* x, const OfaTensor4* y, const float* w7, in
 bool conv_tc_supported(const OfaConvArgs* a);
 int launch_conv_tc(const OfaConvArgs* a, cudaStream_t st);
 
+// ---- conv_thin.cu : the thin ends (64 -> 3 on tcgen05 with kx folded into N; 3 -> 64 on CUDA cores) ---
+bool conv_out_rows_supported(const OfaConvArgs* a);
+int launch_conv_out_rows(const OfaConvArgs* a, cudaStream_t st);
+bool conv_stem_supported(const OfaConvArgs* a);
+int launch_conv_stem(const OfaConvArgs* a, cudaStream_t st);
+
 // ---- mbconv_planar.cu : MBConv block on channel-planar 16-bit intermediates (tcgen05) ---------------
 bool mbconv_planar_supported(const OfaMBConvArgs* a);
 int launch_pack_block_weights(const float* w_exp, long long e_so, long long e_si, const float* w_proj,

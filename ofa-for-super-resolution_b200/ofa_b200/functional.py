@@ -377,8 +377,14 @@ def conv_bn_act_infer(x, w, cin, cout, ks, bn=None, act=B.ACT_NONE, store=B.STOR
     P = x.shape[0] * x.shape[2] * x.shape[3]
     nbytes = P * (cin * x.element_size() + cout * y.element_size()) + \
         (y.numel() * residual.element_size() if residual is not None else 0)
-    tag = 'conv%dx%d %d->%d%s %s' % (ks, ks, cin, cout, {0: '', 1: '+ps', 2: '+pus'}[store],
-                                     'tc' if w_bf16 is not None else 'simt')
+    half_nhwc = x.dtype in (torch.bfloat16, torch.float16) and x.is_contiguous(memory_format=torch.channels_last)
+    if impl != B.IMPL_SIMT and store == B.STORE_PLAIN and half_nhwc and cin == 64 and ks in (3, 5) and ks * cout <= 16:
+        kind = 'rows-tc'          # conv_out_rows_kernel (kx folded into the accumulator columns)
+    elif impl != B.IMPL_SIMT and store == B.STORE_PLAIN and cin <= 4 and cout == 64 and ks in (3, 5):
+        kind = 'stem'             # conv_stem_kernel
+    else:
+        kind = 'tc' if w_bf16 is not None else 'simt'
+    tag = 'conv%dx%d %d->%d%s %s' % (ks, ks, cin, cout, {0: '', 1: '+ps', 2: '+pus'}[store], kind)
     _call(tag, 2.0 * P * ks * ks * cin * cout, nbytes,
           lambda: B.check(B.lib().ofa_conv_fwd(byref(a), impl, _stream(x))))
     return y

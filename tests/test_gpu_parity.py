@@ -227,6 +227,47 @@ def test_conv_tc_fp32_nchw_output(dev):
     assert relerr(got, ref) < 1e-4
 
 
+@pytest.mark.parametrize('ks,cout', [(5, 3), (3, 3), (3, 5), (5, 1)])
+@pytest.mark.parametrize('dtype', [torch.float16, torch.bfloat16])
+def test_conv_out_rows(dev, ks, cout, dtype):
+    """a9, thin output (64 -> 3 at 4x resolution): kx folded into the accumulator columns, rolling row
+    ring.  Several 128-pixel strips (W = 300), several 32-row blocks with a ragged last one (H = 70),
+    batch 2, fp32 NCHW output as the caller receives it."""
+    from ofa_b200 import functional as OF, backend as B
+    import ofa_b200
+    ofa_b200.set_impl(B.IMPL_AUTO)
+    w = rnd(cout + 2, 64, ks, ks, seed=41, scale=0.05)
+    x = rnd(2, 64, 70, 300, seed=42).to(dtype).float()
+    bn = bn_params(cout + 2, 43, dev)
+    ref = ref_bn(O.sliced_conv(x, w.to(dtype).float(), cout), bn, cout)
+
+    class _BN:
+        weight, bias, running_mean, running_var, eps = bn['gamma'], bn['beta'], bn['mean'], bn['var'], 1e-5
+    xd = x.to(dev).to(dtype).contiguous(memory_format=torch.channels_last)
+    got = OF.conv_bn_act_infer(xd, w.to(dev), 64, cout, ks, _BN, B.ACT_NONE, B.STORE_PLAIN, None, OF.PackedWeightCache(),
+                               out_dtype=torch.float32, out_nchw=True)
+    assert got.dtype == torch.float32 and relerr(got, ref) < 1e-4
+
+
+@pytest.mark.parametrize('ks,cin', [(5, 3), (3, 3), (3, 1)])
+@pytest.mark.parametrize('out', [torch.float16, torch.bfloat16, torch.float32])
+def test_conv_stem(dev, ks, cin, out):
+    """a9, the stem (3 -> 64 on the user's fp32 NCHW image): exact fp32 arithmetic, 16-bit NHWC output."""
+    from ofa_b200 import functional as OF, backend as B
+    import ofa_b200
+    ofa_b200.set_impl(B.IMPL_AUTO)
+    w = rnd(64, cin, ks, ks, seed=51, scale=0.2)
+    x = rnd(2, cin, 37, 90, seed=52)
+    bn = bn_params(64, 53, dev)
+    ref = torch.clamp(ref_bn(O.sliced_conv(x, w, 64), bn, 64), 0, 6)
+
+    class _BN:
+        weight, bias, running_mean, running_var, eps = bn['gamma'], bn['beta'], bn['mean'], bn['var'], 1e-5
+    got = OF.conv_bn_act_infer(x.to(dev), w.to(dev), cin, 64, ks, _BN, B.ACT_RELU6, B.STORE_PLAIN, None, None, out_dtype=out)
+    assert got.dtype == out
+    assert relerr(got, ref) < {torch.float32: 1e-5, torch.float16: 2 ** -10, torch.bfloat16: 2 ** -7}[out]
+
+
 # =================================================================================================
 # planar tcgen05 MBConv stages (expand / Toeplitz depthwise / project), each through its C-ABI entry
 # =================================================================================================
