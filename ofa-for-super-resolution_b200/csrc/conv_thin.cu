@@ -43,10 +43,12 @@ struct ConvOutParams {
   TV y;
 };
 
+// KS_ / COUT_: compile-time kernel size and output channels (0 = take them from the parameters)
+template <int KS_, int COUT_>
 __global__ void __launch_bounds__(CO_THREADS, 1)
 conv_out_rows_kernel(const __grid_constant__ CUtensorMap tm_x, const ConvOutParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
   uint8_t* sA = smem;                                              // ring of image rows
   uint8_t* sB = sA + CO_RING * CO_ROW_BYTES;                       // ks x [16 rows x 128 B] weights, swizzled
   float* sP = reinterpret_cast<float*>(sB + 5 * 2048);             // 2 x [16][CO_PPITCH] transpose buffers
@@ -60,19 +62,21 @@ conv_out_rows_kernel(const __grid_constant__ CUtensorMap tm_x, const ConvOutPara
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
-  const int R = p.ks >> 1;
+  const int ks = KS_ ? KS_ : p.ks;
+  const int cout = COUT_ ? COUT_ : p.cout;
+  const int R = ks >> 1;
 
   // weights: B_ky[n = kx*cout + co][k = ci], K-major, 128-byte swizzle, 16 rows (zero padded)
-  for (int i = threadIdx.x; i < p.ks * 16 * 64; i += CO_THREADS) {
+  for (int i = threadIdx.x; i < ks * 16 * 64; i += CO_THREADS) {
     const int ci = i & 63, n = (i >> 6) & 15, ky = i >> 10;
-    const int kx = n / p.cout, co = n - kx * p.cout;
+    const int kx = n / cout, co = n - kx * cout;
     float v = 0.f;
-    if (kx < p.ks) v = p.w[co * p.w_so + ci * p.w_si + ky * p.w_sh + kx * p.w_sw];
+    if (kx < ks) v = p.w[co * p.w_so + ci * p.w_si + ky * p.w_sh + kx * p.w_sw];
     *reinterpret_cast<uint16_t*>(sB + ky * 2048 + n * 128 + (((ci >> 3) ^ (n & 7)) << 4) + (ci & 7) * 2) = cvt16(v, p.f16);
   }
   if (threadIdx.x < 8) {
     float sc = 0.f, sh = 0.f;
-    if ((int)threadIdx.x < p.cout) epi_scale_shift(p.epi, threadIdx.x, sc, sh);
+    if ((int)threadIdx.x < cout) epi_scale_shift(p.epi, threadIdx.x, sc, sh);
     s_scale[threadIdx.x] = sc;
     s_shift[threadIdx.x] = sh;
   }
@@ -135,7 +139,9 @@ conv_out_rows_kernel(const __grid_constant__ CUtensorMap tm_x, const ConvOutPara
         ptx::mbar_wait(&tempty[acc], accph ^ 1);
         ptx::tc_fence_after();
         const uint32_t d0 = tmem_base + (uint32_t)(acc * 16);
-        for (int ky = 0; ky < p.ks; ++ky) {
+#pragma unroll
+        for (int ky = 0; ky < (KS_ ? KS_ : 5); ++ky) {
+          if (ky >= ks) break;
           int slot = head + ky;
           if (slot >= CO_RING) slot -= CO_RING;
           const uint64_t da = ptx::umma_desc_sw128(sA_addr + (uint32_t)(slot * CO_ROW_BYTES), 1024);
@@ -183,12 +189,17 @@ conv_out_rows_kernel(const __grid_constant__ CUtensorMap tm_x, const ConvOutPara
         ptx::named_bar_sync(1, 128);
         if (valid) {
           const int Y = y0 + j;
-          for (int co = 0; co < p.cout; ++co) {
+#pragma unroll
+          for (int co = 0; co < (COUT_ ? COUT_ : 8); ++co) {
+            if (co >= cout) break;
             float s = 0.f;
-            for (int kx = 0; kx < p.ks; ++kx) s += P[(kx * p.cout + co) * CO_PPITCH + xl + kx - R];
+#pragma unroll
+            for (int kx = 0; kx < (KS_ ? KS_ : 5); ++kx)
+              if (kx < ks) s += P[(kx * cout + co) * CO_PPITCH + xl + kx - R];
             float o = apply_act(fmaf(s, s_scale[co], s_shift[co]), p.epi.act);
             if (p.epi.res.ptr) o += p.epi.res.ld(p.epi.res.off(n, co, Y, X));
-            p.y.st(p.y.off(n, co, Y, X), o);
+            if (p.y.dtype == OFA_F32) reinterpret_cast<float*>(p.y.ptr)[p.y.off(n, co, Y, X)] = o;
+            else p.y.st(p.y.off(n, co, Y, X), o);
           }
         }
         pb ^= 1;
@@ -339,11 +350,18 @@ int launch_conv_out_rows(const OfaConvArgs* a, cudaStream_t st) {
                        strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
   const size_t smem = 1024 + CO_RING * CO_ROW_BYTES + 5 * 2048 + 2 * 16 * CO_PPITCH * 4 + 64 + (2 * CO_RING + 2 * CO_ACC) * 8 + 64;
-  OFA_CUDA(cudaFuncSetAttribute(conv_out_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int num_work = p.N * p.strips * p.row_blocks;
   int grid = sm_count();
   if (grid > num_work) grid = num_work;
-  conv_out_rows_kernel<<<grid, CO_THREADS, smem, st>>>(tx, p);
+#define OFA_CO_LAUNCH(K_, C_)                                                                                       \
+  do {                                                                                                              \
+    OFA_CUDA(cudaFuncSetAttribute(conv_out_rows_kernel<K_, C_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    conv_out_rows_kernel<K_, C_><<<grid, CO_THREADS, smem, st>>>(tx, p);                                            \
+  } while (0)
+  if (p.ks == 5 && p.cout == 3) OFA_CO_LAUNCH(5, 3);
+  else if (p.ks == 3 && p.cout == 3) OFA_CO_LAUNCH(3, 3);
+  else OFA_CO_LAUNCH(0, 0);
+#undef OFA_CO_LAUNCH
   return check_launch("conv_out_rows_kernel");
 }
 

@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(THREADS, 2)
 dw_fast_kernel(const __grid_constant__ CUtensorMap tmap_x, const DwParams p) {
   using L = DwSmem<KS>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint8_t* smem = smem_raw + ((128u - (ptx::smem_u32(smem_raw) & 127u)) & 127u);   // keeps the shared address space
   const uint32_t* tile = reinterpret_cast<const uint32_t*>(smem);           // [HALO_H][HALO_W][32] words
   float* filt = reinterpret_cast<float*>(smem + L::FILT_OFF);               // [KS*KS][CH]
   float* k5s = reinterpret_cast<float*>(smem + L::K5_OFF);                  // [CH][25]

@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(EX_THREADS, 1)
 expand_planar_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                      const __grid_constant__ CUtensorMap tm_y, const ExpandParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
   uint8_t* sW = smem;                                              // mt x 16 KiB, resident
   uint8_t* sX = sW + EX_MAX_MT * 16384;                            // pixel-tile ring
   uint8_t* sS = sX + EX_X_STAGES * EX_X_BYTES;                     // 8 warps x 2 x 4 KiB staging
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1)
 dw_planar_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_y,
                  const DwPlanarParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
   uint8_t* sA = smem;
   uint8_t* sO = sA + DW_A_STAGES * DW_A_STRIDE;                    // 2 output staging tiles (1024-aligned)
   uint8_t* sB = sO + 2 * DW_OUT_BYTES;                             // 2 filter buffers
@@ -466,7 +466,7 @@ project_planar_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
                       const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_y,
                       const ProjectParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
   uint8_t* sA = smem;
   uint8_t* sW = sA + PJ_A_STAGES * PJ_A_BYTES;                     // kcs x 8 KiB resident
   uint8_t* sR = sW + PJ_MAX_KC * 8192;                             // 2 residual / output tiles
