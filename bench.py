@@ -176,17 +176,21 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, drain=None):
         with torch.no_grad():
             for _ in range(warmup):
                 fn()
+            if drain:
+                drain()
             barrier()
             evs = []
-            for _ in range(steps):
+            for k in range(steps):
                 flush.zero_()                       # L2 flush between timed iterations (not timed)
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 fn()
+                if drain and k == steps - 1:
+                    drain()                         # the last frame's copy-out is inside the timed region
                 e1.record()
                 evs.append((e0, e1))
             barrier()
@@ -199,10 +203,31 @@ def run_ours(args):
     def step_resident():
         return net(x_dev)
 
+    # e2e: the call a user makes (net(x)) with the frame coming from pinned host memory and the fp32 SR image
+    # going back to pinned host memory, every step.  The device -> host copy of frame i runs on a copy stream
+    # while frame i+1 computes (two result buffers on each side); the timed region ends when the LAST copy has
+    # landed (the compute stream waits for the copy stream before the closing event).
+    copy_stream = torch.cuda.Stream(device=dev)
+    y_hosts = [y_host, torch.empty_like(y_host).pin_memory()]
+    e2e_state = {'i': 0, 'done': [None, None]}
+
     def step_e2e():
+        i = e2e_state['i'] & 1
+        e2e_state['i'] += 1
         xd = x_host.to(dev, non_blocking=True)
         y = net(xd)
-        y_host.copy_(y, non_blocking=True)
+        ready = torch.cuda.Event()
+        ready.record()
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ready)
+            y_hosts[i].copy_(y, non_blocking=True)
+            y.record_stream(copy_stream)
+            done = torch.cuda.Event()
+            done.record()
+        e2e_state['done'][i] = done
+
+    def e2e_drain():
+        torch.cuda.current_stream().wait_stream(copy_stream)
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
@@ -211,7 +236,7 @@ def run_ours(args):
     total_ms = timed(step_resident, args.steps, args.warmup)
     launches = B.launch_count() * args.steps // (args.steps + args.warmup)
     clocks = sampler.finish() if sampler else None
-    e2e_ms = timed(step_e2e, args.steps, args.warmup)
+    e2e_ms = timed(step_e2e, args.steps, args.warmup, drain=e2e_drain)
 
     ms_per_step = total_ms / args.steps
     value = world * out_pix / 1e6 / (ms_per_step / 1e3)
@@ -280,6 +305,17 @@ def run_ours(args):
 
 
 if __name__ == '__main__':
+    # exactly ONE line may reach stdout (the JSON): libraries that print there (NCCL's version banner) are
+    # sent to stderr, the JSON line is written to the saved descriptor
+    sys.stdout.flush()
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    _print = print
+
+    def print(*args, **kw):  # noqa: A001
+        sys.stdout.flush()
+        os.write(_real_stdout, (' '.join(str(x) for x in args) + '\n').encode())
+
     a = parse()
     if a.impl == 'reference':
         run_reference(a)

@@ -241,16 +241,19 @@ struct DwPlanarParams {
   const float* w7; const float* m75; const float* m53;
   const float* gamma; const float* beta; const float* mean; const float* var; float eps;
   int tiles_x, tiles_y;
-  long long total_tiles;
+  int total_tiles;
+  int short_last;   // the last tile row has <= 64 valid rows: it runs as an M = 64 MMA tile
 };
 
-__device__ __forceinline__ void dw_decode(const DwPlanarParams& p, long long t, int& pc, int& y0, int& x0) {
-  const int tx = (int)(t % p.tiles_x);
-  const long long r = t / p.tiles_x;
-  const int ty = (int)(r % p.tiles_y);
-  pc = (int)(r / p.tiles_y);
-  y0 = ty * DW_TH;
-  x0 = tx * DW_TW;
+// tile index -> plane, tile origin, and whether it is a short (M = 64) tile
+__device__ __forceinline__ bool dw_decode(const DwPlanarParams& p, int t, int& pc, int& y0, int& x0) {
+  const unsigned tx = (unsigned)t % (unsigned)p.tiles_x;
+  const unsigned r = (unsigned)t / (unsigned)p.tiles_x;
+  const unsigned ty = r % (unsigned)p.tiles_y;
+  pc = (int)(r / (unsigned)p.tiles_y);
+  y0 = (int)ty * DW_TH;
+  x0 = (int)tx * DW_TW;
+  return p.short_last && (int)ty == p.tiles_y - 1;
 }
 // offset of element (n = accumulator column, k = input column within the chunk) in a K-major, unswizzled
 // B tile: 8 x 16-byte core matrices, K-halves 128 bytes apart, 8-column groups 256 bytes apart
@@ -259,8 +262,8 @@ __device__ __forceinline__ int dw_b_off(int n, int k) { return (n >> 3) * 256 + 
 // KS: kernel size; F16: fp16 (1) or bf16 (0) storage; RELU6: the activation is ReLU6 (else p.act at run time)
 template <int KS, int F16, int RELU6>
 __global__ void __launch_bounds__(DW_THREADS, 1)
-dw_planar_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_y,
-                 const DwPlanarParams p) {
+dw_planar_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_xs,
+                 const __grid_constant__ CUtensorMap tm_y, const DwPlanarParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
   uint8_t* sA = smem;
@@ -277,7 +280,7 @@ dw_planar_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
-  if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&tm_x); ptx::prefetch_tmap(&tm_y); }
+  if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&tm_x); ptx::prefetch_tmap(&tm_xs); ptx::prefetch_tmap(&tm_y); }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < DW_A_STAGES; ++s) { ptx::mbar_init(&a_full[s], 1); ptx::mbar_init(&a_empty[s], 1); }
     for (int a = 0; a < DW_ACC_STAGES; ++a) { ptx::mbar_init(&tfull[a], 1); ptx::mbar_init(&tempty[a], DW_EPI_WARPS); }
@@ -290,22 +293,24 @@ dw_planar_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   ptx::tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
 
-  const long long t_begin = p.total_tiles * blockIdx.x / gridDim.x;
-  const long long t_end = p.total_tiles * (blockIdx.x + 1) / gridDim.x;
+  const int t_begin = (int)((long long)p.total_tiles * blockIdx.x / gridDim.x);
+  const int t_end = (int)((long long)p.total_tiles * (blockIdx.x + 1) / gridDim.x);
   constexpr int R = KS >> 1;
   constexpr uint32_t atom_bytes = (uint32_t)((DW_TH + KS - 1) * 128);
+  constexpr uint32_t atom_bytes_short = (uint32_t)((DW_TH / 2 + KS - 1) * 128);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
-      for (long long t = t_begin; t < t_end; ++t) {
+      for (int t = t_begin; t < t_end; ++t) {
         int pc, y0, x0;
-        dw_decode(p, t, pc, y0, x0);
+        const bool shrt = dw_decode(p, t, pc, y0, x0);
+        const CUtensorMap* tm = shrt ? &tm_xs : &tm_x;
         ptx::mbar_wait(&a_empty[s], ph ^ 1);
-        ptx::mbar_arrive_expect_tx(&a_full[s], 2 * atom_bytes);
-        ptx::tma_load_3d(sA + s * DW_A_STRIDE, &tm_x, &a_full[s], x0 - DW_XPAD, y0 - R, pc);
-        ptx::tma_load_3d(sA + s * DW_A_STRIDE + DW_ATOM_STRIDE, &tm_x, &a_full[s], x0 - DW_XPAD + 64, y0 - R, pc);
+        ptx::mbar_arrive_expect_tx(&a_full[s], 2 * (shrt ? atom_bytes_short : atom_bytes));
+        ptx::tma_load_3d(sA + s * DW_A_STRIDE, tm, &a_full[s], x0 - DW_XPAD, y0 - R, pc);
+        ptx::tma_load_3d(sA + s * DW_A_STRIDE + DW_ATOM_STRIDE, tm, &a_full[s], x0 - DW_XPAD + 64, y0 - R, pc);
         if (++s == DW_A_STAGES) { s = 0; ph ^= 1; }
       }
     }
@@ -313,14 +318,20 @@ dw_planar_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     // ===================== MMA issuer =====================
     const uint32_t leader = (lane == 0) ? 1u : 0u;
     constexpr int fmt = F16 ? 0 : 1;
-    constexpr uint32_t idesc32 = ptx::umma_idesc_f16(128, 32, fmt, fmt, 0, 0);
-    constexpr uint32_t idesc_first = ptx::umma_idesc_f16(128, DW_ACC_COLS, fmt, fmt, 0, 0);
+    constexpr uint32_t idesc32_tall = ptx::umma_idesc_f16(128, 32, fmt, fmt, 0, 0);
+    constexpr uint32_t idesc_first_tall = ptx::umma_idesc_f16(128, DW_ACC_COLS, fmt, fmt, 0, 0);
+    // M = 64 variants (short tiles): half the A rows are read; the accumulator rows land in lanes
+    // 0-15 of each 32-lane quarter (row m -> lane 32 * (m / 16) + m % 16)
+    constexpr uint32_t idesc32_short = ptx::umma_idesc_f16(64, 32, fmt, fmt, 0, 0);
+    constexpr uint32_t idesc_first_short = ptx::umma_idesc_f16(64, DW_ACC_COLS, fmt, fmt, 0, 0);
     const uint32_t sA_addr = ptx::smem_u32(sA), sB_addr = ptx::smem_u32(sB);
     int s = 0, acc = 0, bi = 0, cur_pc = -1;
     uint32_t ph = 0, accph = 0, bph = 0;
-    for (long long t = t_begin; t < t_end; ++t) {
+    for (int t = t_begin; t < t_end; ++t) {
       int pc, y0, x0;
-      dw_decode(p, t, pc, y0, x0);
+      const bool shrt = dw_decode(p, t, pc, y0, x0);
+      const uint32_t idesc32 = shrt ? idesc32_short : idesc32_tall;
+      const uint32_t idesc_first = shrt ? idesc_first_short : idesc_first_tall;
       if (pc != cur_pc) {
         if (cur_pc >= 0) {
           ptx::umma_commit_pred(&b_empty[bi], leader);     // all MMAs reading the old filter tiles are done
@@ -358,7 +369,7 @@ dw_planar_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     // ===================== filter builder: active filter -> Toeplitz B tiles =====================
     int bi = 0, cur_pc = -1; uint32_t bph = 0;
     constexpr int dx0 = DW_XPAD + R;
-    for (long long t = t_begin; t < t_end; ++t) {
+    for (int t = t_begin; t < t_end; ++t) {
       int pc, y0, x0;
       dw_decode(p, t, pc, y0, x0);
       if (pc == cur_pc) continue;
@@ -393,12 +404,13 @@ dw_planar_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     // ===================== epilogue (warps 3..10): lane quarter x 56-column half =====================
     const int quarter = warp & 3;
     const int hf = (warp - 3) >> 2;
-    const int row = quarter * 32 + lane;
     const bool issuer = (warp == 3 && lane == 0);
     int acc = 0, ob = 0; uint32_t accph = 0;
-    for (long long t = t_begin; t < t_end; ++t) {
+    for (int t = t_begin; t < t_end; ++t) {
       int pc, y0, x0;
-      dw_decode(p, t, pc, y0, x0);
+      const bool shrt = dw_decode(p, t, pc, y0, x0);
+      const int row = shrt ? quarter * 16 + lane : quarter * 32 + lane;   // accumulator lane -> tile row
+      const bool live = !shrt || lane < 16;
       float scale, shift;
       bn_fold(p.gamma, p.beta, p.mean, p.var, p.eps, pc % p.C, scale, shift);
       ptx::mbar_wait(&tfull[acc], accph);
@@ -426,9 +438,11 @@ dw_planar_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       if (issuer) ptx::tma_store_wait_read<1>();       // the store that last read staging tile `ob` is done
       ptx::named_bar_sync(1, 32 * DW_EPI_WARPS);
       uint8_t* dst = sO + ob * DW_OUT_BYTES + row * (DW_TW * 2) + hf * 112;
+      if (live) {
 #pragma unroll
-      for (int j = 0; j < 7; ++j)
-        *reinterpret_cast<uint4*>(dst + j * 16) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        for (int j = 0; j < 7; ++j)
+          *reinterpret_cast<uint4*>(dst + j * 16) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+      }
       ptx::fence_proxy_async();
       ptx::named_bar_sync(1, 32 * DW_EPI_WARPS);
       if (issuer) {
@@ -695,14 +709,21 @@ int launch_dw_planar(const void* x, void* y, int N, int C, int H, int W, const f
   if (bn) { p.gamma = bn->gamma; p.beta = bn->beta; p.mean = bn->mean; p.var = bn->var; p.eps = bn->eps; }
   p.tiles_x = (W + DW_TW - 1) / DW_TW;
   p.tiles_y = (H + DW_TH - 1) / DW_TH;
-  p.total_tiles = (long long)p.NC * p.tiles_x * p.tiles_y;
-  CUtensorMap tx, ty;
+  const long long total = (long long)p.NC * p.tiles_x * p.tiles_y;
+  if (total >= (1ll << 31)) return fail(OFA_ERR_UNSUPPORTED, "dw_planar: too many tiles");
+  p.total_tiles = (int)total;
+  const int rem = H % DW_TH;
+  p.short_last = (rem > 0 && rem <= DW_TH / 2) ? 1 : 0;
+  CUtensorMap tx, txs, ty;
   int rc;
   uint64_t dims[3] = {(uint64_t)W, (uint64_t)H, (uint64_t)p.NC};
   uint64_t str[2] = {(uint64_t)W * 2, (uint64_t)H * W * 2};
   {
     uint32_t box[3] = {64, (uint32_t)(DW_TH + ks - 1), 1};
     if ((rc = encode_tmap(&tx, dt16(f16), 3, const_cast<void*>(x), dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)))
+      return rc;
+    box[1] = (uint32_t)(DW_TH / 2 + ks - 1);
+    if ((rc = encode_tmap(&txs, dt16(f16), 3, const_cast<void*>(x), dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)))
       return rc;
   }
   {
@@ -717,7 +738,7 @@ int launch_dw_planar(const void* x, void* y, int N, int C, int H, int W, const f
   do {                                                                                                           \
     OFA_CUDA(cudaFuncSetAttribute(dw_planar_kernel<KS_, F16_, R6_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                   (int)smem));                                                                   \
-    dw_planar_kernel<KS_, F16_, R6_><<<(unsigned)grid, DW_THREADS, smem, st>>>(tx, ty, p);                       \
+    dw_planar_kernel<KS_, F16_, R6_><<<(unsigned)grid, DW_THREADS, smem, st>>>(tx, txs, ty, p);                      \
   } while (0)
 #define OFA_DW_LAUNCH_KS(KS_)                                           \
   do {                                                                  \
