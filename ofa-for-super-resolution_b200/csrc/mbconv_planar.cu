@@ -348,6 +348,10 @@ dw_planar_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       const uint64_t da0 = ptx::umma_desc_sw128(sA_addr + (uint32_t)(s * DW_A_STRIDE), 1024);
       const uint64_t dbf = ptx::umma_desc(sB_addr + (uint32_t)(bi * DW_B_BYTES), 128, 256, 0);
       const uint64_t db0 = dbf + (uint64_t)(DW_BFIRST_BYTES >> 4);
+      // ragged right edge: input chunks past the reach of the last valid output column are skipped (the
+      // first MMA has zero-initialised every accumulator column)
+      const int valid_w = min(DW_TW, p.W - x0);
+      const int nch = min(DW_CHUNKS, (valid_w + DW_XPAD + R + 15) >> 4);
 #pragma unroll
       for (int dy = 0; dy < KS; ++dy) {
 #pragma unroll
@@ -356,7 +360,7 @@ dw_planar_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           const uint64_t da = da0 + (uint64_t)(((j >> 2) * DW_ATOM_STRIDE + dy * 128 + (j & 3) * 32) >> 4);
           if (dy == 0 && j == 0)
             ptx::umma_bf16_pred(d0, da, dbf, idesc_first, 0u, leader);
-          else
+          else if (j < nch)
             ptx::umma_bf16_pred(d0 + (uint32_t)(16 * j), da, db0 + (uint64_t)((dy * 1024) >> 4), idesc32, 1u, leader);
         }
       }
