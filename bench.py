@@ -32,6 +32,11 @@ SUBNET = dict(ks=7, e=6, d=4, pixel_d=2)
 WEIGHT_SEED = 1234
 
 
+def workload_text(W, H):
+    return ('OFAMobileNetS4 max subnet (ks=7,e=6,d=4,pixel_d=2 -> 14 MBConv blocks), 4x SR forward, LR %dx%d -> %dx%d, '
+            '1 frame per step per GPU, frames sharded across ranks (no collective)' % (W, H, 4 * W, 4 * H))
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -55,6 +60,28 @@ def peaks():
         return {'hbm': d['hbm_gbs'], 'tensor_burst': d['bf16_tflops'], 'tensor_sustained': d['bf16_tflops_sustained'],
                 'source': 'MEASURED_PEAKS.json'}
     return {'hbm': 6650.0, 'tensor_burst': 1590.0, 'tensor_sustained': 1400.0, 'source': 'fallback (B200_PROFILING.md)'}
+
+
+# ncu --set full captures of the hot kernels (profiles/*.csv, written by tools/ncu_summary.py): DRAM bytes per launch
+NCU_PROFILES = {'dw7x7 C384 planar': 'r1_ncu_dw7_planar_v3.csv', 'mbconv expand 64->384 planar': 'r1_ncu_expand_planar_v1.csv',
+                'mbconv project 384->64 planar': 'r1_ncu_project_planar_v1.csv', 'conv5x5 64->3 rows-tc': 'r1_ncu_conv_out_rows_v1.csv'}
+
+
+def ncu_traffic(tag):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `tag` from the committed ncu summary, or None."""
+    import csv
+    name = NCU_PROFILES.get(tag)
+    path = os.path.join(ROOT, 'profiles', name) if name else None
+    if not path or not os.path.exists(path):
+        return None
+    rows = list(csv.reader(open(path)))
+    hdr, units, last = rows[0], rows[1], rows[-1]
+    scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+    tot = 0.0
+    for key in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+        i = hdr.index(key)
+        tot += float(last[i].replace(',', '')) * scale.get(units[i], 1.0)
+    return tot
 
 
 class ClockSampler(threading.Thread):
@@ -124,7 +151,8 @@ def run_reference(args):
         'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'S4 max subnet (ks=7,e=6,d=4,pixel_d=2) 4x SR forward, bounded tile sample on host cores'},
+        'config': {'workload': workload_text(args.lr_w, args.lr_h),
+                   'reference_sample': 'each step = one %dx%d LR tile of that frame (Mpix/s is size-normalised)' % (args.cpu_tile, args.cpu_tile)},
         'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port', 'sample': sample},
         'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
@@ -275,7 +303,9 @@ def run_ours(args):
         else:
             roof = {'bound': 'hbm', 'achieved': top['GBps'], 'peak': pk['hbm'], 'unit': 'GB/s',
                     'frac': top['GBps'] / pk['hbm'], 'traffic': None}
-        roof.update({'kernel': tag, 'share_of_step': top['share'], 'peak_source': pk['source'], 'kernels': table[:8]})
+        roof['traffic'] = ncu_traffic(tag)
+        roof.update({'kernel': tag, 'share_of_step': top['share'], 'peak_source': pk['source'],
+                     'algorithmic_bytes': nbytes, 'kernels': table[:8]})
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -290,9 +320,7 @@ def run_ours(args):
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': args.dtype, 'data': 'synthetic',
-            'config': {'workload': 'OFAMobileNetS4 max subnet (ks=7,e=6,d=4,pixel_d=2 -> 14 MBConv blocks), 4x SR '
-                                   'forward, LR %dx%d -> %dx%d, 1 frame per step per GPU, frames sharded across ranks '
-                                   '(no collective)' % (W, H, 4 * W, 4 * H),
+            'config': {'workload': workload_text(W, H),
                        'l2': 'flushed between timed iterations (256 MiB write); per-step activations are also >> L2',
                        'timing': 'CUDA events per step on the launch stream, summed, max over ranks'},
             'e2e': {'value': e2e_val, 'unit': UNIT, 'h2d_bytes_per_step': x_host.numel() * 4,

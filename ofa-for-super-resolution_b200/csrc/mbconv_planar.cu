@@ -75,6 +75,8 @@ struct ExpandParams {
   int tiles_per_img;
 };
 
+// F16: fp16 (1) or bf16 (0) output; RELU6: the activation is ReLU6 (else p.act at run time)
+template <int F16, int RELU6>
 __global__ void __launch_bounds__(EX_THREADS, 1)
 expand_planar_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                      const __grid_constant__ CUtensorMap tm_y, const ExpandParams p) {
@@ -181,9 +183,11 @@ expand_planar_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
               uint32_t pk[4];
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const float a = apply_act(fmaf(__uint_as_float(v[j * 8 + 2 * i]), scale, shift), p.act);
-                const float b = apply_act(fmaf(__uint_as_float(v[j * 8 + 2 * i + 1]), scale, shift), p.act);
-                pk[i] = pack16(a, b, p.f16);
+                float a = fmaf(__uint_as_float(v[j * 8 + 2 * i]), scale, shift);
+                float b = fmaf(__uint_as_float(v[j * 8 + 2 * i + 1]), scale, shift);
+                if (RELU6) { a = fminf(fmaxf(a, 0.f), 6.f); b = fminf(fmaxf(b, 0.f), 6.f); }
+                else { a = apply_act(a, p.act); b = apply_act(b, p.act); }
+                pk[i] = pack16(a, b, F16);
               }
               *reinterpret_cast<uint4*>(dst + ((j ^ (lane & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
@@ -694,11 +698,21 @@ int launch_expand_planar(const void* x, void* y, const void* wexp_p, int N, int 
     if ((rc = encode_tmap(&ty, dt16(f16), 3, y, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   }
   const size_t smem = 1024 + EX_MAX_MT * 16384 + EX_X_STAGES * EX_X_BYTES + EX_EPI_WARPS * 2 * EX_SBUF_BYTES + 256;
-  OFA_CUDA(cudaFuncSetAttribute(expand_planar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = sm_count();
   const int tiles = N * p.tiles_per_img;
   if (grid > tiles) grid = tiles;
-  expand_planar_kernel<<<grid, EX_THREADS, smem, st>>>(tx, tw, ty, p);
+  const int relu6 = act == OFA_ACT_RELU6 ? 1 : 0;
+#define OFA_EX_LAUNCH(F16_, R6_)                                                                                  \
+  do {                                                                                                            \
+    OFA_CUDA(cudaFuncSetAttribute(expand_planar_kernel<F16_, R6_>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                  (int)smem));                                                                    \
+    expand_planar_kernel<F16_, R6_><<<grid, EX_THREADS, smem, st>>>(tx, tw, ty, p);                               \
+  } while (0)
+  if (f16 && relu6) OFA_EX_LAUNCH(1, 1);
+  else if (f16) OFA_EX_LAUNCH(1, 0);
+  else if (relu6) OFA_EX_LAUNCH(0, 1);
+  else OFA_EX_LAUNCH(0, 0);
+#undef OFA_EX_LAUNCH
   return check_launch("expand_planar_kernel");
 }
 
