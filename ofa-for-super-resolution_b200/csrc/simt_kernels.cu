@@ -319,58 +319,102 @@ __device__ __forceinline__ void pix_decode(long long p, long long HW, int W, int
   w = rem - h * W;
 }
 
+// Batch statistics as a two-level reduction: grid = (channel groups, pixel splits); a block folds its pixel
+// range with per-thread Welford updates and Chan's pairwise combination (no catastrophic cancellation when
+// mean^2 >> var), writes one (count, mean, M2) triple per channel; a second tiny kernel combines the splits in a
+// fixed order in double precision -> deterministic, and every SM takes part.
+struct Wf { float n, mean, m2; };
+__device__ __forceinline__ void wf_add(Wf& a, float x) {
+  a.n += 1.f;
+  const float d = x - a.mean;
+  a.mean += d / a.n;
+  a.m2 = fmaf(d, x - a.mean, a.m2);
+}
+__device__ __forceinline__ void wf_merge(Wf& a, const Wf& b) {
+  if (b.n == 0.f) return;
+  const float n = a.n + b.n, d = b.mean - a.mean;
+  a.mean += d * (b.n / n);
+  a.m2 += b.m2 + d * d * (a.n * b.n / n);
+  a.n = n;
+}
+
 __global__ void __launch_bounds__(BN_THREADS)
-bn_stats_kernel(TV x, float* __restrict__ mean, float* __restrict__ var, int c_is_inner) {
-  __shared__ float red[BN_PL][BN_CH + 1];
-  __shared__ float smean[BN_CH];
+bn_stats_partial_kernel(TV x, float* __restrict__ part, int splits, long long per_split, int c_is_inner) {
+  __shared__ Wf red[BN_PL][BN_CH + 1];
   int cl, pl;
   if (c_is_inner) { cl = threadIdx.x % BN_CH; pl = threadIdx.x / BN_CH; }
   else            { pl = threadIdx.x % BN_PL; cl = threadIdx.x / BN_PL; }
   const int c = blockIdx.x * BN_CH + cl;
   const long long HW = (long long)x.h * x.w;
   const long long P = HW * x.n;
-  const bool ok = c < x.c;
-  float s = 0.f;
-  if (ok)
-    for (long long p = pl; p < P; p += BN_PL) {
-      int n, h, w;
-      pix_decode(p, HW, x.w, n, h, w);
-      s += x.ld(x.off(n, c, h, w));
+  const long long p_lo = (long long)blockIdx.y * per_split;
+  const long long p_hi = p_lo + per_split < P ? p_lo + per_split : P;
+  Wf w = {0.f, 0.f, 0.f};
+  if (c < x.c)
+    for (long long p = p_lo + pl; p < p_hi; p += BN_PL) {
+      int n, h, ww;
+      pix_decode(p, HW, x.w, n, h, ww);
+      wf_add(w, x.ld(x.off(n, c, h, ww)));
     }
-  red[pl][cl] = s;
+  red[pl][cl] = w;
   __syncthreads();
   if (threadIdx.x < BN_CH) {
-    double t = 0.0;
-    for (int i = 0; i < BN_PL; ++i) t += red[i][threadIdx.x];
-    smean[threadIdx.x] = (float)(t / (double)P);
-  }
-  __syncthreads();
-  const float m = smean[cl];
-  float q = 0.f;
-  if (ok)
-    for (long long p = pl; p < P; p += BN_PL) {
-      int n, h, w;
-      pix_decode(p, HW, x.w, n, h, w);
-      float d = x.ld(x.off(n, c, h, w)) - m;
-      q = fmaf(d, d, q);
-    }
-  red[pl][cl] = q;
-  __syncthreads();
-  if (threadIdx.x < BN_CH) {
-    int cc = blockIdx.x * BN_CH + threadIdx.x;
+    const int cc = blockIdx.x * BN_CH + threadIdx.x;
     if (cc < x.c) {
-      double t = 0.0;
-      for (int i = 0; i < BN_PL; ++i) t += red[i][threadIdx.x];
-      mean[cc] = smean[threadIdx.x];
-      var[cc] = (float)(t / (double)P);
+      Wf t = red[0][threadIdx.x];
+      for (int i = 1; i < BN_PL; ++i) wf_merge(t, red[i][threadIdx.x]);
+      float* o = part + ((size_t)blockIdx.y * x.c + cc) * 3;
+      o[0] = t.n; o[1] = t.mean; o[2] = t.m2;
     }
   }
 }
 
+__global__ void bn_stats_final_kernel(const float* __restrict__ part, int splits, int C, float* __restrict__ mean,
+                                      float* __restrict__ var) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double n = 0.0, m = 0.0, m2 = 0.0;
+  for (int s = 0; s < splits; ++s) {
+    const float* o = part + ((size_t)s * C + c) * 3;
+    const double bn = o[0], bm = o[1], b2 = o[2];
+    if (bn == 0.0) continue;
+    const double nn = n + bn, d = bm - m;
+    m += d * (bn / nn);
+    m2 += b2 + d * d * (n * bn / nn);
+    n = nn;
+  }
+  mean[c] = (float)m;
+  var[c] = (float)(n > 0.0 ? m2 / n : 0.0);
+}
+
+// pixel splits of a per-channel reduction: enough blocks to fill the GPU, at least ~4k pixels each
+static int bn_splits(const TV& x, long long* per_split) {
+  const long long P = (long long)x.n * x.h * x.w;
+  const int groups = (x.c + BN_CH - 1) / BN_CH;
+  long long want = (4LL * sm_count() + groups - 1) / groups;
+  long long maxs = (P + 4095) / 4096;
+  if (want > maxs) want = maxs;
+  if (want < 1) want = 1;
+  if (want > 1024) want = 1024;
+  *per_split = (P + want - 1) / want;
+  return (int)((P + *per_split - 1) / *per_split);
+}
+
 int launch_bn_stats(const TV& x, float* mean, float* var, cudaStream_t st) {
   if (x.c == 0) return OFA_OK;
-  bn_stats_kernel<<<(x.c + BN_CH - 1) / BN_CH, BN_THREADS, 0, st>>>(x, mean, var, x.sc == 1);
-  return check_launch("bn_stats_kernel");
+  long long per_split = 0;
+  const int splits = bn_splits(x, &per_split);
+  float* part = nullptr;
+  OFA_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&part), (size_t)splits * x.c * 3 * sizeof(float), st));
+  dim3 grid((x.c + BN_CH - 1) / BN_CH, splits);
+  bn_stats_partial_kernel<<<grid, BN_THREADS, 0, st>>>(x, part, splits, per_split, x.sc == 1);
+  int rc = check_launch("bn_stats_partial_kernel");
+  if (!rc) {
+    bn_stats_final_kernel<<<(x.c + 127) / 128, 128, 0, st>>>(part, splits, x.c, mean, var);
+    rc = check_launch("bn_stats_final_kernel");
+  }
+  cudaFreeAsync(part, st);
+  return rc;
 }
 
 __global__ void bn_update_running_kernel(const float* __restrict__ mean, const float* __restrict__ var,
@@ -394,9 +438,9 @@ int launch_bn_update_running(const float* mean, const float* var, long long coun
 // (a14) BN (+act) backward
 // =================================================================================================
 __global__ void __launch_bounds__(BN_THREADS)
-bn_bwd_reduce_kernel(TV x, TV dy, const float* __restrict__ gamma, const float* __restrict__ beta,
-                     const float* __restrict__ mean, const float* __restrict__ var, float eps, int act,
-                     float* __restrict__ sum_dz, float* __restrict__ sum_dz_xhat, int c_is_inner) {
+bn_bwd_reduce_partial_kernel(TV x, TV dy, const float* __restrict__ gamma, const float* __restrict__ beta,
+                             const float* __restrict__ mean, const float* __restrict__ var, float eps, int act,
+                             float* __restrict__ part, long long per_split, int c_is_inner) {
   __shared__ float red0[BN_PL][BN_CH + 1];
   __shared__ float red1[BN_PL][BN_CH + 1];
   int cl, pl;
@@ -405,11 +449,13 @@ bn_bwd_reduce_kernel(TV x, TV dy, const float* __restrict__ gamma, const float* 
   const int c = blockIdx.x * BN_CH + cl;
   const long long HW = (long long)x.h * x.w;
   const long long P = HW * x.n;
+  const long long p_lo = (long long)blockIdx.y * per_split;
+  const long long p_hi = p_lo + per_split < P ? p_lo + per_split : P;
   float s0 = 0.f, s1 = 0.f;
   if (c < x.c) {
     const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
     const float m = mean[c], rstd = rsqrtf(var[c] + eps);
-    for (long long p = pl; p < P; p += BN_PL) {
+    for (long long p = p_lo + pl; p < p_hi; p += BN_PL) {
       int n, h, w;
       pix_decode(p, HW, x.w, n, h, w);
       float xhat = (x.ld(x.off(n, c, h, w)) - m) * rstd;
@@ -427,19 +473,45 @@ bn_bwd_reduce_kernel(TV x, TV dy, const float* __restrict__ gamma, const float* 
     if (cc < x.c) {
       double t0 = 0.0, t1 = 0.0;
       for (int i = 0; i < BN_PL; ++i) { t0 += red0[i][threadIdx.x]; t1 += red1[i][threadIdx.x]; }
-      sum_dz[cc] = (float)t0;
-      sum_dz_xhat[cc] = (float)t1;
+      float* o = part + ((size_t)blockIdx.y * x.c + cc) * 2;
+      o[0] = (float)t0;
+      o[1] = (float)t1;
     }
   }
+}
+
+__global__ void bn_bwd_reduce_final_kernel(const float* __restrict__ part, int splits, int C,
+                                           float* __restrict__ sum_dz, float* __restrict__ sum_dz_xhat) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double t0 = 0.0, t1 = 0.0;
+  for (int s = 0; s < splits; ++s) {
+    const float* o = part + ((size_t)s * C + c) * 2;
+    t0 += o[0];
+    t1 += o[1];
+  }
+  sum_dz[c] = (float)t0;
+  sum_dz_xhat[c] = (float)t1;
 }
 
 int launch_bn_bwd_reduce(const TV& x, const TV& dy, const float* gamma, const float* beta,
                          const float* mean, const float* var, float eps, int act, float* sum_dz,
                          float* sum_dz_xhat, cudaStream_t st) {
   if (x.c == 0) return OFA_OK;
-  bn_bwd_reduce_kernel<<<(x.c + BN_CH - 1) / BN_CH, BN_THREADS, 0, st>>>(x, dy, gamma, beta, mean, var, eps, act,
-                                                                      sum_dz, sum_dz_xhat, x.sc == 1);
-  return check_launch("bn_bwd_reduce_kernel");
+  long long per_split = 0;
+  const int splits = bn_splits(x, &per_split);
+  float* part = nullptr;
+  OFA_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&part), (size_t)splits * x.c * 2 * sizeof(float), st));
+  dim3 grid((x.c + BN_CH - 1) / BN_CH, splits);
+  bn_bwd_reduce_partial_kernel<<<grid, BN_THREADS, 0, st>>>(x, dy, gamma, beta, mean, var, eps, act, part, per_split,
+                                                           x.sc == 1);
+  int rc = check_launch("bn_bwd_reduce_partial_kernel");
+  if (!rc) {
+    bn_bwd_reduce_final_kernel<<<(x.c + 127) / 128, 128, 0, st>>>(part, splits, x.c, sum_dz, sum_dz_xhat);
+    rc = check_launch("bn_bwd_reduce_final_kernel");
+  }
+  cudaFreeAsync(part, st);
+  return rc;
 }
 
 __global__ void bn_bwd_apply_kernel(TV x, TV dy, TV dx, const float* __restrict__ gamma,

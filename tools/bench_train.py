@@ -1,0 +1,55 @@
+"""C3 (BASELINE.json configs[2]) on one GPU: progressive-shrinking training step of OFAMobileNetS4 on a batch of
+64 synthetic 96x96 HR patches (24x24 LR in), forward + backward through the library's kernels.  Not the
+headline bench; prints ms/step and patches/s.
+    python tools/bench_train.py [--batch 64] [--steps 5]
+"""
+import argparse, os, random, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'ofa-for-super-resolution_b200'))
+sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+import torch
+import ofa_b200
+import ofa_sr_oracle as O
+from ofa_b200 import backend as B
+from ofa_b200.elastic_nn.modules.dynamic_op import DynamicSeparableConv2d
+from ofa_b200.elastic_nn.networks import OFAMobileNetS4
+
+ap = argparse.ArgumentParser()
+ap.add_argument('--batch', type=int, default=64)
+ap.add_argument('--steps', type=int, default=5)
+ap.add_argument('--max', action='store_true', help='max subnet instead of sampled ones')
+a = ap.parse_args()
+dev = torch.device('cuda:0')
+DynamicSeparableConv2d.KERNEL_TRANSFORM_MODE = 1
+cfg = dict(ks_list=[3, 5, 7], expand_ratio_list=[3, 4, 6], depth_list=[2, 3, 4], pixelshuffle_depth_list=[1, 2])
+net = OFAMobileNetS4(**{k: list(v) for k, v in cfg.items()})
+spec = O.SuperNetSpec('s4', cfg['ks_list'], cfg['expand_ratio_list'], cfg['depth_list'], [1, 2])
+net.load_state_dict(O.synth_state_dict(spec.param_shapes(), 7))
+net = net.to(dev).train()
+lr_img = torch.rand(a.batch, 3, 24, 24, device=dev)
+hr_img = torch.rand(a.batch, 3, 96, 96, device=dev)
+
+
+def step(i):
+    net.zero_grad(set_to_none=True)
+    random.seed(i)
+    if a.max:
+        net.set_active_subnet(ks=7, e=6, d=4, pixel_d=2)
+    else:
+        net.sample_active_subnet()
+        net.set_active_subnet(pixel_d=2)
+    loss = torch.nn.functional.mse_loss(net(lr_img), hr_img)
+    loss.backward()
+    return loss
+
+
+for i in range(2):
+    step(i)
+torch.cuda.synchronize()
+B.launch_count_reset()
+t0 = time.perf_counter()
+for i in range(a.steps):
+    step(10 + i)
+torch.cuda.synchronize()
+dt = (time.perf_counter() - t0) / a.steps
+print('train step: %.2f ms  %.1f patches/s  (%d library launches/step)' % (dt * 1e3, a.batch / dt, B.launch_count() // a.steps))
