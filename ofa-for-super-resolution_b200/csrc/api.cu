@@ -147,11 +147,11 @@ static int dw_common(const OfaTensor4* x, const OfaTensor4* y, const float* w7, 
   if ((rc = check_transform_args(kmax, m75, m53, transform_on, ks))) return rc;
   if ((rc = check_epi(epi, y))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  bool fast_ok = !flip && dw_fast_supported(x, y, ks, epi);
+  bool fast_ok = dw_fast_supported(x, y, ks, epi);
   if (impl == OFA_IMPL_FAST && !fast_ok)
     return fail(OFA_ERR_UNSUPPORTED, "depthwise FAST path needs NHWC-dense bf16 x/y with C %% 64 == 0");
   if (fast_ok && impl != OFA_IMPL_SIMT)
-    return launch_dw_fast(x, y, w7, kmax, m75, m53, transform_on, ks, epi, st);
+    return launch_dw_fast(x, y, w7, kmax, m75, m53, transform_on, ks, flip, epi, st);
   return launch_dw_simt(make_tv(x), make_tv(y), w7, kmax, m75, m53, transform_on, ks, flip, make_epi(epi), st);
 }
 
@@ -163,7 +163,7 @@ int ofa_dw_fwd(const OfaTensor4* x, const OfaTensor4* y, const float* w7, int32_
 
 int ofa_dw_bwd_data(const OfaTensor4* dy, const OfaTensor4* dx, const float* w7, int32_t kmax,
                     const float* m75, const float* m53, int32_t transform_on, int32_t ks, void* stream) {
-  return dw_common(dy, dx, w7, kmax, m75, m53, transform_on, ks, 1, nullptr, OFA_IMPL_SIMT, stream);
+  return dw_common(dy, dx, w7, kmax, m75, m53, transform_on, ks, 1, nullptr, OFA_IMPL_AUTO, stream);
 }
 
 int ofa_conv_fwd(const OfaConvArgs* a, int32_t impl, void* stream) {

@@ -22,7 +22,7 @@ constexpr int THREADS = 256;
 
 struct DwParams {
   int N, H, W, C;
-  int kmax, transform_on;
+  int kmax, transform_on, flip;
   const float* w7;
   const float* m75;
   const float* m53;
@@ -121,7 +121,7 @@ dw_fast_kernel(const __grid_constant__ CUtensorMap tmap_x, const DwParams p) {
         v = acc;
       }
     }
-    filt[j * CH + c] = v;
+    filt[(p.flip ? KS * KS - 1 - j : j) * CH + c] = v;   // flip: 180-degree rotation = the data-gradient filter
   }
   __syncthreads();
   ptx::mbar_wait(bar, 0);
@@ -189,13 +189,13 @@ bool dw_fast_supported(const OfaTensor4* x, const OfaTensor4* y, int ks, const O
 }
 
 int launch_dw_fast(const OfaTensor4* x, const OfaTensor4* y, const float* w7, int kmax, const float* m75,
-                   const float* m53, int transform_on, int ks, const OfaEpilogue* epi, cudaStream_t st) {
+                   const float* m53, int transform_on, int ks, int flip, const OfaEpilogue* epi, cudaStream_t st) {
   if (kmax != 7 && transform_on && ks < kmax && kmax != 5)
     return fail(OFA_ERR_UNSUPPORTED, "dw_fast: kmax %d", kmax);
   DwParams p;
   memset(&p, 0, sizeof(p));
   p.N = x->n; p.H = x->h; p.W = x->w; p.C = x->c;
-  p.kmax = kmax; p.transform_on = transform_on;
+  p.kmax = kmax; p.transform_on = transform_on; p.flip = flip;
   p.w7 = w7; p.m75 = m75; p.m53 = m53;
   if (epi) {
     p.gamma = epi->gamma; p.beta = epi->beta; p.mean = epi->mean; p.var = epi->var; p.eps = epi->eps;

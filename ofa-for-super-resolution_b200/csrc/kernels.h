@@ -35,7 +35,7 @@ int launch_conv_bwd_weight(const TV& x, const TV& dy, float* dw, long long w_so,
 // ---- dw_fast.cu : NHWC bf16 depthwise, smem halo tiles --------------------------------------------
 bool dw_fast_supported(const OfaTensor4* x, const OfaTensor4* y, int ks, const OfaEpilogue* epi);
 int launch_dw_fast(const OfaTensor4* x, const OfaTensor4* y, const float* w7, int kmax, const float* m75,
-                   const float* m53, int transform_on, int ks, const OfaEpilogue* epi, cudaStream_t st);
+                   const float* m53, int transform_on, int ks, int flip, const OfaEpilogue* epi, cudaStream_t st);
 
 // ---- conv_tc.cu : NHWC bf16 implicit GEMM on tcgen05 / TMEM / TMA --------------------------------
 bool conv_tc_supported(const OfaConvArgs* a);

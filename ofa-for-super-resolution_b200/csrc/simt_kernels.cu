@@ -271,6 +271,41 @@ int launch_pack_weight(const float* w, long long w_so, long long w_si, long long
 // =================================================================================================
 // elementwise: y = store(act(affine(x))) + residual
 // =================================================================================================
+// -------------------------------------------------------------------------------------------------
+// dense-NHWC fast paths: element (pixel p, channel c) lives at p * C + c, so the hot elementwise and
+// per-channel reduction kernels index with one multiply (no div/mod chains) and move channel PAIRS.
+// -------------------------------------------------------------------------------------------------
+inline bool tv_nhwc_dense(const TV& t) {
+  return t.sc == 1 && t.sw == t.c && t.sh == (long long)t.w * t.c && t.sn == (long long)t.h * t.w * t.c;
+}
+__device__ __forceinline__ float2 tv_ld2(const TV& t, long long o) {   // o even, 2 consecutive channels
+  if (t.dtype == OFA_F32) return *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(t.ptr) + o);
+  return unpack16(*reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint16_t*>(t.ptr) + o), t.dtype == OFA_F16);
+}
+__device__ __forceinline__ void tv_st2(const TV& t, long long o, float2 v) {
+  if (t.dtype == OFA_F32) *reinterpret_cast<float2*>(reinterpret_cast<float*>(t.ptr) + o) = v;
+  else *reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(t.ptr) + o) = pack16(v.x, v.y, t.dtype == OFA_F16);
+}
+inline bool tv_pair_ok(const TV& t) {
+  const int es = t.dtype == OFA_F32 ? 4 : 2;
+  return tv_nhwc_dense(t) && (t.c % 2 == 0) && (reinterpret_cast<uintptr_t>(t.ptr) % (2 * es) == 0);
+}
+
+__global__ void affine_act_nhwc_kernel(TV x, TV y, Epi epi, unsigned pairs, unsigned cpairs) {
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += gridDim.x * blockDim.x) {
+    const int c = 2 * (int)(i % cpairs);
+    float s0, h0, s1, h1;
+    epi_scale_shift(epi, c, s0, h0);
+    epi_scale_shift(epi, c + 1, s1, h1);
+    const long long o = 2ll * i;
+    float2 v = tv_ld2(x, o);
+    v.x = apply_act(fmaf(v.x, s0, h0), epi.act);
+    v.y = apply_act(fmaf(v.y, s1, h1), epi.act);
+    if (epi.res.ptr) { const float2 r = tv_ld2(epi.res, o); v.x += r.x; v.y += r.y; }
+    tv_st2(y, o, v);
+  }
+}
+
 __global__ void affine_act_kernel(TV x, TV y, Epi epi, int store, int c_is_inner) {
   const long long total = (long long)x.n * x.c * x.h * x.w;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -302,6 +337,11 @@ int launch_affine_act(const TV& x, const TV& y, const Epi& epi, int store, cudaS
   long long blocks = (total + 255) / 256;
   long long cap = (long long)sm_count() * 16;
   if (blocks > cap) blocks = cap;
+  if (store == OFA_STORE_PLAIN && total < (1ll << 32) && tv_pair_ok(x) && tv_pair_ok(y) &&
+      (!epi.res.ptr || tv_pair_ok(epi.res))) {
+    affine_act_nhwc_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, y, epi, (unsigned)(total / 2), (unsigned)(x.c / 2));
+    return check_launch("affine_act_nhwc_kernel");
+  }
   affine_act_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, y, epi, store, x.sc == 1);
   return check_launch("affine_act_kernel");
 }
@@ -369,6 +409,36 @@ bn_stats_partial_kernel(TV x, float* __restrict__ part, int splits, long long pe
   }
 }
 
+// dense NHWC: lane = channel PAIR (a block covers 64 channels), 8 pixel lanes, one multiply per element
+__global__ void __launch_bounds__(BN_THREADS)
+bn_stats_partial_nhwc_kernel(TV x, float* __restrict__ part, long long per_split) {
+  __shared__ Wf red[BN_PL][2 * BN_CH + 1];
+  const int cl = threadIdx.x % BN_CH, pl = threadIdx.x / BN_CH;
+  const int c = (blockIdx.x * BN_CH + cl) * 2;
+  const long long P = (long long)x.n * x.h * x.w;
+  const long long p_lo = (long long)blockIdx.y * per_split;
+  const long long p_hi = p_lo + per_split < P ? p_lo + per_split : P;
+  Wf w0 = {0.f, 0.f, 0.f}, w1 = {0.f, 0.f, 0.f};
+  if (c < x.c)
+    for (long long p = p_lo + pl; p < p_hi; p += BN_PL) {
+      const float2 v = tv_ld2(x, p * x.c + c);
+      wf_add(w0, v.x);
+      wf_add(w1, v.y);
+    }
+  red[pl][2 * cl] = w0;
+  red[pl][2 * cl + 1] = w1;
+  __syncthreads();
+  if (threadIdx.x < 2 * BN_CH) {
+    const int cc = blockIdx.x * 2 * BN_CH + threadIdx.x;
+    if (cc < x.c) {
+      Wf t = red[0][threadIdx.x];
+      for (int i = 1; i < BN_PL; ++i) wf_merge(t, red[i][threadIdx.x]);
+      float* o = part + ((size_t)blockIdx.y * x.c + cc) * 3;
+      o[0] = t.n; o[1] = t.mean; o[2] = t.m2;
+    }
+  }
+}
+
 __global__ void bn_stats_final_kernel(const float* __restrict__ part, int splits, int C, float* __restrict__ mean,
                                       float* __restrict__ var) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -406,9 +476,16 @@ int launch_bn_stats(const TV& x, float* mean, float* var, cudaStream_t st) {
   const int splits = bn_splits(x, &per_split);
   float* part = nullptr;
   OFA_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&part), (size_t)splits * x.c * 3 * sizeof(float), st));
-  dim3 grid((x.c + BN_CH - 1) / BN_CH, splits);
-  bn_stats_partial_kernel<<<grid, BN_THREADS, 0, st>>>(x, part, splits, per_split, x.sc == 1);
-  int rc = check_launch("bn_stats_partial_kernel");
+  int rc;
+  if (tv_pair_ok(x)) {
+    dim3 grid((x.c + 2 * BN_CH - 1) / (2 * BN_CH), splits);
+    bn_stats_partial_nhwc_kernel<<<grid, BN_THREADS, 0, st>>>(x, part, per_split);
+    rc = check_launch("bn_stats_partial_nhwc_kernel");
+  } else {
+    dim3 grid((x.c + BN_CH - 1) / BN_CH, splits);
+    bn_stats_partial_kernel<<<grid, BN_THREADS, 0, st>>>(x, part, splits, per_split, x.sc == 1);
+    rc = check_launch("bn_stats_partial_kernel");
+  }
   if (!rc) {
     bn_stats_final_kernel<<<(x.c + 127) / 128, 128, 0, st>>>(part, splits, x.c, mean, var);
     rc = check_launch("bn_stats_final_kernel");
@@ -480,6 +557,47 @@ bn_bwd_reduce_partial_kernel(TV x, TV dy, const float* __restrict__ gamma, const
   }
 }
 
+__global__ void __launch_bounds__(BN_THREADS)
+bn_bwd_reduce_partial_nhwc_kernel(TV x, TV dy, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                  const float* __restrict__ mean, const float* __restrict__ var, float eps, int act,
+                                  float* __restrict__ part, long long per_split) {
+  __shared__ float red0[BN_PL][2 * BN_CH + 1];
+  __shared__ float red1[BN_PL][2 * BN_CH + 1];
+  const int cl = threadIdx.x % BN_CH, pl = threadIdx.x / BN_CH;
+  const int c = (blockIdx.x * BN_CH + cl) * 2;
+  const long long P = (long long)x.n * x.h * x.w;
+  const long long p_lo = (long long)blockIdx.y * per_split;
+  const long long p_hi = p_lo + per_split < P ? p_lo + per_split : P;
+  float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+  if (c < x.c) {
+    const float g0 = gamma ? gamma[c] : 1.f, g1 = gamma ? gamma[c + 1] : 1.f;
+    const float be0 = beta ? beta[c] : 0.f, be1 = beta ? beta[c + 1] : 0.f;
+    const float m0 = mean[c], m1 = mean[c + 1];
+    const float r0 = rsqrtf(var[c] + eps), r1 = rsqrtf(var[c + 1] + eps);
+    for (long long p = p_lo + pl; p < p_hi; p += BN_PL) {
+      const long long o = p * x.c + c;
+      const float2 xv = tv_ld2(x, o), gv = tv_ld2(dy, o);
+      const float xh0 = (xv.x - m0) * r0, xh1 = (xv.y - m1) * r1;
+      const float dz0 = gv.x * act_grad(fmaf(g0, xh0, be0), act), dz1 = gv.y * act_grad(fmaf(g1, xh1, be1), act);
+      a0 += dz0; a1 += dz1;
+      b0 = fmaf(dz0, xh0, b0); b1 = fmaf(dz1, xh1, b1);
+    }
+  }
+  red0[pl][2 * cl] = a0; red0[pl][2 * cl + 1] = a1;
+  red1[pl][2 * cl] = b0; red1[pl][2 * cl + 1] = b1;
+  __syncthreads();
+  if (threadIdx.x < 2 * BN_CH) {
+    const int cc = blockIdx.x * 2 * BN_CH + threadIdx.x;
+    if (cc < x.c) {
+      double t0 = 0.0, t1 = 0.0;
+      for (int i = 0; i < BN_PL; ++i) { t0 += red0[i][threadIdx.x]; t1 += red1[i][threadIdx.x]; }
+      float* o = part + ((size_t)blockIdx.y * x.c + cc) * 2;
+      o[0] = (float)t0;
+      o[1] = (float)t1;
+    }
+  }
+}
+
 __global__ void bn_bwd_reduce_final_kernel(const float* __restrict__ part, int splits, int C,
                                            float* __restrict__ sum_dz, float* __restrict__ sum_dz_xhat) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -502,10 +620,18 @@ int launch_bn_bwd_reduce(const TV& x, const TV& dy, const float* gamma, const fl
   const int splits = bn_splits(x, &per_split);
   float* part = nullptr;
   OFA_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&part), (size_t)splits * x.c * 2 * sizeof(float), st));
-  dim3 grid((x.c + BN_CH - 1) / BN_CH, splits);
-  bn_bwd_reduce_partial_kernel<<<grid, BN_THREADS, 0, st>>>(x, dy, gamma, beta, mean, var, eps, act, part, per_split,
-                                                           x.sc == 1);
-  int rc = check_launch("bn_bwd_reduce_partial_kernel");
+  int rc;
+  if (tv_pair_ok(x) && tv_pair_ok(dy)) {
+    dim3 grid((x.c + 2 * BN_CH - 1) / (2 * BN_CH), splits);
+    bn_bwd_reduce_partial_nhwc_kernel<<<grid, BN_THREADS, 0, st>>>(x, dy, gamma, beta, mean, var, eps, act, part,
+                                                                  per_split);
+    rc = check_launch("bn_bwd_reduce_partial_nhwc_kernel");
+  } else {
+    dim3 grid((x.c + BN_CH - 1) / BN_CH, splits);
+    bn_bwd_reduce_partial_kernel<<<grid, BN_THREADS, 0, st>>>(x, dy, gamma, beta, mean, var, eps, act, part, per_split,
+                                                             x.sc == 1);
+    rc = check_launch("bn_bwd_reduce_partial_kernel");
+  }
   if (!rc) {
     bn_bwd_reduce_final_kernel<<<(x.c + 127) / 128, 128, 0, st>>>(part, splits, x.c, sum_dz, sum_dz_xhat);
     rc = check_launch("bn_bwd_reduce_final_kernel");
@@ -546,6 +672,31 @@ __global__ void bn_bwd_apply_kernel(TV x, TV dy, TV dx, const float* __restrict_
   }
 }
 
+__global__ void bn_bwd_apply_nhwc_kernel(TV x, TV dy, TV dx, const float* __restrict__ gamma,
+                                         const float* __restrict__ beta, const float* __restrict__ mean,
+                                         const float* __restrict__ var, float eps, int act, int training,
+                                         const float* __restrict__ sum_dz, const float* __restrict__ sum_dz_xhat,
+                                         unsigned pairs, unsigned cpairs) {
+  const float invP = 1.f / (float)((long long)x.n * x.h * x.w);
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += gridDim.x * blockDim.x) {
+    const int c = 2 * (int)(i % cpairs);
+    const long long o = 2ll * i;
+    const float2 xv = tv_ld2(x, o), gv = tv_ld2(dy, o);
+    float2 out;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int cc = c + k;
+      const float g = gamma ? gamma[cc] : 1.f, b = beta ? beta[cc] : 0.f;
+      const float m = mean ? mean[cc] : 0.f, rstd = var ? rsqrtf(var[cc] + eps) : 1.f;
+      const float xhat = ((k ? xv.y : xv.x) - m) * rstd;
+      const float dz = (k ? gv.y : gv.x) * act_grad(fmaf(g, xhat, b), act);
+      const float v = training ? g * rstd * (dz - sum_dz[cc] * invP - xhat * sum_dz_xhat[cc] * invP) : g * rstd * dz;
+      if (k) out.y = v; else out.x = v;
+    }
+    tv_st2(dx, o, out);
+  }
+}
+
 int launch_bn_bwd_apply(const TV& x, const TV& dy, const TV& dx, const float* gamma, const float* beta,
                         const float* mean, const float* var, float eps, int act, int training,
                         const float* sum_dz, const float* sum_dz_xhat, cudaStream_t st) {
@@ -554,6 +705,12 @@ int launch_bn_bwd_apply(const TV& x, const TV& dy, const TV& dx, const float* ga
   long long blocks = (total + 255) / 256;
   long long cap = (long long)sm_count() * 16;
   if (blocks > cap) blocks = cap;
+  if (total < (1ll << 32) && tv_pair_ok(x) && tv_pair_ok(dy) && tv_pair_ok(dx)) {
+    bn_bwd_apply_nhwc_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, dy, dx, gamma, beta, mean, var, eps, act, training,
+                                                               sum_dz, sum_dz_xhat, (unsigned)(total / 2),
+                                                               (unsigned)(x.c / 2));
+    return check_launch("bn_bwd_apply_nhwc_kernel");
+  }
   bn_bwd_apply_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, dy, dx, gamma, beta, mean, var, eps, act, training,
                                                         sum_dz, sum_dz_xhat, x.sc == 1);
   return check_launch("bn_bwd_apply_kernel");

@@ -7,6 +7,7 @@ of twice154/ofa-for-super-resolution, behind the reference's own `ofa/elastic_nn
 All activation math runs in libofa_sr_b200.so (include/ofa_sr_b200.h); there is no CPU fallback.
 """
 from . import backend, functional  # noqa: F401
-from .functional import set_compute_dtype, get_compute_dtype, set_impl  # noqa: F401
+from .functional import (set_compute_dtype, get_compute_dtype, set_impl, set_train_dtype, get_train_dtype,  # noqa: F401
+                         set_mid_dtype)
 
 __version__ = '0.1.0'

@@ -16,7 +16,7 @@ import torch
 
 from . import backend as B
 
-_state = {'compute_dtype': torch.float16, 'impl': B.IMPL_AUTO, 'mid_dtype': B.OFA_F16}
+_state = {'compute_dtype': torch.float16, 'impl': B.IMPL_AUTO, 'mid_dtype': B.OFA_F16, 'train_dtype': torch.float32}
 
 
 def set_compute_dtype(dtype):
@@ -33,6 +33,19 @@ def set_mid_dtype(dtype):
     torch.float16 (default: 3 more mantissa bits than bf16 on [0, 6]) or torch.bfloat16."""
     assert dtype in (torch.float16, torch.bfloat16)
     _state['mid_dtype'] = B.OFA_F16 if dtype == torch.float16 else B.OFA_BF16
+
+
+def set_train_dtype(dtype):
+    """Activation / activation-gradient storage of the autograd (training) path.  torch.float32 (default):
+    the exact CUDA-core kernels.  torch.bfloat16: mixed precision — fp32 master weights, bf16 activations and
+    gradients, forward convs and data gradients on the tcgen05 implicit-GEMM kernel, fp32 accumulation,
+    fp32 weight gradients (progressive-shrinking training as BASELINE.json configs[2] names it)."""
+    assert dtype in (torch.float32, torch.bfloat16)
+    _state['train_dtype'] = dtype
+
+
+def get_train_dtype():
+    return _state['train_dtype']
 
 
 def get_compute_dtype():
@@ -182,14 +195,43 @@ def _conv_out(x, cout, store, dtype, nchw=False):
     return torch.empty(shape, dtype=dtype, device=x.device, memory_format=torch.channels_last)
 
 
+_train_caches = {}
+
+
+def _train_cache(w, kind):
+    key = (w.data_ptr(), kind)
+    c = _train_caches.get(key)
+    if c is None:
+        c = _train_caches[key] = PackedWeightCache()
+    return c
+
+
+def _is_half_nhwc(t):
+    return t.dtype in (torch.bfloat16, torch.float16) and t.is_contiguous(memory_format=torch.channels_last)
+
+
 class ConvFn(torch.autograd.Function):
-    """y = conv2d(x, w[:cout, :cin]), stride 1, same padding; the slice is addressed in place."""
+    """y = conv2d(x, w[:cout, :cin]), stride 1, same padding; the slice is addressed in place.
+    fp32 activations: the exact CUDA-core kernels.  16-bit NHWC activations (set_train_dtype): forward and
+    data gradient run on the tcgen05 implicit-GEMM kernel (the data gradient is the same conv with the
+    weight slice transposed and rotated by 180 degrees, packed from the fp32 master with swapped /
+    negative strides); the weight gradient accumulates in fp32 into the slice."""
 
     @staticmethod
     def forward(ctx, x, w, cin, cout, ks):
-        y = _conv_out(x, cout, B.STORE_PLAIN, x.dtype)
-        a = _conv_args(x, y, w, cin, cout, ks)
-        B.check(B.lib().ofa_conv_fwd(byref(a), B.IMPL_SIMT, _stream(x)))
+        tdt = _state['train_dtype']
+        ydt = tdt if tdt != torch.float32 else x.dtype
+        y = _conv_out(x, cout, B.STORE_PLAIN, ydt)
+        impl, w16, cin_pad, cout_pad = B.IMPL_SIMT, None, 0, 0
+        if tdt != torch.float32:
+            if _is_half_nhwc(x) and cin % 64 == 0:
+                cache = _train_cache(w, ('f', cin, cout))
+                w16 = cache.get(w, cin, cout, ks, B.STORE_PLAIN, x.dtype)
+                cin_pad, cout_pad, impl = cache.cin_pad, cache.cout_pad, B.IMPL_AUTO
+            elif cin <= 4 and cout == 64:
+                impl = B.IMPL_AUTO        # stem kernel: fp32 image in, 16-bit NHWC out
+        a = _conv_args(x, y, w, cin, cout, ks, B.STORE_PLAIN, None, w16, cin_pad, cout_pad)
+        B.check(B.lib().ofa_conv_fwd(byref(a), impl, _stream(x)))
         ctx.save_for_backward(x, w)
         ctx.dims = (cin, cout, ks)
         return y
@@ -201,13 +243,29 @@ class ConvFn(torch.autograd.Function):
         L = B.lib()
         st = _stream(x)
         so, si, sh, sw = w.stride()
+        if dy.dtype != torch.float32 and not dy.is_contiguous(memory_format=torch.channels_last):
+            dy = dy.contiguous(memory_format=torch.channels_last)
         tdy = B.t4(dy)
         dx = dw = None
         if ctx.needs_input_grad[0]:
             n, _, h, wd = x.shape
             dx = B.new_nhwc(n, cin, h, wd, dy.dtype, dy.device)
-            tdx = B.t4(dx)
-            B.check(L.ofa_conv_bwd_data(byref(tdy), byref(tdx), B.fptr(w), so, si, sh, sw, cin, cout, ks, st))
+            if _is_half_nhwc(dy) and cout % 64 == 0 and _state['train_dtype'] != torch.float32:
+                # dX = conv(dY, W^T rotated 180 deg): pack W[o, i, ks-1-ky, ks-1-kx] as a (cout -> cin) weight
+                cache = _train_cache(w, ('b', cin, cout))
+                key = (w.data_ptr(), w._version, tuple(w.shape), cin, cout, ks, str(w.device), dy.dtype)
+                if cache._key != key:
+                    cin_pad_b, cout_pad_b = cout, (cin + 15) // 16 * 16
+                    buf = torch.empty((ks * ks, cout_pad_b, cin_pad_b), dtype=dy.dtype, device=w.device)
+                    last = (ks - 1) * sh + (ks - 1) * sw
+                    B.check(L.ofa_pack_weight_16(w.data_ptr() + 4 * last, si, so, -sh, -sw, cout, cin, ks, cin_pad_b,
+                                                 cout_pad_b, B.STORE_PLAIN, B.dtype_code(dy.dtype), buf.data_ptr(), st))
+                    cache._key, cache._buf, cache.cin_pad, cache.cout_pad = key, buf, cin_pad_b, cout_pad_b
+                a = _conv_args(dy, dx, None, cout, cin, ks, B.STORE_PLAIN, None, cache._buf, cache.cin_pad, cache.cout_pad)
+                B.check(L.ofa_conv_fwd(byref(a), B.IMPL_FAST, st))
+            else:
+                tdx = B.t4(dx)
+                B.check(L.ofa_conv_bwd_data(byref(tdy), byref(tdx), B.fptr(w), so, si, sh, sw, cin, cout, ks, st))
         if ctx.needs_input_grad[1]:
             dw = torch.zeros_like(w)
             tx = B.t4(x)

@@ -103,8 +103,11 @@ class ConvLayer(MyModule):
         y = OF.conv2d(x, w, self.in_channels, self.out_channels, self.kernel_size)
         if self._store == B.STORE_PLAIN:
             if bn is not None:
-                return OF.bn_act(y, bn, self.out_channels, self._act_code, residual)
-            assert self._act_code == B.ACT_NONE and residual is None
+                y = OF.bn_act(y, bn, self.out_channels, self._act_code, residual)
+            else:
+                assert self._act_code == B.ACT_NONE and residual is None
+            if self.out_dtype is not None and y.dtype != self.out_dtype:
+                y = y.to(self.out_dtype)      # mixed-precision training: the caller's loss sees fp32
             return y
         if bn is not None:
             y = OF.bn_act(y, bn, self.out_channels, B.ACT_NONE, None)

@@ -18,8 +18,10 @@ ap = argparse.ArgumentParser()
 ap.add_argument('--batch', type=int, default=64)
 ap.add_argument('--steps', type=int, default=5)
 ap.add_argument('--max', action='store_true', help='max subnet instead of sampled ones')
+ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
 a = ap.parse_args()
 dev = torch.device('cuda:0')
+ofa_b200.set_train_dtype(torch.bfloat16 if a.dtype == 'bf16' else torch.float32)
 DynamicSeparableConv2d.KERNEL_TRANSFORM_MODE = 1
 cfg = dict(ks_list=[3, 5, 7], expand_ratio_list=[3, 4, 6], depth_list=[2, 3, 4], pixelshuffle_depth_list=[1, 2])
 net = OFAMobileNetS4(**{k: list(v) for k, v in cfg.items()})
@@ -52,4 +54,4 @@ for i in range(a.steps):
     step(10 + i)
 torch.cuda.synchronize()
 dt = (time.perf_counter() - t0) / a.steps
-print('train step: %.2f ms  %.1f patches/s  (%d library launches/step)' % (dt * 1e3, a.batch / dt, B.launch_count() // a.steps))
+print(a.dtype, 'train step: %.2f ms  %.1f patches/s  (%d library launches/step)' % (dt * 1e3, a.batch / dt, B.launch_count() // a.steps))
