@@ -450,6 +450,8 @@ int ofa_conv_bwd_weight(const OfaTensor4* x, const OfaTensor4* dy, float* dw, in
   OFA_REQUIRE(dw != nullptr, "null dw");
   OFA_REQUIRE(x->c == cin && dy->c == cout && dy->n == x->n && dy->h == x->h && dy->w == x->w,
               "conv_bwd_weight: shape mismatch");
+  if (wgrad_tc_supported(x, dy, cin, cout, ks))
+    return launch_wgrad_tc(x, dy, dw, w_so, w_si, w_sh, w_sw, cin, cout, ks, (cudaStream_t)stream);
   return launch_conv_bwd_weight(make_tv(x), make_tv(dy), dw, w_so, w_si, w_sh, w_sw, cin, cout, ks,
                                 (cudaStream_t)stream);
 }

@@ -47,6 +47,11 @@ int launch_conv_out_rows(const OfaConvArgs* a, cudaStream_t st);
 bool conv_stem_supported(const OfaConvArgs* a);
 int launch_conv_stem(const OfaConvArgs* a, cudaStream_t st);
 
+// ---- wgrad_tc.cu : dense-conv weight gradient on tcgen05 (pixels are K; both operands MN-major) ---------
+bool wgrad_tc_supported(const OfaTensor4* x, const OfaTensor4* dy, int cin, int cout, int ks);
+int launch_wgrad_tc(const OfaTensor4* x, const OfaTensor4* dy, float* dw, long long w_so, long long w_si,
+                    long long w_sh, long long w_sw, int cin, int cout, int ks, cudaStream_t st);
+
 // ---- mbconv_planar.cu : MBConv block on channel-planar 16-bit intermediates (tcgen05) ---------------
 bool mbconv_planar_supported(const OfaMBConvArgs* a);
 int launch_pack_block_weights(const float* w_exp, long long e_so, long long e_si, const float* w_proj,

@@ -461,11 +461,11 @@ __global__ void bn_stats_final_kernel(const float* __restrict__ part, int splits
 static int bn_splits(const TV& x, long long* per_split) {
   const long long P = (long long)x.n * x.h * x.w;
   const int groups = (x.c + BN_CH - 1) / BN_CH;
-  long long want = (4LL * sm_count() + groups - 1) / groups;
-  long long maxs = (P + 4095) / 4096;
+  long long want = (8LL * sm_count() + groups - 1) / groups;
+  long long maxs = (P + 255) / 256;
   if (want > maxs) want = maxs;
   if (want < 1) want = 1;
-  if (want > 1024) want = 1024;
+  if (want > 48) want = 48;     // the finalize kernel walks the splits serially per channel
   *per_split = (P + want - 1) / want;
   return (int)((P + *per_split - 1) / *per_split);
 }
@@ -770,12 +770,79 @@ dw_bwd_filter_kernel(TV x, TV dy, float* __restrict__ dw, long long pix_per_bloc
   }
 }
 
+// dense-NHWC variant: lane = channel pair, 32-bit pixel arithmetic, paired loads (the re-reads of x hit L1)
+template <int KS>
+__global__ void __launch_bounds__(BN_THREADS)
+dw_bwd_filter_nhwc_kernel(TV x, TV dy, float* __restrict__ dw, int pix_per_block) {
+  __shared__ float red[BN_PL][2 * BN_CH + 1];
+  const int cl = threadIdx.x % BN_CH, pl = threadIdx.x / BN_CH;
+  const int c = (blockIdx.x * BN_CH + cl) * 2;
+  const int H = x.h, W = x.w, C = x.c;
+  const int HW = H * W, P = HW * x.n;
+  const int p_begin = blockIdx.y * pix_per_block;
+  const int p_end = min(p_begin + pix_per_block, P);
+  constexpr int R = KS / 2;
+  float2 acc[KS * KS];
+#pragma unroll
+  for (int j = 0; j < KS * KS; ++j) acc[j] = make_float2(0.f, 0.f);
+  if (c < C)
+    for (int p = p_begin + pl; p < p_end; p += BN_PL) {
+      const int n = p / HW, r = p - n * HW;
+      const int h = r / W, w = r - h * W;
+      const float2 g = tv_ld2(dy, (long long)p * C + c);
+#pragma unroll
+      for (int ky = 0; ky < KS; ++ky) {
+        const int ih = h + ky - R;
+        if (ih < 0 || ih >= H) continue;
+#pragma unroll
+        for (int kx = 0; kx < KS; ++kx) {
+          const int iw = w + kx - R;
+          if (iw < 0 || iw >= W) continue;
+          const float2 v = tv_ld2(x, (long long)(p + (ky - R) * W + (kx - R)) * C + c);
+          acc[ky * KS + kx].x = fmaf(v.x, g.x, acc[ky * KS + kx].x);
+          acc[ky * KS + kx].y = fmaf(v.y, g.y, acc[ky * KS + kx].y);
+        }
+      }
+    }
+#pragma unroll
+  for (int j = 0; j < KS * KS; ++j) {
+    red[pl][2 * cl] = acc[j].x;
+    red[pl][2 * cl + 1] = acc[j].y;
+    __syncthreads();
+    if (threadIdx.x < 2 * BN_CH) {
+      const int cc = blockIdx.x * 2 * BN_CH + threadIdx.x;
+      if (cc < C) {
+        float t = 0.f;
+        for (int i = 0; i < BN_PL; ++i) t += red[i][threadIdx.x];
+        atomicAdd(&dw[(size_t)cc * KS * KS + j], t);
+      }
+    }
+    __syncthreads();
+  }
+}
+
 int launch_dw_bwd_filter(const TV& x, const TV& dy, int ks, float* dw, cudaStream_t st) {
   if (x.c == 0) return OFA_OK;
   cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)x.c * ks * ks, st);
   if (e != cudaSuccess) return fail(OFA_ERR_CUDA, "memset dw: %s", cudaGetErrorString(e));
   long long P = (long long)x.n * x.h * x.w;
   if (P == 0) return OFA_OK;
+  if (tv_pair_ok(x) && tv_pair_ok(dy) && P < (1ll << 30)) {
+    const int cb2 = (x.c + 2 * BN_CH - 1) / (2 * BN_CH);
+    long long sp = (long long)sm_count() * 8 / cb2;
+    if (sp < 1) sp = 1;
+    long long ppb2 = (P + sp - 1) / sp;
+    if (ppb2 < 64) ppb2 = 64;
+    sp = (P + ppb2 - 1) / ppb2;
+    dim3 grid2(cb2, (unsigned)sp);
+    switch (ks) {
+      case 3: dw_bwd_filter_nhwc_kernel<3><<<grid2, BN_THREADS, 0, st>>>(x, dy, dw, (int)ppb2); break;
+      case 5: dw_bwd_filter_nhwc_kernel<5><<<grid2, BN_THREADS, 0, st>>>(x, dy, dw, (int)ppb2); break;
+      case 7: dw_bwd_filter_nhwc_kernel<7><<<grid2, BN_THREADS, 0, st>>>(x, dy, dw, (int)ppb2); break;
+      default: return fail(OFA_ERR_UNSUPPORTED, "depthwise kernel size %d", ks);
+    }
+    return check_launch("dw_bwd_filter_nhwc_kernel");
+  }
   int cb = (x.c + BN_CH - 1) / BN_CH;
   long long splits = (long long)sm_count() * 4 / cb;
   if (splits < 1) splits = 1;

@@ -134,7 +134,7 @@ class DwConvFn(torch.autograd.Function):
         tdy = B.t4(dy)
         dx = dw7 = dm75 = dm53 = None
         if ctx.needs_input_grad[0]:
-            dx = B.new_nhwc(n, c, h, w, dy.dtype, dy.device)
+            dx = B.new_nhwc(n, c, h, w, x.dtype, dy.device)
             tdx = B.t4(dx)
             B.check(L.ofa_dw_bwd_data(byref(tdy), byref(tdx), B.fptr(w7), kmax, p75, p53,
                                       int(bool(transform_on)), ks, st))
@@ -221,6 +221,8 @@ class ConvFn(torch.autograd.Function):
     def forward(ctx, x, w, cin, cout, ks):
         tdt = _state['train_dtype']
         ydt = tdt if tdt != torch.float32 else x.dtype
+        if cout < 16:
+            ydt = torch.float32   # thin tensors (X4's 3-channel learned LR image) stay fp32, as in inference
         y = _conv_out(x, cout, B.STORE_PLAIN, ydt)
         impl, w16, cin_pad, cout_pad = B.IMPL_SIMT, None, 0, 0
         if tdt != torch.float32:
@@ -249,8 +251,8 @@ class ConvFn(torch.autograd.Function):
         dx = dw = None
         if ctx.needs_input_grad[0]:
             n, _, h, wd = x.shape
-            dx = B.new_nhwc(n, cin, h, wd, dy.dtype, dy.device)
-            if _is_half_nhwc(dy) and cout % 64 == 0 and _state['train_dtype'] != torch.float32:
+            dx = B.new_nhwc(n, cin, h, wd, x.dtype, dy.device)     # gradients carry their activation's type
+            if _is_half_nhwc(dy) and dy.dtype == x.dtype and cout % 64 == 0 and _state['train_dtype'] != torch.float32:
                 # dX = conv(dY, W^T rotated 180 deg): pack W[o, i, ks-1-ky, ks-1-kx] as a (cout -> cin) weight
                 cache = _train_cache(w, ('b', cin, cout))
                 key = (w.data_ptr(), w._version, tuple(w.shape), cin, cout, ks, str(w.device), dy.dtype)
@@ -268,8 +270,29 @@ class ConvFn(torch.autograd.Function):
                 B.check(L.ofa_conv_bwd_data(byref(tdy), byref(tdx), B.fptr(w), so, si, sh, sw, cin, cout, ks, st))
         if ctx.needs_input_grad[1]:
             dw = torch.zeros_like(w)
-            tx = B.t4(x)
-            B.check(L.ofa_conv_bwd_weight(byref(tx), byref(tdy), dw.data_ptr(), so, si, sh, sw, cin, cout, ks, st))
+            tdt = _state['train_dtype']
+            if tdt != torch.float32 and cin == 64 and cout < 8 and _is_half_nhwc(x):
+                # thin output (64 -> 3): pad dY to 8 channels so the tcgen05 weight-gradient kernel applies
+                dy8 = torch.empty((dy.shape[0], 8, dy.shape[2], dy.shape[3]), dtype=x.dtype, device=dy.device,
+                                  memory_format=torch.channels_last).zero_()
+                dy8[:, :cout] = dy
+                dw8 = torch.zeros((8, w.shape[1], ks, ks), dtype=torch.float32, device=w.device)
+                t8 = B.t4(dy8)
+                tx = B.t4(x)
+                B.check(L.ofa_conv_bwd_weight(byref(tx), byref(t8), dw8.data_ptr(), *dw8.stride(), cin, 8, ks, st))
+                dw[:cout] = dw8[:cout]
+            elif tdt != torch.float32 and cout == 64 and cin < 8 and _is_half_nhwc(dy):
+                # thin input (the stem, 3 -> 64): pad X to 8 channels
+                x8 = torch.empty((x.shape[0], 8, x.shape[2], x.shape[3]), dtype=dy.dtype, device=dy.device,
+                                 memory_format=torch.channels_last).zero_()
+                x8[:, :cin] = x
+                dw8 = torch.zeros((w.shape[0], 8, ks, ks), dtype=torch.float32, device=w.device)
+                t8 = B.t4(x8)
+                B.check(L.ofa_conv_bwd_weight(byref(t8), byref(tdy), dw8.data_ptr(), *dw8.stride(), 8, cout, ks, st))
+                dw[:, :cin] = dw8[:, :cin]
+            else:
+                tx = B.t4(x)
+                B.check(L.ofa_conv_bwd_weight(byref(tx), byref(tdy), dw.data_ptr(), so, si, sh, sw, cin, cout, ks, st))
         return dx, dw, None, None, None
 
 
@@ -323,7 +346,7 @@ class BnActFn(torch.autograd.Function):
                                     B.fptr(var), eps, act, s0.data_ptr(), s1.data_ptr(), st))
         dx = dgamma = dbeta = None
         if ctx.needs_input_grad[0]:
-            dx = B.new_nhwc(n, c, h, w, dy.dtype, dy.device)
+            dx = B.new_nhwc(n, c, h, w, x.dtype, dy.device)
             tdx = B.t4(dx)
             B.check(L.ofa_bn_bwd_apply(byref(tx), byref(tdy), byref(tdx), _null_or(gamma), _null_or(beta),
                                        B.fptr(mean), B.fptr(var), eps, act, int(training), s0.data_ptr(),

@@ -8,13 +8,13 @@ torch.manual_seed(0)
 def cos(a, b):
     a = a.float().flatten(); b = b.float().flatten()
     return float(a @ b / (a.norm() * b.norm()))
-for (cin, cout, ks, cmi, cmo) in [(64, 384, 1, 64, 384), (384, 64, 1, 384, 64), (192, 64, 1, 384, 64), (64, 64, 5, 64, 64), (64, 256, 5, 64, 256), (64, 3, 5, 64, 3), (64, 192, 1, 64, 384)]:
+for (cin, cout, ks, cmi, cmo) in [(64, 384, 1, 64, 384), (384, 64, 1, 384, 64), (192, 64, 1, 384, 64), (64, 64, 5, 64, 64), (64, 256, 5, 64, 256), (64, 3, 5, 64, 3), (64, 192, 1, 64, 384), (3, 64, 5, 3, 64), (64, 3, 3, 64, 3), (3, 64, 3, 3, 64)]:
     w = (torch.randn(cmo, cmi, ks, ks, device=dev) * 0.1).requires_grad_(True)
     x32 = torch.randn(2, cin, 12, 20, device=dev)
     res = {}
     for dt in (torch.float32, torch.bfloat16):
         ofa_b200.set_train_dtype(dt)
-        x = x32.to(dt).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+        x = (x32.to(dt) if cin >= 16 else x32.clone()).contiguous(memory_format=torch.channels_last).requires_grad_(True)
         y = OF.conv2d(x, w, cin, cout, ks)
         g = torch.randn(y.shape, device=dev, generator=torch.Generator(device=dev).manual_seed(1)).to(y.dtype).contiguous(memory_format=torch.channels_last)
         w.grad = None
