@@ -66,14 +66,25 @@ class FlatGradAllReduce:
     """Gradient exchange of data-parallel progressive-shrinking training.
 
     All parameters own a slot in one flat fp32 buffer (fixed layout, so every rank issues the same
-    collective whatever sub-network was sampled).  `reduce()` packs the available .grad tensors
-    (zeros elsewhere), all-reduces the buffer in `n_buckets` contiguous buckets (the tail of the net —
-    whose gradients are ready first in backward — goes first so the transfer overlaps the rest of the
-    pack), averages, and scatters the result back into .grad (creating it where a rank had none, so
-    the optimizer sees identical gradients everywhere)."""
+    collectives whatever sub-network was sampled; inactive blocks simply contribute zeros).  The buffer is
+    split into a TAIL segment (parameters of the layers that run last in forward, whose gradients are
+    complete first in backward) and a HEAD segment.
 
-    def __init__(self, params, n_buckets=2, process_group=None):
-        self.params = [p for p in params if p.requires_grad]
+    * `reduce()` alone: packs the available .grad tensors, all-reduces the segments (tail first) in
+      `n_buckets` buckets each, averages, and scatters the result back into .grad (creating it where a rank
+      had none, so the optimizer sees identical gradients everywhere).
+    * overlapped with backward: `watch(boundary_tensor)` before the step's LAST `loss.backward()` registers a
+      gradient hook on the activation that separates tail from head.  When autograd reaches it every tail
+      gradient is final, so the tail segment is packed and its all-reduce is launched asynchronously while
+      the head's backward is still running; `reduce()` then only has the head segment left to send.
+    """
+
+    def __init__(self, params, n_buckets=2, process_group=None, tail_params=None):
+        params = [p for p in params if p.requires_grad]
+        tail_ids = {id(p) for p in (tail_params or [])}
+        self.tail = [p for p in params if id(p) in tail_ids]
+        self.head = [p for p in params if id(p) not in tail_ids]
+        self.params = self.tail + self.head            # flat layout: tail segment first
         self.group = process_group
         self.offsets = []
         total = 0
@@ -81,21 +92,52 @@ class FlatGradAllReduce:
             self.offsets.append(total)
             total += p.numel()
         self.total = total
+        self.tail_numel = sum(p.numel() for p in self.tail)
         dev = self.params[0].device if self.params else torch.device('cpu')
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
-        cuts = [round(total * i / n_buckets) for i in range(n_buckets + 1)]
-        self.buckets = [(cuts[i], cuts[i + 1]) for i in range(n_buckets) if cuts[i + 1] > cuts[i]]
+        self.n_buckets = n_buckets
+        self._tail_handles = None
+
+    def _buckets(self, lo, hi):
+        n = hi - lo
+        cuts = [lo + round(n * i / self.n_buckets) for i in range(self.n_buckets + 1)]
+        return [(cuts[i], cuts[i + 1]) for i in range(self.n_buckets) if cuts[i + 1] > cuts[i]]
+
+    def _pack(self, first, last):
+        for p, off in zip(self.params[first:last], self.offsets[first:last]):
+            seg = self.flat[off:off + p.numel()]
+            if p.grad is not None:
+                seg.copy_(p.grad.reshape(-1))
+            else:
+                seg.zero_()
+
+    def _launch(self, lo, hi):
+        import torch.distributed as dist
+        return [dist.all_reduce(self.flat[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+                for a, b in self._buckets(lo, hi)]
+
+    def watch(self, boundary):
+        """Arm the overlap for the next backward: `boundary` is the activation tensor between the head layers
+        and the `tail_params` layers (it must require grad)."""
+        assert self.tail, 'FlatGradAllReduce(..., tail_params=...) is needed for the overlapped mode'
+
+        def _hook(grad):
+            if self._tail_handles is None:
+                self._pack(0, len(self.tail))
+                self._tail_handles = self._launch(0, self.tail_numel)
+            return grad
+        boundary.register_hook(_hook)
 
     def reduce(self):
         import torch.distributed as dist
         world = dist.get_world_size(self.group)
-        self.flat.zero_()
-        for p, off in zip(self.params, self.offsets):
-            if p.grad is not None:
-                self.flat[off:off + p.numel()].copy_(p.grad.reshape(-1))
-        handles = []
-        for lo, hi in reversed(self.buckets):
-            handles.append(dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        handles = self._tail_handles
+        if handles is None:                            # not overlapped: send the tail now
+            self._pack(0, len(self.tail))
+            handles = self._launch(0, self.tail_numel) if self.tail_numel else []
+        self._tail_handles = None
+        self._pack(len(self.tail), len(self.params))
+        handles += self._launch(self.tail_numel, self.total)
         for h in handles:
             h.wait()
         self.flat.div_(world)
@@ -105,6 +147,18 @@ class FlatGradAllReduce:
                 p.grad = g.clone()
             else:
                 p.grad.copy_(g)
+
+
+def s4_tail_parameters(net):
+    """Tail / head split of OFAMobileNetS4 for the overlapped all-reduce: everything after the trunk's long skip
+    (dec_final_conv_blocks, the PixelShuffle stages at the end of `blocks`, the output conv) is the tail; the
+    boundary activation is the input of dec_final_conv_blocks[0].  Returns (tail_params, boundary_module)."""
+    tail = list(net.dec_final_conv_blocks.parameters()) + list(net.dec_final_output_conv_block.parameters())
+    n_shuffle = len(net.block_group_info) - 4
+    for group in net.block_group_info[len(net.block_group_info) - n_shuffle:]:
+        for idx in group:
+            tail += list(net.blocks[idx].parameters())
+    return tail, net.dec_final_conv_blocks[0]
 
 
 def broadcast_parameters(module, src=0, process_group=None):

@@ -89,6 +89,54 @@ def _worker(rank, world, port, ret):
         dist.destroy_process_group()
 
 
+def _worker_overlap(rank, world, port, ret):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        head = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 5))
+        unused = torch.nn.Linear(5, 5)                 # an inactive block: no .grad on any rank
+        tail = torch.nn.Sequential(torch.nn.Linear(5, 4), torch.nn.Tanh(), torch.nn.Linear(4, 3))
+        params = list(head.parameters()) + list(unused.parameters()) + list(tail.parameters())
+        sync = P.FlatGradAllReduce(params, n_buckets=2, tail_params=list(tail.parameters()))
+        launched_in_backward = []
+        orig_launch = sync._launch
+
+        def spy(lo, hi):
+            launched_in_backward.append((lo, hi, all(p.grad is None for p in head.parameters())))
+            return orig_launch(lo, hi)
+        sync._launch = spy
+        torch.manual_seed(100 + rank)
+        x = torch.randn(8, 6)
+        h = head(x)
+        sync.watch(h)                                  # boundary activation between head and tail
+        tail(h).pow(2).sum().backward()
+        local = [None if p.grad is None else p.grad.clone() for p in params]
+        sync.reduce()
+        gathered = [None] * world
+        dist.all_gather_object(gathered, [None if g is None else g.tolist() for g in local])
+        ok = True
+        for i, p in enumerate(params):
+            parts = [torch.tensor(g[i]) if g[i] is not None else torch.zeros_like(p) for g in gathered]
+            ok = ok and p.grad is not None and torch.allclose(p.grad, sum(parts) / world, atol=1e-6)
+        # the tail segment went out while the head had no gradients yet (i.e. during backward), the rest after
+        ok = ok and len(launched_in_backward) == 2 and launched_in_backward[0] == (0, sync.tail_numel, True)
+        ok = ok and launched_in_backward[1][:2] == (sync.tail_numel, sync.total) and launched_in_backward[1][2] is False
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_flat_grad_allreduce_overlaps_backward_world2_gloo():
+    world = 2
+    port = 31500 + (os.getpid() % 2000)
+    with mp.Manager() as m:
+        ret = m.dict()
+        mp.spawn(_worker_overlap, args=(world, port, ret), nprocs=world, join=True)
+        assert dict(ret) == {0: True, 1: True}
+
+
 def test_flat_grad_allreduce_world2_gloo():
     world = 2
     port = 29500 + (os.getpid() % 2000)

@@ -20,7 +20,13 @@ ap.add_argument('--steps', type=int, default=5)
 ap.add_argument('--max', action='store_true', help='max subnet instead of sampled ones')
 ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
 a = ap.parse_args()
-dev = torch.device('cuda:0')
+rank = int(os.environ.get('RANK', '0')); world = int(os.environ.get('WORLD_SIZE', '1'))
+local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+torch.cuda.set_device(local_rank)
+dev = torch.device('cuda', local_rank)
+if world > 1:
+    import torch.distributed as dist
+    dist.init_process_group('nccl', device_id=dev)
 ofa_b200.set_train_dtype(torch.bfloat16 if a.dtype == 'bf16' else torch.float32)
 DynamicSeparableConv2d.KERNEL_TRANSFORM_MODE = 1
 cfg = dict(ks_list=[3, 5, 7], expand_ratio_list=[3, 4, 6], depth_list=[2, 3, 4], pixelshuffle_depth_list=[1, 2])
@@ -28,8 +34,17 @@ net = OFAMobileNetS4(**{k: list(v) for k, v in cfg.items()})
 spec = O.SuperNetSpec('s4', cfg['ks_list'], cfg['expand_ratio_list'], cfg['depth_list'], [1, 2])
 net.load_state_dict(O.synth_state_dict(spec.param_shapes(), 7))
 net = net.to(dev).train()
-lr_img = torch.rand(a.batch, 3, 24, 24, device=dev)
-hr_img = torch.rand(a.batch, 3, 96, 96, device=dev)
+per_rank = a.batch // world                      # batch-sharded data parallelism (strong scaling of one step)
+lr_img = torch.rand(per_rank, 3, 24, 24, device=dev)
+hr_img = torch.rand(per_rank, 3, 96, 96, device=dev)
+reducer = None
+if world > 1:
+    from ofa_b200 import parallel as P
+    P.broadcast_parameters(net, src=0)
+    tail, boundary_module = P.s4_tail_parameters(net)
+    reducer = P.FlatGradAllReduce(net.parameters(), n_buckets=2, tail_params=tail)
+    # the tail segment's all-reduce starts as soon as backward reaches the input of the tail layers
+    boundary_module.register_forward_pre_hook(lambda m, inp: reducer.watch(inp[0]) if inp[0].requires_grad else None)
 
 
 def step(i):
@@ -42,6 +57,8 @@ def step(i):
         net.set_active_subnet(pixel_d=2)
     loss = torch.nn.functional.mse_loss(net(lr_img), hr_img)
     loss.backward()
+    if reducer is not None:
+        reducer.reduce()
     return loss
 
 
@@ -54,4 +71,11 @@ for i in range(a.steps):
     step(10 + i)
 torch.cuda.synchronize()
 dt = (time.perf_counter() - t0) / a.steps
-print(a.dtype, 'train step: %.2f ms  %.1f patches/s  (%d library launches/step)' % (dt * 1e3, a.batch / dt, B.launch_count() // a.steps))
+if world > 1:
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+if rank == 0:
+    print('%d GPU(s)' % world, a.dtype, 'train step: %.2f ms  %.1f patches/s  (%d library launches/step/rank)' % (dt * 1e3, a.batch / dt, B.launch_count() // a.steps))
+if world > 1:
+    dist.destroy_process_group()
