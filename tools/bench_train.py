@@ -17,7 +17,7 @@ from ofa_b200.elastic_nn.networks import OFAMobileNetS4
 ap = argparse.ArgumentParser()
 ap.add_argument('--batch', type=int, default=64)
 ap.add_argument('--steps', type=int, default=5)
-ap.add_argument('--max', action='store_true', help='max subnet instead of sampled ones')
+ap.add_argument('--max-subnet', dest='max', action='store_true', help='max subnet instead of sampled ones')
 ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
 a = ap.parse_args()
 rank = int(os.environ.get('RANK', '0')); world = int(os.environ.get('WORLD_SIZE', '1'))
