@@ -28,7 +28,8 @@ struct DwParams {
   const float* m53;
   const float* gamma; const float* beta; const float* mean; const float* var; float eps;
   int act;
-  __nv_bfloat16* y;
+  uint16_t* y;
+  int f16;   // storage format of x and y: 1 = fp16, 0 = bf16
   int tiles_w, tiles_h;
 };
 
@@ -142,7 +143,7 @@ dw_fast_kernel(const __grid_constant__ CUtensorMap tmap_x, const DwParams p) {
       const uint32_t* row = tile + ((warp + ky) * L::HALO_W + x0) * 32 + lane;
       float2 in[RUN + KS - 1];
 #pragma unroll
-      for (int i = 0; i < RUN + KS - 1; ++i) in[i] = bf2_unpack(row[i * 32]);
+      for (int i = 0; i < RUN + KS - 1; ++i) in[i] = unpack16(row[i * 32], p.f16);
 #pragma unroll
       for (int kx = 0; kx < KS; ++kx) {
         const float2 wv = filt2[(ky * KS + kx) * 32 + lane];
@@ -151,15 +152,14 @@ dw_fast_kernel(const __grid_constant__ CUtensorMap tmap_x, const DwParams p) {
       }
     }
     if (h < p.H) {
-      __nv_bfloat16* yrow = p.y + (((size_t)n * p.H + h) * p.W) * p.C + c0 + 2 * lane;
+      uint16_t* yrow = p.y + (((size_t)n * p.H + h) * p.W) * p.C + c0 + 2 * lane;
 #pragma unroll
       for (int i = 0; i < RUN; ++i) {
         int w = w0 + x0 + i;
         if (w < p.W) {
           float a = apply_act(fmaf(acc[i].x, sc.x, sh.x), p.act);
           float b = apply_act(fmaf(acc[i].y, sc.y, sh.y), p.act);
-          __nv_bfloat162 o = __floats2bfloat162_rn(a, b);
-          *reinterpret_cast<__nv_bfloat162*>(yrow + (size_t)w * p.C) = o;
+          *reinterpret_cast<uint32_t*>(yrow + (size_t)w * p.C) = pack16(a, b, p.f16);
         }
       }
     }
@@ -178,7 +178,7 @@ int launch_ks(const CUtensorMap& tm, const DwParams& p, cudaStream_t st) {
 }  // namespace
 
 bool dw_fast_supported(const OfaTensor4* x, const OfaTensor4* y, int ks, const OfaEpilogue* epi) {
-  if (x->dtype != OFA_BF16 || y->dtype != OFA_BF16) return false;
+  if (!is_16bit(x->dtype) || y->dtype != x->dtype) return false;
   if (!is_nhwc_dense(x) || !is_nhwc_dense(y)) return false;
   if (x->c % CH != 0 || x->c == 0) return false;
   if (ks != 3 && ks != 5 && ks != 7) return false;
@@ -201,14 +201,15 @@ int launch_dw_fast(const OfaTensor4* x, const OfaTensor4* y, const float* w7, in
     p.gamma = epi->gamma; p.beta = epi->beta; p.mean = epi->mean; p.var = epi->var; p.eps = epi->eps;
     p.act = epi->act;
   }
-  p.y = reinterpret_cast<__nv_bfloat16*>(y->ptr);
+  p.y = reinterpret_cast<uint16_t*>(y->ptr);
+  p.f16 = x->dtype == OFA_F16 ? 1 : 0;
   p.tiles_w = (p.W + TW - 1) / TW;
   p.tiles_h = (p.H + TH - 1) / TH;
   CUtensorMap tm;
   uint64_t dims[4] = {(uint64_t)p.C, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.N};
   uint64_t strides[3] = {(uint64_t)p.C * 2, (uint64_t)p.W * p.C * 2, (uint64_t)p.H * p.W * p.C * 2};
   uint32_t box[4] = {CH, (uint32_t)(TW + ks - 1), (uint32_t)(TH + ks - 1), 1};
-  int rc = encode_tmap(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x->ptr, dims, strides, box,
+  int rc = encode_tmap(&tm, p.f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x->ptr, dims, strides, box,
                        CU_TENSOR_MAP_SWIZZLE_NONE);
   if (rc) return rc;
   switch (ks) {

@@ -446,6 +446,8 @@ def conv_bn_act_infer(x, w, cin, cout, ks, bn=None, act=B.ACT_NONE, store=B.STOR
     """ConvLayer / DynamicPointConv2d(+BN+act) in inference: one kernel."""
     dtype = out_dtype or _state['compute_dtype']
     y = _conv_out(x, cout, store, dtype, nchw=out_nchw)
+    if y.numel() == 0:            # empty batch / empty image: nothing to launch (F.conv2d returns an empty tensor too)
+        return y
     e, keep = _bn_epilogue(bn, act, residual)
     w_bf16, cin_pad, cout_pad = None, 0, 0
     impl = _state['impl']
@@ -474,6 +476,8 @@ def conv_bn_act_infer(x, w, cin, cout, ks, bn=None, act=B.ACT_NONE, store=B.STOR
 def dw_bn_act_infer(x, w7, m75, m53, ks, transform_on, bn, act):
     n, c, h, w = x.shape
     y = B.new_nhwc(n, c, h, w, x.dtype, x.device)
+    if y.numel() == 0:
+        return y
     e, keep = _bn_epilogue(bn, act, None)
     p75, p53 = _transform_ptrs(m75, m53)
     tx, ty = B.t4(x), B.t4(y)
@@ -495,6 +499,8 @@ def mbconv_infer(x, w_exp, w_dw, m75, m53, w_proj, cin, mid, cout, ks, transform
     """Whole inference MBConv block (expand -> dw -> project [+x]) through ofa_mbconv_fwd; needs
     NHWC-dense bf16 x.  Returns NHWC bf16."""
     n, _, h, w = x.shape
+    if x.numel() == 0:
+        return B.new_nhwc(n, cout, h, w, x.dtype, x.device)
     planar = planar_supported(x, cin, mid, cout) and _state['impl'] not in (B.IMPL_SIMT, B.IMPL_NHWC)
     if _profiler is not None and planar:
         return _mbconv_planar_staged(x, w_exp, w_dw, m75, m53, w_proj, mid, ks, transform_on, act, bn_exp, bn_dw,

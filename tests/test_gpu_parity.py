@@ -120,6 +120,23 @@ def test_dw_simt_fp32(dev, ks, layout, C):
     assert relerr(got2, ref2) < 1e-5
 
 
+def test_fp16_net_on_ragged_width_uses_nhwc_kernels(dev):
+    """W % 8 != 0 takes the three NHWC kernels instead of the planar path (TMA needs 16-byte row pitches): the
+    fp16 default must stay on the fast depthwise kernel there and agree with the oracle."""
+    import ofa_b200
+    ofa_b200.set_compute_dtype(torch.float16)
+    net = _build_net('s4', [1, 2], 91, dev)
+    spec = O.SuperNetSpec('s4', FULL['ks_list'], FULL['expand_ratio_list'], FULL['depth_list'], [1, 2])
+    sd = O.synth_state_dict(spec.param_shapes(), 91)
+    x = torch.from_numpy(np.random.RandomState(2).rand(1, 3, 21, 45).astype(np.float32))
+    for sub in (dict(ks=7, e=6, d=4, pixel_d=2), dict(ks=3, e=3, d=2, pixel_d=1)):
+        net.set_active_subnet(**sub)
+        spec.set_active_subnet(**sub)
+        with torch.no_grad():
+            y = net(x.to(dev))
+        assert relerr(y, O.supernet_forward(x, sd, spec)) < 1e-2
+
+
 @pytest.mark.parametrize('ks', [3, 5, 7])
 @pytest.mark.parametrize('shape', [(1, 64, 8, 32), (2, 192, 19, 45), (1, 384, 40, 70)])
 def test_dw_fast_bf16(dev, ks, shape):
@@ -714,6 +731,42 @@ def test_ragged_and_tiny_images(dev):
             with torch.no_grad():
                 y = net(x.to(dev))
             assert relerr(y, ref) < tol, (shape, dt)
+
+
+def test_empty_batch_returns_empty(dev):
+    """N = 0 (the reference's F.conv2d path returns an empty tensor of the right shape)."""
+    import ofa_b200
+    net = _build_net('s4', [1, 2], 51, dev)
+    net.set_active_subnet(ks=7, e=6, d=4, pixel_d=2)
+    for dt in (torch.float16, torch.float32):
+        ofa_b200.set_compute_dtype(dt)
+        with torch.no_grad():
+            y = net(torch.rand(0, 3, 16, 24, device=dev))
+        assert tuple(y.shape) == (0, 3, 64, 96) and y.dtype == torch.float32
+
+
+def test_cuda_graph_capture_is_bit_identical(dev):
+    """The whole inference forward can be captured in a CUDA graph (every kernel launches on the caller's
+    current stream, tensor maps are kernel parameters) and replays bit-identically."""
+    import ofa_b200
+    ofa_b200.set_compute_dtype(torch.float16)
+    net = _build_net('s4', [1, 2], 52, dev)
+    net.set_active_subnet(ks=5, e=4, d=3, pixel_d=2)
+    x = torch.rand(1, 3, 40, 64, device=dev)
+    with torch.no_grad():
+        y = net(x)
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            net(x)
+        torch.cuda.current_stream().wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            yg = net(x)
+        x.copy_(torch.rand_like(x))
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(yg, net(x)) and not torch.equal(yg, y)
 
 
 def test_no_cpu_path(dev):
