@@ -269,6 +269,16 @@ int ofa_bn_bwd_apply(const OfaTensor4* x, const OfaTensor4* dy, const OfaTensor4
                      float eps, int32_t act, int32_t training, const float* sum_dz,
                      const float* sum_dz_xhat, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * (evaluation side) the validate metric on the device —
+ * psnr(rgb2y(tensor2img_np(a)), rgb2y(tensor2img_np(b))): sr_run_manager.py:364,496,567-597, ofa/utils.py:27-34.
+ *   a, b           [N,3,H,W] images (any strides, fp32 or 16-bit), values clamped to [0,1] as the reference does
+ *   sse_per_image  DEVICE int64[N] (overwritten): sum over pixels of (Y_a - Y_b)^2 with Y the BT.601 luma of the
+ *                  uint8-rounded image — an exact integer; the host turns it into PSNR (ofa_b200.metrics.psnr_y
+ *                  also reproduces the reference's make_grid padding quirk for N > 1)
+ * ------------------------------------------------------------------------------------------- */
+int ofa_psnr_y_sse(const OfaTensor4* a, const OfaTensor4* b, int64_t* sse_per_image, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

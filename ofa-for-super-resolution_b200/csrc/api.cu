@@ -401,6 +401,19 @@ int ofa_project_planar_fwd(const void* x_planar, const void* res_nhwc, void* y_n
                                (cudaStream_t)stream);
 }
 
+int ofa_psnr_y_sse(const OfaTensor4* a, const OfaTensor4* b, int64_t* sse_per_image, void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  if (a && a->n == 0) return OFA_OK;
+  if ((rc = check_tensor(a, "a"))) return rc;
+  if ((rc = check_tensor(b, "b"))) return rc;
+  if ((rc = same_shape(a, b, "psnr_y a vs b"))) return rc;
+  OFA_REQUIRE(a->c == 3, "ofa_psnr_y_sse: RGB images expected (got %d channels)", a->c);
+  OFA_REQUIRE(sse_per_image != nullptr, "ofa_psnr_y_sse: null output");
+  OFA_REQUIRE((long long)a->h * a->w < (1ll << 31), "ofa_psnr_y_sse: image too large");
+  return launch_psnr_y_sse(make_tv(a), make_tv(b), reinterpret_cast<long long*>(sse_per_image), (cudaStream_t)stream);
+}
+
 int ofa_dw_bwd_filter(const OfaTensor4* x, const OfaTensor4* dy, int32_t ks, float* dw_active, void* stream) {
   int rc = require_device();
   if (rc) return rc;

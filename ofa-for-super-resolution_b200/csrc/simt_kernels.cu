@@ -1032,4 +1032,55 @@ int launch_conv_bwd_weight(const TV& x, const TV& dy, float* dw, long long w_so,
   return check_launch("conv_bwd_weight_kernel");
 }
 
+// =================================================================================================
+// (§8f-1) evaluation metric on the device: per-image sum of squared differences of the BT.601 luma of the
+// uint8-rounded images — psnr(rgb2y(tensor2img_np(a)), rgb2y(tensor2img_np(b))), sr_run_manager.py:364,567-597.
+// Integer result (exact): clamp -> x255 in fp32 -> round half to even -> uint8; Y = rint((65.481 R + 128.553 G
+// + 24.966 B) / 255 + 16) in fp64.  grid = (pixel blocks, images); one 64-bit atomic per block.
+// =================================================================================================
+__device__ __forceinline__ int luma_u8(const TV& t, int n, int h, int w) {
+  double acc = 0.0;
+  const double k[3] = {65.481, 128.553, 24.966};
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float v = fminf(fmaxf(t.ld(t.off(n, c, h, w)), 0.f), 1.f);
+    acc += k[c] * (double)rintf(v * 255.0f);
+  }
+  return (int)rint(acc / 255.0 + 16.0);
+}
+
+__global__ void psnr_y_sse_kernel(TV a, TV b, unsigned long long* __restrict__ sse) {
+  __shared__ unsigned long long red[8];
+  const int n = blockIdx.y;
+  const int HW = a.h * a.w;
+  unsigned long long s = 0;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
+    const int h = p / a.w, w = p - h * a.w;
+    const int d = luma_u8(a, n, h, w) - luma_u8(b, n, h, w);
+    s += (unsigned long long)(d * d);
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    atomicAdd(&sse[n], t);
+  }
+}
+
+int launch_psnr_y_sse(const TV& a, const TV& b, long long* sse, cudaStream_t st) {
+  if (a.n == 0) return OFA_OK;
+  cudaError_t e = cudaMemsetAsync(sse, 0, sizeof(long long) * (size_t)a.n, st);
+  if (e != cudaSuccess) return fail(OFA_ERR_CUDA, "memset sse: %s", cudaGetErrorString(e));
+  const long long HW = (long long)a.h * a.w;
+  if (HW == 0) return OFA_OK;
+  long long bx = (HW + 255) / 256;
+  const long long cap = (long long)sm_count() * 8;
+  if (bx > cap) bx = cap;
+  dim3 grid((unsigned)bx, (unsigned)a.n);
+  psnr_y_sse_kernel<<<grid, 256, 0, st>>>(a, b, reinterpret_cast<unsigned long long*>(sse));
+  return check_launch("psnr_y_sse_kernel");
+}
+
 }  // namespace ofa

@@ -344,3 +344,36 @@ def psnr_uint8(a, b):
     if mse == 0:
         return float('inf')
     return 20 * math.log10(255.0 / math.sqrt(mse))
+
+
+def y_uint8_batch(t):
+    """rgb2y(tensor2img_np(.)) per image of a [N,3,H,W] batch (sr_run_manager.py:567-597): clamp to [0,1],
+    x255 in fp32, round half to even, uint8; Y = round((65.481 R + 128.553 G + 24.966 B)/255 + 16) in float64."""
+    t = t.detach().float().cpu().clamp(0, 1).numpy()
+    img = (t * 255.0).round().astype(np.uint8).astype(np.float64)
+    y = ((65.481 * img[:, 0] + 128.553 * img[:, 1] + 24.966 * img[:, 2]) / 255.0 + 16.0).round()
+    return y.astype(np.uint8)
+
+
+def psnr_y_sse(a, b):
+    """Per-image sum of squared Y-uint8 differences (exact integers) of two [N,3,H,W] batches."""
+    d = y_uint8_batch(a).astype(np.int64) - y_uint8_batch(b).astype(np.int64)
+    return (d * d).reshape(d.shape[0], -1).sum(axis=1)
+
+
+def psnr_y_from_sse(sse, n, h, w):
+    """The reference's validate metric psnr(rgb2y(tensor2img_np(out)), rgb2y(tensor2img_np(hr)))
+    (sr_run_manager.py:364,496; ofa/utils.py:27-34) from the per-image SSEs.  QUIRK kept: for a batch the
+    reference first tiles the images with torchvision.utils.make_grid(nrow=int(sqrt(N)), padding=2), so the mean
+    runs over the grid INCLUDING its zero padding (identical in both images: it adds pixels, not error)."""
+    if n == 1:
+        count = h * w
+    else:
+        nrow = int(math.sqrt(n))
+        xmaps = min(nrow, n)
+        ymaps = int(math.ceil(float(n) / xmaps))
+        count = ((h + 2) * ymaps + 2) * ((w + 2) * xmaps + 2)
+    mse = float(np.sum(sse)) / count
+    if mse == 0:
+        return float('inf')
+    return 20 * math.log10(255.0 / math.sqrt(mse))

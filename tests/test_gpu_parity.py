@@ -733,6 +733,32 @@ def test_ragged_and_tiny_images(dev):
             assert relerr(y, ref) < tol, (shape, dt)
 
 
+def test_device_psnr_metric_is_bit_exact(dev):
+    """§8f-1: the validate metric on the device — integer SSE bit-exact against the oracle (which is pinned to the
+    reference's own functions), PSNR equal to the reference's golden values incl. the make_grid batch quirk;
+    fp32 NCHW, channels-last and 16-bit inputs."""
+    import json
+    import math
+    import os
+    from ofa_b200 import metrics
+    with open(os.path.join(os.path.dirname(__file__), 'golden', 'reference_metric.json')) as f:
+        cases = json.load(f)
+    for c in cases:
+        rs = np.random.RandomState(c['seed'])
+        a = (rs.rand(*c['shape']) * 1.2 - 0.1).astype(np.float32)
+        b = (a + c['noise'] * rs.randn(*c['shape'])).astype(np.float32)
+        ta, tb = torch.from_numpy(a), torch.from_numpy(b)
+        sse = metrics.psnr_y_sse(ta.to(dev), tb.to(dev).contiguous(memory_format=torch.channels_last))
+        assert sse.cpu().tolist() == O.psnr_y_sse(ta, tb).tolist()
+        got = metrics.psnr_y(ta.to(dev), tb.to(dev))
+        if c['psnr'] is None:
+            assert math.isinf(got)
+        else:
+            assert abs(got - c['psnr']) < 1e-9
+        h16a, h16b = ta.half(), tb.half()
+        assert metrics.psnr_y_sse(h16a.to(dev), h16b.to(dev)).cpu().tolist() == O.psnr_y_sse(h16a.float(), h16b.float()).tolist()
+
+
 def test_empty_batch_returns_empty(dev):
     """N = 0 (the reference's F.conv2d path returns an empty tensor of the right shape)."""
     import ofa_b200

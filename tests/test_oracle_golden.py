@@ -128,3 +128,23 @@ def test_psnr_metric():
     ya = O.tensor_to_y_uint8(a)
     assert ya.dtype == np.uint8 and ya.shape == (8, 8)
     assert O.psnr_uint8(ya, ya) == float('inf')
+
+
+def test_metric_matches_reference_functions():
+    """oracle psnr_y_* vs psnr(rgb2y(tensor2img_np(.)), ...) of the unmodified reference (make_golden_metric.py),
+    including the make_grid padding quirk for batches."""
+    import json
+    import math
+    import os
+    with open(os.path.join(os.path.dirname(__file__), 'golden', 'reference_metric.json')) as f:
+        cases = json.load(f)
+    for c in cases:
+        rs = np.random.RandomState(c['seed'])
+        a = (rs.rand(*c['shape']) * 1.2 - 0.1).astype(np.float32)
+        b = (a + c['noise'] * rs.randn(*c['shape'])).astype(np.float32)
+        n, _, h, w = c['shape']
+        got = O.psnr_y_from_sse(O.psnr_y_sse(torch.from_numpy(a), torch.from_numpy(b)), n, h, w)
+        if c['psnr'] is None:
+            assert math.isinf(got)
+        else:
+            assert abs(got - c['psnr']) < 1e-12, (c, got)
