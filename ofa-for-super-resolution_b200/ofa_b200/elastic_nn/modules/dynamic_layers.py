@@ -84,8 +84,8 @@ class DynamicMBConvLayer(MyModule):
         bn_dw = self.depth_conv.bn.bn
         bn_pl = self.point_linear.bn.bn
         w_pl = self.point_linear.conv.conv.weight
-        hooked = DynamicBatchNorm2d.SET_RUNNING_STATISTICS or any(
-            'forward' in b.__dict__ for b in (bn_dw, bn_pl))
+        bn_ex = self.inverted_bottleneck.bn.bn if self.inverted_bottleneck is not None else None
+        hooked = DynamicBatchNorm2d.SET_RUNNING_STATISTICS or OF.bn_hooked(bn_ex, bn_dw, bn_pl)
 
         if OF.inference_mode_active(self) and not hooked:
             if self.inverted_bottleneck is not None:

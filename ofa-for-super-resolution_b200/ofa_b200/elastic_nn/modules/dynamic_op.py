@@ -118,11 +118,8 @@ class DynamicBatchNorm2d(nn.Module):
     def bn_forward(x, bn, feature_dim, act=B.ACT_NONE, residual=None):
         # A per-instance `forward` override is the hook elastic_nn.utils.set_running_statistics
         # installs on a deep copy (reference elastic_nn/utils.py:29-52); honour it.
-        if (bn.num_features == feature_dim or DynamicBatchNorm2d.SET_RUNNING_STATISTICS) \
-                and 'forward' in bn.__dict__:
-            y = bn(x)
-            assert act == B.ACT_NONE and residual is None
-            return y
+        # (reference dynamic_op.py:150-151: `bn(x)` when C == num_features or SET_RUNNING_STATISTICS; OF.bn_act
+        # calls the override when there is one and applies the fused activation / residual afterwards)
         return OF.bn_act(x, bn, feature_dim, act, residual)
 
     def forward(self, x):

@@ -361,10 +361,53 @@ class BnActFn(torch.autograd.Function):
         return dx, dgamma, dbeta, None, None, dres, None, None, None, None
 
 
+def bn_hooked(*bns):
+    """True when any of the BatchNorm modules carries a per-instance forward override (set_running_statistics)."""
+    return any(b is not None and 'forward' in b.__dict__ for b in bns)
+
+
+def act_residual(y, act=B.ACT_NONE, residual=None):
+    """y = act(y) + residual through the elementwise kernel (no BN)."""
+    if act == B.ACT_NONE and residual is None:
+        return y
+    n, c, h, w = y.shape
+    out = B.new_nhwc(n, c, h, w, y.dtype, y.device)
+    if out.numel() == 0:
+        return out
+    e, keep = B.epilogue(act=act, residual=residual)
+    ty, to = B.t4(y), B.t4(out)
+    B.check(B.lib().ofa_affine_act(byref(ty), byref(to), byref(e), B.STORE_PLAIN, _stream(y)))
+    return out
+
+
+def batch_stats(x):
+    """Per-channel batch mean and BIASED variance of x [N,C,H,W] on the device (ofa_bn_stats): fp32 [C] each."""
+    c = x.shape[1]
+    mean = torch.empty(c, dtype=torch.float32, device=x.device)
+    var = torch.empty(c, dtype=torch.float32, device=x.device)
+    tx = B.t4(x)
+    B.check(B.lib().ofa_bn_stats(byref(tx), mean.data_ptr(), var.data_ptr(), _stream(x)))
+    return mean, var
+
+
+def normalize_with(x, mean, var, gamma, beta, eps):
+    """F.batch_norm(x, mean, var, gamma[:C], beta[:C], False, 0.0, eps) through the elementwise kernel."""
+    n, c, h, w = x.shape
+    y = B.new_nhwc(n, c, h, w, x.dtype, x.device)
+    e, keep = B.epilogue(gamma, beta, mean, var, eps, B.ACT_NONE, None)
+    tx, ty = B.t4(x), B.t4(y)
+    B.check(B.lib().ofa_affine_act(byref(tx), byref(ty), byref(e), B.STORE_PLAIN, _stream(x)))
+    return y
+
+
 def bn_act(x, bn, C, act=B.ACT_NONE, residual=None, full_width=False):
     """DynamicBatchNorm2d.bn_forward semantics (dynamic_op.py:148-167) for an nn.BatchNorm2d `bn`
     on the first C channels.  `full_width` = the reference's `bn(x)` branch, which also bumps
     num_batches_tracked through nn.BatchNorm2d.forward."""
+    if 'forward' in bn.__dict__:
+        # a per-instance `forward` override = the hook set_running_statistics installs on every BatchNorm2d of a
+        # deep copy (reference elastic_nn/utils.py:29-52): honour it, then apply the rest of the fused epilogue
+        return act_residual(bn(x), act, residual)
     training = bn.training or not bn.track_running_stats
     momentum = 0.0
     if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:

@@ -91,7 +91,7 @@ class ConvLayer(MyModule):
         in-place long-skip adds (`x += dec_big_skip`, ofa_mbs4.py:159)."""
         bn = self.bn if self.use_bn else None
         w = self.conv.weight
-        if OF.inference_mode_active(self):
+        if OF.inference_mode_active(self) and not OF.bn_hooked(bn):
             out_dtype = self.out_dtype
             if out_dtype is None and self.out_channels < 16 and self._store == B.STORE_PLAIN:
                 # thin tensors (the 3-channel learned low-resolution image of X4) stay fp32: it costs
@@ -234,7 +234,9 @@ class MBInvertedConvLayer(MyModule):
 
     def forward(self, x, residual=None):
         act, mid = self._act_code, self._feature_dim
-        infer = OF.inference_mode_active(self)
+        infer = OF.inference_mode_active(self) and not OF.bn_hooked(
+            self.inverted_bottleneck.bn if self.inverted_bottleneck is not None else None, self.depth_conv.bn,
+            self.point_linear.bn)
         dw = self.depth_conv.conv.weight
         if infer:
             if self.inverted_bottleneck is not None:

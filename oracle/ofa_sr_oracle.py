@@ -81,11 +81,23 @@ def sliced_conv(x, w, cout):
     return F.conv2d(x, w[:cout, :cin].contiguous(), None, 1, ks // 2, 1, 1)
 
 
+_RECAL_SINK = None
+
+
 def batch_norm(x, sd, prefix, training=False, momentum=0.1, eps=1e-5):
     """DynamicBatchNorm2d.bn_forward — dynamic_op.py:148-167.  Running statistics in `sd` are updated
     in place on the [:C] slice when training, and num_batches_tracked is bumped."""
     C = x.shape[1]
     rm, rv = sd[prefix + 'running_mean'], sd[prefix + 'running_var']
+    if _RECAL_SINK is not None:
+        # set_running_statistics (elastic_nn/utils.py:29-47): normalise with THIS batch's statistics (biased
+        # variance) and record them, weighted by the batch size
+        mean = x.mean(0, keepdim=True).mean(2, keepdim=True).mean(3, keepdim=True)
+        var = ((x - mean) * (x - mean)).mean(0, keepdim=True).mean(2, keepdim=True).mean(3, keepdim=True)
+        mean, var = torch.squeeze(mean), torch.squeeze(var)
+        _RECAL_SINK.append((prefix, mean.reshape(-1), var.reshape(-1), x.shape[0]))
+        return F.batch_norm(x, mean.reshape(-1), var.reshape(-1), sd[prefix + 'weight'][:C], sd[prefix + 'bias'][:C],
+                            False, 0.0, eps)
     if training:
         sd[prefix + 'num_batches_tracked'] += 1
     return F.batch_norm(x, rm[:C], rv[:C], sd[prefix + 'weight'][:C], sd[prefix + 'bias'][:C], training,
@@ -377,3 +389,29 @@ def psnr_y_from_sse(sse, n, h, w):
     if mse == 0:
         return float('inf')
     return 20 * math.log10(255.0 / math.sqrt(mse))
+
+
+def set_running_statistics(sd, spec, batches):
+    """elastic_nn/utils.py:16-66 — BatchNorm re-calibration of the active sub-network: forward every batch with
+    each BN normalising by the batch's own statistics, then write the batch-size-weighted averages of the recorded
+    means / biased variances into the first C entries of running_mean / running_var (in place in `sd`)."""
+    global _RECAL_SINK
+    _RECAL_SINK = []
+    try:
+        with torch.no_grad():
+            for x in batches:
+                supernet_forward(x, sd, spec)
+        rec = _RECAL_SINK
+    finally:
+        _RECAL_SINK = None
+    acc = {}
+    for prefix, mean, var, n in rec:
+        a = acc.setdefault(prefix, [0.0, 0.0, 0])
+        a[0] = a[0] + mean * n
+        a[1] = a[1] + var * n
+        a[2] += n
+    for prefix, (sm, sv, cnt) in acc.items():
+        C = sm.shape[0]
+        sd[prefix + 'running_mean'][:C] = sm / cnt
+        sd[prefix + 'running_var'][:C] = sv / cnt
+    return sd

@@ -759,6 +759,39 @@ def test_device_psnr_metric_is_bit_exact(dev):
         assert metrics.psnr_y_sse(h16a.to(dev), h16b.to(dev)).cpu().tolist() == O.psnr_y_sse(h16a.float(), h16b.float()).tolist()
 
 
+def test_bn_recalibration_vs_oracle(dev):
+    """§8f-2: elastic_nn.utils.set_running_statistics on the product (statistics and normalisation on the device, the
+    fused inference kernels step aside for the per-BatchNorm forward overrides) vs the oracle, which is pinned to the
+    reference's own function.  Inactive blocks / channels must keep their old statistics bit for bit."""
+    import ofa_b200
+    from ofa_b200.elastic_nn.utils import set_running_statistics
+    ofa_b200.set_compute_dtype(torch.float32)
+    net = _build_net('s4', [1, 2], 95, dev)
+    spec = O.SuperNetSpec('s4', FULL['ks_list'], FULL['expand_ratio_list'], FULL['depth_list'], [1, 2])
+    sd = O.synth_state_dict(spec.param_shapes(), 95)
+    before = {k: v.clone() for k, v in sd.items()}
+    sub = dict(ks=5, e=4, d=3, pixel_d=2)
+    net.set_active_subnet(**sub)
+    spec.set_active_subnet(**sub)
+    rs = np.random.RandomState(9)
+    batches = [torch.from_numpy(rs.rand(3, 3, 8, 12).astype(np.float32)), torch.from_numpy(rs.rand(2, 3, 8, 12).astype(np.float32))]
+    set_running_statistics(net, [{'image': b} for b in batches])
+    O.set_running_statistics(sd, spec, batches)
+    got = net.state_dict()
+    changed = 0
+    for k, v in sd.items():
+        if k.endswith('running_mean') or k.endswith('running_var'):
+            np.testing.assert_allclose(got[k].cpu().numpy(), v.numpy(), rtol=2e-4, atol=2e-6, err_msg=k)
+            same = torch.equal(v, before[k])
+            assert same == torch.equal(got[k].cpu(), before[k]), k       # untouched buffers stay untouched
+            changed += 0 if same else 1
+    assert changed > 40
+    # and the re-calibrated net still runs through the fused inference path
+    with torch.no_grad():
+        y = net(batches[0].to(dev))
+    assert relerr(y, O.supernet_forward(batches[0], sd, spec)) < 1e-3
+
+
 def test_empty_batch_returns_empty(dev):
     """N = 0 (the reference's F.conv2d path returns an empty tensor of the right shape)."""
     import ofa_b200

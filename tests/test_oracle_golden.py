@@ -148,3 +148,20 @@ def test_metric_matches_reference_functions():
             assert math.isinf(got)
         else:
             assert abs(got - c['psnr']) < 1e-12, (c, got)
+
+
+def test_bn_recalibration_matches_reference():
+    """oracle set_running_statistics vs the unmodified reference's (make_golden_recal.py): every running_mean /
+    running_var of the S4 supernet after re-calibrating the (ks=5, e=4, d=3, pixel_d=2) subnet on two batches."""
+    import os
+    gold = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'reference_recal.npz'))
+    FULL = dict(ks_list=[3, 5, 7], expand_ratio_list=[3, 4, 6], depth_list=[2, 3, 4])
+    spec = O.SuperNetSpec('s4', FULL['ks_list'], FULL['expand_ratio_list'], FULL['depth_list'], [1, 2])
+    sd = O.synth_state_dict(spec.param_shapes(), 95)
+    spec.set_active_subnet(ks=5, e=4, d=3, pixel_d=2)
+    rs = np.random.RandomState(9)
+    batches = [torch.from_numpy(rs.rand(3, 3, 8, 12).astype(np.float32)), torch.from_numpy(rs.rand(2, 3, 8, 12).astype(np.float32))]
+    O.set_running_statistics(sd, spec, batches)
+    assert len(gold.files) == 108
+    for k in gold.files:
+        np.testing.assert_allclose(sd[k].numpy(), gold[k], rtol=2e-5, atol=1e-6, err_msg=k)

@@ -62,6 +62,13 @@ def _worker(rank, world, port, ret):
             for p in model.parameters():
                 p.data.add_(1.0)
         P.broadcast_parameters(model, src=0)
+        # BN re-calibration meter (elastic_nn/utils.py DistributedTensor): batch-weighted local sums, ONE all-reduce
+        from ofa_b200.elastic_nn.utils import _Avg
+        meter = _Avg()
+        meter.update(torch.full((4,), float(rank + 1)), 3)
+        meter.update(torch.full((4,), float(10 * (rank + 1))), 2)
+        expect = sum((3.0 * (r + 1) + 2.0 * 10 * (r + 1)) / 5.0 for r in range(world)) / world
+        assert torch.allclose(meter.avg(True), torch.full((4,), expect))
         sync = P.FlatGradAllReduce(model.parameters(), n_buckets=2)
         # every rank seeds `random` identically -> same "sub-network" choice (progressive_shrinking.py:164)
         random.seed(int('%d%.3d%.3d' % (7, 0, 0)))
