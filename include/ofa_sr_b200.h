@@ -279,6 +279,29 @@ int ofa_bn_bwd_apply(const OfaTensor4* x, const OfaTensor4* dy, const OfaTensor4
  * ------------------------------------------------------------------------------------------- */
 int ofa_psnr_y_sse(const OfaTensor4* a, const OfaTensor4* b, int64_t* sse_per_image, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ *  multi-tensor Adam — torch.optim.Adam(net_params, init_lr) with the per-group L2 weight decay
+ * of sr_run_manager.py:115-133,180-185 ('bn#bias' keys: 0), betas / eps as given, no amsgrad.
+ *   table_dev   DEVICE array of n_tensors descriptors (parameter, both moments, size, the tensor's weight decay)
+ *   chunks_dev  DEVICE int32 pairs (tensor index, chunk index): one CUDA block per 2048-element chunk
+ *   grads_dev   DEVICE array of n_tensors gradient pointers for THIS step; NULL = the tensor had no gradient (its
+ *               block is outside the sampled sub-network): it is skipped, step counter and moments untouched,
+ *               exactly as optimizer.step() skips p.grad is None
+ *   steps_dev   DEVICE int32[n_tensors] per-tensor step counters (start at 0), bumped for the active tensors
+ * ------------------------------------------------------------------------------------------- */
+typedef struct OfaAdamTensor {
+  float* p;
+  float* m;
+  float* v;
+  int64_t numel;
+  float weight_decay;
+  int32_t reserved;
+} OfaAdamTensor;
+
+int ofa_adam_step(const OfaAdamTensor* table_dev, const int32_t* chunks_dev, int32_t n_tensors, int32_t n_chunks,
+                  const float* const* grads_dev, int32_t* steps_dev, float lr, float beta1, float beta2,
+                  float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -401,6 +401,19 @@ int ofa_project_planar_fwd(const void* x_planar, const void* res_nhwc, void* y_n
                                (cudaStream_t)stream);
 }
 
+int ofa_adam_step(const OfaAdamTensor* table_dev, const int32_t* chunks_dev, int32_t n_tensors, int32_t n_chunks,
+                  const float* const* grads_dev, int32_t* steps_dev, float lr, float beta1, float beta2, float eps,
+                  void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  OFA_REQUIRE(n_tensors >= 0 && n_chunks >= 0, "ofa_adam_step: negative counts");
+  if (n_tensors == 0 || n_chunks == 0) return OFA_OK;
+  OFA_REQUIRE(table_dev && chunks_dev && grads_dev && steps_dev, "ofa_adam_step: null pointer");
+  OFA_REQUIRE(beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f, "ofa_adam_step: bad hyper-parameters");
+  return launch_adam_step(table_dev, chunks_dev, n_tensors, n_chunks, grads_dev, steps_dev, lr, beta1, beta2, eps,
+                          (cudaStream_t)stream);
+}
+
 int ofa_psnr_y_sse(const OfaTensor4* a, const OfaTensor4* b, int64_t* sse_per_image, void* stream) {
   int rc = require_device();
   if (rc) return rc;

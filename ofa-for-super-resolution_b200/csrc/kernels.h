@@ -32,6 +32,9 @@ int launch_active_filter_bwd(const float* w7, int kmax, const float* m75, const 
 int launch_conv_bwd_weight(const TV& x, const TV& dy, float* dw, long long w_so, long long w_si,
                            long long w_sh, long long w_sw, int cin, int cout, int ks, cudaStream_t st);
 
+int launch_adam_step(const OfaAdamTensor* table, const int* chunks, int n_tensors, int n_chunks,
+                     const float* const* grads, int* steps, float lr, float beta1, float beta2, float eps,
+                     cudaStream_t st);
 int launch_psnr_y_sse(const TV& a, const TV& b, long long* sse, cudaStream_t st);
 
 // ---- dw_fast.cu : NHWC bf16 depthwise, smem halo tiles --------------------------------------------

@@ -1083,4 +1083,56 @@ int launch_psnr_y_sse(const TV& a, const TV& b, long long* sse, cudaStream_t st)
   return check_launch("psnr_y_sse_kernel");
 }
 
+// =================================================================================================
+// (§8f-3) multi-tensor Adam: torch.optim.Adam as sr_run_manager.py:115-133 builds it (L2 weight decay per
+// parameter group: the 'bn#bias' keys get 0).  One launch updates every ACTIVE parameter tensor; tensors whose
+// gradient pointer is NULL (blocks outside the sampled sub-network) are skipped entirely — their step counters
+// and moments do not move, exactly like optimizer.step() skipping p.grad is None.
+// =================================================================================================
+__global__ void adam_bump_steps_kernel(const float* const* __restrict__ grads, int* __restrict__ steps, int n) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n && grads[t] != nullptr) steps[t] += 1;
+}
+
+constexpr int ADAM_CHUNK = 256 * 8;
+
+__global__ void __launch_bounds__(256)
+adam_step_kernel(const OfaAdamTensor* __restrict__ table, const int2* __restrict__ chunks,
+                 const float* const* __restrict__ grads, const int* __restrict__ steps, float lr, float beta1,
+                 float beta2, float eps) {
+  const int2 ck = chunks[blockIdx.x];
+  const float* __restrict__ g = grads[ck.x];
+  if (g == nullptr) return;
+  const OfaAdamTensor T = table[ck.x];
+  const int step = steps[ck.x];
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+  const float step_size = lr / bc1;
+  const long long base = (long long)ck.y * ADAM_CHUNK;
+#pragma unroll
+  for (int k = 0; k < ADAM_CHUNK / 256; ++k) {
+    const long long i = base + k * 256 + threadIdx.x;
+    if (i < T.numel) {
+      const float p = T.p[i];
+      const float gi = fmaf(T.weight_decay, p, g[i]);
+      const float m = T.m[i] = beta1 * T.m[i] + (1.f - beta1) * gi;
+      const float v = T.v[i] = beta2 * T.v[i] + (1.f - beta2) * gi * gi;
+      const float denom = sqrtf(v) / bc2_sqrt + eps;
+      T.p[i] = p - step_size * (m / denom);
+    }
+  }
+}
+
+int launch_adam_step(const OfaAdamTensor* table, const int* chunks, int n_tensors, int n_chunks,
+                     const float* const* grads, int* steps, float lr, float beta1, float beta2, float eps,
+                     cudaStream_t st) {
+  if (n_tensors == 0 || n_chunks == 0) return OFA_OK;
+  adam_bump_steps_kernel<<<(n_tensors + 127) / 128, 128, 0, st>>>(grads, steps, n_tensors);
+  int rc = check_launch("adam_bump_steps_kernel");
+  if (rc) return rc;
+  adam_step_kernel<<<n_chunks, 256, 0, st>>>(table, reinterpret_cast<const int2*>(chunks), grads, steps, lr, beta1, beta2,
+                                             eps);
+  return check_launch("adam_step_kernel");
+}
+
 }  // namespace ofa

@@ -90,6 +90,8 @@ SYMBOLS = {
                                     c_void_p, c_void_p, c_int32, c_int32, c_int32, POINTER(OfaBn), c_int32, c_void_p]),
     'ofa_project_planar_fwd': (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                          c_int32, POINTER(OfaBn), c_void_p]),
+    'ofa_adam_step': (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_float, c_float, c_float,
+                                c_float, c_void_p]),
     'ofa_psnr_y_sse': (c_int32, [_T4, _T4, c_void_p, c_void_p]),
     'ofa_dw_bwd_data': (c_int32, [_T4, _T4, c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_int32,
                                   c_void_p]),

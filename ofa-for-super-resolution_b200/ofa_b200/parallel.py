@@ -71,8 +71,8 @@ class FlatGradAllReduce:
     complete first in backward) and a HEAD segment.
 
     * `reduce()` alone: packs the available .grad tensors, all-reduces the segments (tail first) in
-      `n_buckets` buckets each, averages, and scatters the result back into .grad (creating it where a rank
-      had none, so the optimizer sees identical gradients everywhere).
+      `n_buckets` buckets each, averages, and scatters the result back into the existing .grad tensors
+      (inactive parameters have no .grad on any rank and keep none: the optimizer skips them).
     * overlapped with backward: `watch(boundary_tensor)` before the step's LAST `loss.backward()` registers a
       gradient hook on the activation that separates tail from head.  When autograd reaches it every tail
       gradient is final, so the tail segment is packed and its all-reduce is launched asynchronously while
@@ -141,12 +141,11 @@ class FlatGradAllReduce:
         for h in handles:
             h.wait()
         self.flat.div_(world)
+        # every rank sampled the same sub-network (identical `random` seeds), so a parameter without a gradient has
+        # none on any rank: it stays None and the optimizer skips it, exactly as in the single-GPU reference
         for p, off in zip(self.params, self.offsets):
-            g = self.flat[off:off + p.numel()].view_as(p)
-            if p.grad is None:
-                p.grad = g.clone()
-            else:
-                p.grad.copy_(g)
+            if p.grad is not None:
+                p.grad.copy_(self.flat[off:off + p.numel()].view_as(p))
 
 
 def s4_tail_parameters(net):

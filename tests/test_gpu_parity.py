@@ -792,6 +792,39 @@ def test_bn_recalibration_vs_oracle(dev):
     assert relerr(y, O.supernet_forward(batches[0], sd, spec)) < 1e-3
 
 
+def test_fused_adam_matches_torch_adam(dev):
+    """§8f-3: FusedAdam vs torch.optim.Adam built as sr_run_manager.py:115-133 builds it (two groups, L2 weight decay
+    except on the 'bn#bias' keys): five steps with a cosine learning rate, parameters that have no gradient in some
+    steps (inactive blocks) must be skipped — moments, step counters and weights untouched."""
+    from ofa_b200 import optim
+    torch.manual_seed(3)
+    shapes = {'conv.weight': (64, 3, 5, 5), 'bn.weight': (64,), 'bn.bias': (64,), 'blocks.1.conv.weight': (384, 64, 1, 1),
+              'blocks.1.bn.weight': (384,), 'blocks.2.conv.weight': (5000,), 'blocks.2.bias': (7,)}
+    ref_p = {k: torch.randn(*v).requires_grad_(True) for k, v in shapes.items()}
+    our_p = {k: v.detach().clone().to(dev).requires_grad_(True) for k, v in ref_p.items()}
+    d_ref, nd_ref = optim.split_no_decay(ref_p.items())
+    d_our, nd_our = optim.split_no_decay(our_p.items())
+    assert len(nd_our) == 4
+    ref = torch.optim.Adam([{'params': d_ref, 'weight_decay': 3e-5}, {'params': nd_ref, 'weight_decay': 0}], 1e-2)
+    ours = optim.FusedAdam(d_our, nd_our, lr=1e-2, weight_decay=3e-5)
+    for step in range(5):
+        lr = optim.cosine_lr(1e-2, 2, step // 3, step % 3, 3)
+        for g in ref.param_groups:
+            g['lr'] = lr
+        ours.set_lr(lr)
+        for k in shapes:
+            active = not (k.startswith('blocks.2') and step in (1, 3))      # an inactive block in two of the steps
+            g = torch.randn(*shapes[k]) if active else None
+            ref_p[k].grad = g
+            our_p[k].grad = None if g is None else g.to(dev)
+        ref.step()
+        ours.step()
+        for k in shapes:
+            assert relerr(our_p[k], ref_p[k]) < 2e-6, (step, k)
+    assert ours._steps.cpu().tolist().count(3) == 2 and ours._steps.cpu().tolist().count(5) == 5
+    assert abs(optim.warmup_lr(0.1, 50, 10, 1, 3, 0.01) - ((1 * 10 + 3 + 1) / 50 * (0.1 - 0.01) + 0.01)) < 1e-12
+
+
 def test_empty_batch_returns_empty(dev):
     """N = 0 (the reference's F.conv2d path returns an empty tensor of the right shape)."""
     import ofa_b200

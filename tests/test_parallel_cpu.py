@@ -86,7 +86,10 @@ def _worker(rank, world, port, ret):
         for i, p in enumerate(model.parameters()):
             parts = [torch.tensor(g[i]) if g[i] is not None else torch.zeros_like(p) for g in gathered]
             expect = sum(parts) / world
-            ok = ok and p.grad is not None and torch.allclose(p.grad, expect, atol=1e-6)
+            if all(g[i] is None for g in gathered):
+                ok = ok and p.grad is None                # inactive everywhere: stays None, the optimizer skips it
+            else:
+                ok = ok and p.grad is not None and torch.allclose(p.grad, expect, atol=1e-6)
         w0 = [p.detach().clone() for p in model.parameters()]
         allw = [None] * world
         dist.all_gather_object(allw, [w.tolist() for w in w0])
@@ -126,7 +129,10 @@ def _worker_overlap(rank, world, port, ret):
         ok = True
         for i, p in enumerate(params):
             parts = [torch.tensor(g[i]) if g[i] is not None else torch.zeros_like(p) for g in gathered]
-            ok = ok and p.grad is not None and torch.allclose(p.grad, sum(parts) / world, atol=1e-6)
+            if all(g[i] is None for g in gathered):
+                ok = ok and p.grad is None
+            else:
+                ok = ok and p.grad is not None and torch.allclose(p.grad, sum(parts) / world, atol=1e-6)
         # the tail segment went out while the head had no gradients yet (i.e. during backward), the rest after
         ok = ok and len(launched_in_backward) == 2 and launched_in_backward[0] == (0, sync.tail_numel, True)
         ok = ok and launched_in_backward[1][:2] == (sync.tail_numel, sync.total) and launched_in_backward[1][2] is False

@@ -1,5 +1,5 @@
 """C3 (BASELINE.json configs[2]) on one GPU: progressive-shrinking training step of OFAMobileNetS4 on a batch of
-64 synthetic 96x96 HR patches (24x24 LR in), forward + backward through the library's kernels.  Not the
+64 synthetic 96x96 HR patches (24x24 LR in), forward + backward + fused Adam step through the library's kernels.  Not the
 headline bench; prints ms/step and patches/s.
     python tools/bench_train.py [--batch 64] [--steps 5]
 """
@@ -37,6 +37,9 @@ net = net.to(dev).train()
 per_rank = a.batch // world                      # batch-sharded data parallelism (strong scaling of one step)
 lr_img = torch.rand(per_rank, 3, 24, 24, device=dev)
 hr_img = torch.rand(per_rank, 3, 96, 96, device=dev)
+from ofa_b200 import optim
+decay, no_decay = optim.split_no_decay(net.named_parameters())       # 'bn#bias' keys: no weight decay
+opt = optim.FusedAdam(decay, no_decay, lr=1e-4, weight_decay=3e-5)       # Adam(lr 1e-4, wd 3e-5), SURVEY §8d C3
 reducer = None
 if world > 1:
     from ofa_b200 import parallel as P
@@ -59,6 +62,8 @@ def step(i):
     loss.backward()
     if reducer is not None:
         reducer.reduce()
+    opt.set_lr(optim.cosine_lr(1e-4, 120, 0, i, 1000))
+    opt.step()
     return loss
 
 
