@@ -457,6 +457,22 @@ __global__ void bn_stats_final_kernel(const float* __restrict__ part, int splits
   var[c] = (float)(n > 0.0 ? m2 / n : 0.0);
 }
 
+// Stream-ordered scratch (cudaMallocAsync) for the split reductions.  The default memory pool releases its memory
+// back to the OS at every synchronisation (release threshold 0); re-creating ~100 small allocations per training
+// step then costs hundreds of milliseconds.  Once per device the threshold is raised so the pool keeps its pages.
+static void keep_async_pool_resident() {
+  static bool done[64] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  cudaGetLastError();
+  done[dev] = true;
+}
+
 // pixel splits of a per-channel reduction: enough blocks to fill the GPU, at least ~4k pixels each
 static int bn_splits(const TV& x, long long* per_split) {
   const long long P = (long long)x.n * x.h * x.w;
@@ -475,6 +491,7 @@ int launch_bn_stats(const TV& x, float* mean, float* var, cudaStream_t st) {
   long long per_split = 0;
   const int splits = bn_splits(x, &per_split);
   float* part = nullptr;
+  keep_async_pool_resident();
   OFA_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&part), (size_t)splits * x.c * 3 * sizeof(float), st));
   int rc;
   if (tv_pair_ok(x)) {
@@ -619,6 +636,7 @@ int launch_bn_bwd_reduce(const TV& x, const TV& dy, const float* gamma, const fl
   long long per_split = 0;
   const int splits = bn_splits(x, &per_split);
   float* part = nullptr;
+  keep_async_pool_resident();
   OFA_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&part), (size_t)splits * x.c * 2 * sizeof(float), st));
   int rc;
   if (tv_pair_ok(x) && tv_pair_ok(dy)) {

@@ -19,6 +19,7 @@ ap.add_argument('--batch', type=int, default=64)
 ap.add_argument('--steps', type=int, default=5)
 ap.add_argument('--max-subnet', dest='max', action='store_true', help='max subnet instead of sampled ones')
 ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
+ap.add_argument('--verbose', action='store_true')
 a = ap.parse_args()
 rank = int(os.environ.get('RANK', '0')); world = int(os.environ.get('WORLD_SIZE', '1'))
 local_rank = int(os.environ.get('LOCAL_RANK', '0'))
@@ -72,10 +73,17 @@ for i in range(2):
 torch.cuda.synchronize()
 B.launch_count_reset()
 t0 = time.perf_counter()
+per_step = []
 for i in range(a.steps):
+    ts = time.perf_counter()
     step(10 + i)
+    if a.verbose:
+        torch.cuda.synchronize()
+        per_step.append((time.perf_counter() - ts) * 1e3)
 torch.cuda.synchronize()
 dt = (time.perf_counter() - t0) / a.steps
+if a.verbose and rank == 0:
+    print('per-step ms:', ' '.join('%.1f' % t for t in per_step))
 if world > 1:
     t = torch.tensor([dt], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
