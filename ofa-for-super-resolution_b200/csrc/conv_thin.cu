@@ -223,7 +223,7 @@ struct StemParams {
   const float* w; long long w_so, w_si, w_sh, w_sw;
   int cin, ks, f16;
   Epi epi;
-  int tiles_x, tiles_y;
+  int tiles_x, tiles_y, num_tiles;
 };
 
 __global__ void __launch_bounds__(ST_THREADS)
@@ -233,17 +233,19 @@ conv_stem_kernel(const StemParams p) {
   __shared__ float s_scale[64], s_shift[64];
   const int tid = threadIdx.x;
   const int ks = p.ks, R = ks >> 1, cin = p.cin;
-  const int t = blockIdx.x;
   const int per_img = p.tiles_x * p.tiles_y;
-  const int n = t / per_img, r = t - n * per_img;
-  const int y0 = (r / p.tiles_x) * ST_TH, x0 = (r % p.tiles_x) * ST_TW;
   const int H = p.x.h, W = p.x.w;
 
+  // weights once per (persistent) block, read in memory order (coalesced for a dense parameter)
   for (int i = tid; i < ks * ks * cin * 64; i += ST_THREADS) {
-    const int co = i & 63, q = i >> 6;
-    const int ci = q % cin, tap = q / cin;
-    const int ky = tap / ks, kx = tap - ky * ks;
-    s_w[q][co] = p.w[co * p.w_so + ci * p.w_si + ky * p.w_sh + kx * p.w_sw];
+    const int kx = i % ks;
+    int r = i / ks;
+    const int ky = r % ks; r /= ks;
+    const int ci = r % cin, co = r / cin;
+    // channel co = cg*16 + k*4 + e is stored at float4 slot k*4 + cg: the four channel groups of a quarter warp then
+    // read four CONSECUTIVE 16-byte slots (no bank conflict; [co] order put cg 0/2 and 1/3 on the same banks)
+    const int slot = ((co & 15) >> 2) * 4 + (co >> 4);
+    s_w[(ky * ks + kx) * cin + ci][slot * 4 + (co & 3)] = p.w[co * p.w_so + ci * p.w_si + ky * p.w_sh + kx * p.w_sw];
   }
   if (tid < 64) {
     float sc, sh;
@@ -251,6 +253,10 @@ conv_stem_kernel(const StemParams p) {
     s_scale[tid] = sc; s_shift[tid] = sh;
   }
   const int hh = ST_TH + ks - 1, hw = ST_TW + ks - 1;
+  for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+  const int n = t / per_img, r = t - n * per_img;
+  const int y0 = (r / p.tiles_x) * ST_TH, x0 = (r % p.tiles_x) * ST_TW;
+  __syncthreads();                                  // previous tile's readers are done with s_in (and s_w is written)
   for (int i = tid; i < cin * hh * hw; i += ST_THREADS) {
     const int xx = i % hw, q = i / hw;
     const int yy = q % hh, ci = q / hh;
@@ -264,11 +270,11 @@ conv_stem_kernel(const StemParams p) {
   // thread -> 4 consecutive pixels of one row x 16 channels; 4 rows per thread in turn
   const int cg = tid & 3, xg = (tid >> 2) & 15, rg = tid >> 6;
   for (int ry = rg; ry < ST_TH; ry += 4) {
-    float acc[4][16];
+    float2 acc[4][8];            // channel pairs: packed fp32x2 FMAs (fma.rn.f32x2) double the CUDA-core rate
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int c = 0; c < 16; ++c) acc[i][c] = 0.f;
+      for (int c = 0; c < 8; ++c) acc[i][c] = make_float2(0.f, 0.f);
     for (int ky = 0; ky < ks; ++ky) {
       for (int ci = 0; ci < cin; ++ci) {
         float in[4 + ST_MAXK - 1];
@@ -277,14 +283,16 @@ conv_stem_kernel(const StemParams p) {
 #pragma unroll
         for (int kx = 0; kx < ST_MAXK; ++kx) {
           if (kx < ks) {
-            const float4* wp = reinterpret_cast<const float4*>(&s_w[(ky * ks + kx) * cin + ci][cg * 16]);
-            float wv[16];
+            const float4* wp = reinterpret_cast<const float4*>(&s_w[(ky * ks + kx) * cin + ci][0]);
+            float2 wv[8];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) { const float4 f = wp[q]; wv[4 * q] = f.x; wv[4 * q + 1] = f.y; wv[4 * q + 2] = f.z; wv[4 * q + 3] = f.w; }
+            for (int q = 0; q < 4; ++q) { const float4 f = wp[q * 4 + cg]; wv[2 * q] = make_float2(f.x, f.y); wv[2 * q + 1] = make_float2(f.z, f.w); }
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 4; ++i) {
+              const float2 xv = make_float2(in[i + kx], in[i + kx]);
 #pragma unroll
-              for (int c = 0; c < 16; ++c) acc[i][c] = fmaf(in[i + kx], wv[c], acc[i][c]);
+              for (int c = 0; c < 8; ++c) ptx::ffma2(acc[i][c], xv, wv[c]);
+            }
           }
         }
       }
@@ -299,7 +307,8 @@ conv_stem_kernel(const StemParams p) {
 #pragma unroll
           for (int c = 0; c < 16; ++c) {
             const int co = cg * 16 + c;
-            o[c] = apply_act(fmaf(acc[i][c], s_scale[co], s_shift[co]), p.epi.act);
+            const float av = (c & 1) ? acc[i][c >> 1].y : acc[i][c >> 1].x;
+            o[c] = apply_act(fmaf(av, s_scale[co], s_shift[co]), p.epi.act);
             if (p.epi.res.ptr) o[c] += p.epi.res.ld(p.epi.res.off(n, co, Y, X));
           }
           if (p.y.dtype != OFA_F32 && p.y.sc == 1) {          // NHWC 16-bit: two 16-byte stores per pixel
@@ -317,6 +326,7 @@ conv_stem_kernel(const StemParams p) {
       }
     }
   }
+  }   // tile loop
 }
 
 }  // namespace
@@ -384,7 +394,11 @@ int launch_conv_stem(const OfaConvArgs* a, cudaStream_t st) {
   p.epi = make_epi(&a->epi);
   p.tiles_x = (a->x.w + ST_TW - 1) / ST_TW;
   p.tiles_y = (a->x.h + ST_TH - 1) / ST_TH;
-  const long long blocks = (long long)a->x.n * p.tiles_x * p.tiles_y;
+  const long long tiles = (long long)a->x.n * p.tiles_x * p.tiles_y;
+  if (tiles >= (1ll << 31)) return fail(OFA_ERR_UNSUPPORTED, "conv_stem: too many tiles");
+  p.num_tiles = (int)tiles;
+  long long blocks = 4LL * sm_count();            // persistent: the 19 KB weight tensor is loaded once per block
+  if (blocks > tiles) blocks = tiles;
   conv_stem_kernel<<<(unsigned)blocks, ST_THREADS, 0, st>>>(p);
   return check_launch("conv_stem_kernel");
 }
