@@ -221,11 +221,13 @@ constexpr int ST_MAXK = 5, ST_MAXC = 4;
 struct StemParams {
   TV x, y;
   const float* w; long long w_so, w_si, w_sh, w_sw;
-  int cin, ks, f16;
+  int cin, ks, f16, store;
   Epi epi;
   int tiles_x, tiles_y, num_tiles;
 };
 
+// CGS = channel groups of 16: 4 -> 64 output channels (the stems), 1 -> 16 (X4's first conv, stored pixel-unshuffled)
+template <int CGS>
 __global__ void __launch_bounds__(ST_THREADS)
 conv_stem_kernel(const StemParams p) {
   __shared__ float s_in[ST_MAXC][ST_TH + ST_MAXK - 1][ST_TW + ST_MAXK - 1 + 1];
@@ -233,21 +235,22 @@ conv_stem_kernel(const StemParams p) {
   __shared__ float s_scale[64], s_shift[64];
   const int tid = threadIdx.x;
   const int ks = p.ks, R = ks >> 1, cin = p.cin;
+  constexpr int COUT = 16 * CGS;
   const int per_img = p.tiles_x * p.tiles_y;
   const int H = p.x.h, W = p.x.w;
 
   // weights once per (persistent) block, read in memory order (coalesced for a dense parameter)
-  for (int i = tid; i < ks * ks * cin * 64; i += ST_THREADS) {
+  for (int i = tid; i < ks * ks * cin * COUT; i += ST_THREADS) {
     const int kx = i % ks;
     int r = i / ks;
     const int ky = r % ks; r /= ks;
     const int ci = r % cin, co = r / cin;
     // channel co = cg*16 + k*4 + e is stored at float4 slot k*4 + cg: the four channel groups of a quarter warp then
     // read four CONSECUTIVE 16-byte slots (no bank conflict; [co] order put cg 0/2 and 1/3 on the same banks)
-    const int slot = ((co & 15) >> 2) * 4 + (co >> 4);
+    const int slot = ((co & 15) >> 2) * CGS + (co >> 4);
     s_w[(ky * ks + kx) * cin + ci][slot * 4 + (co & 3)] = p.w[co * p.w_so + ci * p.w_si + ky * p.w_sh + kx * p.w_sw];
   }
-  if (tid < 64) {
+  if (tid < COUT) {
     float sc, sh;
     epi_scale_shift(p.epi, tid, sc, sh);
     s_scale[tid] = sc; s_shift[tid] = sh;
@@ -268,8 +271,8 @@ conv_stem_kernel(const StemParams p) {
   __syncthreads();
 
   // thread -> 4 consecutive pixels of one row x 16 channels; 4 rows per thread in turn
-  const int cg = tid & 3, xg = (tid >> 2) & 15, rg = tid >> 6;
-  for (int ry = rg; ry < ST_TH; ry += 4) {
+  const int cg = tid % CGS, xg = (tid / CGS) & 15, rg = tid / (CGS * 16);
+  for (int ry = rg; ry < ST_TH; ry += ST_THREADS / (CGS * 16)) {
     float2 acc[4][8];            // channel pairs: packed fp32x2 FMAs (fma.rn.f32x2) double the CUDA-core rate
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -286,7 +289,7 @@ conv_stem_kernel(const StemParams p) {
             const float4* wp = reinterpret_cast<const float4*>(&s_w[(ky * ks + kx) * cin + ci][0]);
             float2 wv[8];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) { const float4 f = wp[q * 4 + cg]; wv[2 * q] = make_float2(f.x, f.y); wv[2 * q + 1] = make_float2(f.z, f.w); }
+            for (int q = 0; q < 4; ++q) { const float4 f = wp[q * CGS + cg]; wv[2 * q] = make_float2(f.x, f.y); wv[2 * q + 1] = make_float2(f.z, f.w); }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const float2 xv = make_float2(in[i + kx], in[i + kx]);
@@ -309,9 +312,18 @@ conv_stem_kernel(const StemParams p) {
             const int co = cg * 16 + c;
             const float av = (c & 1) ? acc[i][c >> 1].y : acc[i][c >> 1].x;
             o[c] = apply_act(fmaf(av, s_scale[co], s_shift[co]), p.epi.act);
-            if (p.epi.res.ptr) o[c] += p.epi.res.ld(p.epi.res.off(n, co, Y, X));
+            if (p.store == OFA_STORE_PLAIN && p.epi.res.ptr) o[c] += p.epi.res.ld(p.epi.res.off(n, co, Y, X));
           }
-          if (p.y.dtype != OFA_F32 && p.y.sc == 1) {          // NHWC 16-bit: two 16-byte stores per pixel
+          if (p.store != OFA_STORE_PLAIN) {                   // PixelUnshuffle / PixelShuffle store (layers.py:94-98)
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+              int oc, oh, ow;
+              store_coord(p.store, cg * 16 + c, Y, X, oc, oh, ow);
+              float v = o[c];
+              if (p.epi.res.ptr) v += p.epi.res.ld(p.epi.res.off(n, oc, oh, ow));
+              p.y.st(p.y.off(n, oc, oh, ow), v);
+            }
+          } else if (p.y.dtype != OFA_F32 && p.y.sc == 1) {   // NHWC 16-bit: two 16-byte stores per pixel
             uint32_t pk[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) pk[q] = pack16(o[2 * q], o[2 * q + 1], p.f16);
@@ -376,8 +388,10 @@ int launch_conv_out_rows(const OfaConvArgs* a, cudaStream_t st) {
 }
 
 bool conv_stem_supported(const OfaConvArgs* a) {
-  if (a->flip || a->store != OFA_STORE_PLAIN) return false;
-  if (a->cin < 1 || a->cin > ST_MAXC || a->cout != 64) return false;
+  if (a->flip) return false;
+  if (a->cin < 1 || a->cin > ST_MAXC || (a->cout != 64 && a->cout != 16)) return false;
+  if (a->store == OFA_STORE_PIXELSHUFFLE2) return false;
+  if (a->store == OFA_STORE_PLAIN && a->cout != 64 && a->y.dtype != OFA_F32 && a->y.sc == 1) return false;
   if (a->ks != 3 && a->ks != 5) return false;
   if (!a->w || a->x.n <= 0 || a->x.h <= 0 || a->x.w <= 0) return false;
   if (a->y.dtype != OFA_F32 && a->y.sc == 1 && ((reinterpret_cast<uintptr_t>(a->y.ptr) & 15) || a->y.sw % 8 || a->y.sh % 8 || a->y.sn % 8))
@@ -390,7 +404,7 @@ int launch_conv_stem(const OfaConvArgs* a, cudaStream_t st) {
   memset(&p, 0, sizeof(p));
   p.x = make_tv(&a->x); p.y = make_tv(&a->y);
   p.w = a->w; p.w_so = a->w_so; p.w_si = a->w_si; p.w_sh = a->w_sh; p.w_sw = a->w_sw;
-  p.cin = a->cin; p.ks = a->ks; p.f16 = a->y.dtype == OFA_F16 ? 1 : 0;
+  p.cin = a->cin; p.ks = a->ks; p.f16 = a->y.dtype == OFA_F16 ? 1 : 0; p.store = a->store;
   p.epi = make_epi(&a->epi);
   p.tiles_x = (a->x.w + ST_TW - 1) / ST_TW;
   p.tiles_y = (a->x.h + ST_TH - 1) / ST_TH;
@@ -399,7 +413,8 @@ int launch_conv_stem(const OfaConvArgs* a, cudaStream_t st) {
   p.num_tiles = (int)tiles;
   long long blocks = 4LL * sm_count();            // persistent: the 19 KB weight tensor is loaded once per block
   if (blocks > tiles) blocks = tiles;
-  conv_stem_kernel<<<(unsigned)blocks, ST_THREADS, 0, st>>>(p);
+  if (a->cout == 64) conv_stem_kernel<4><<<(unsigned)blocks, ST_THREADS, 0, st>>>(p);
+  else conv_stem_kernel<1><<<(unsigned)blocks, ST_THREADS, 0, st>>>(p);
   return check_launch("conv_stem_kernel");
 }
 

@@ -506,7 +506,8 @@ def conv_bn_act_infer(x, w, cin, cout, ks, bn=None, act=B.ACT_NONE, store=B.STOR
     half_nhwc = x.dtype in (torch.bfloat16, torch.float16) and x.is_contiguous(memory_format=torch.channels_last)
     if impl != B.IMPL_SIMT and store == B.STORE_PLAIN and half_nhwc and cin == 64 and ks in (3, 5) and ks * cout <= 16:
         kind = 'rows-tc'          # conv_out_rows_kernel (kx folded into the accumulator columns)
-    elif impl != B.IMPL_SIMT and store == B.STORE_PLAIN and cin <= 4 and cout == 64 and ks in (3, 5):
+    elif impl != B.IMPL_SIMT and cin <= 4 and ks in (3, 5) and ((cout == 64 and store == B.STORE_PLAIN) or
+                                                                  (cout == 16 and store == B.STORE_PIXELUNSHUFFLE2)):
         kind = 'stem'             # conv_stem_kernel
     else:
         kind = 'tc' if w_bf16 is not None else 'simt'

@@ -285,6 +285,24 @@ def test_conv_stem(dev, ks, cin, out):
     assert relerr(got, ref) < {torch.float32: 1e-5, torch.float16: 2 ** -10, torch.bfloat16: 2 ** -7}[out]
 
 
+@pytest.mark.parametrize('out', [torch.float16, torch.float32])
+def test_conv_stem_16ch_pixelunshuffle(dev, out):
+    """a9 + a11: X4's first layer (3x3 3 -> 16, BN, PixelUnshuffle) on the stem kernel, ragged tile edges."""
+    from ofa_b200 import functional as OF, backend as B
+    import ofa_b200
+    ofa_b200.set_impl(B.IMPL_AUTO)
+    w = rnd(16, 3, 3, 3, seed=61, scale=0.2)
+    x = rnd(2, 3, 38, 90, seed=62)
+    bn = bn_params(16, 63, dev)
+    ref = O.pixel_unshuffle2(ref_bn(O.sliced_conv(x, w, 16), bn, 16))
+
+    class _BN:
+        weight, bias, running_mean, running_var, eps = bn['gamma'], bn['beta'], bn['mean'], bn['var'], 1e-5
+    got = OF.conv_bn_act_infer(x.to(dev), w.to(dev), 3, 16, 3, _BN, B.ACT_NONE, B.STORE_PIXELUNSHUFFLE2, None, None, out_dtype=out)
+    assert got.dtype == out and tuple(got.shape) == (2, 64, 19, 45)
+    assert relerr(got, ref) < (1e-5 if out == torch.float32 else 2 ** -10)
+
+
 # =================================================================================================
 # planar tcgen05 MBConv stages (expand / Toeplitz depthwise / project), each through its C-ABI entry
 # =================================================================================================
