@@ -378,6 +378,32 @@ def test_expand_project_planar(dev, mid, half, trunk_half, n, hw):
         assert relerr(y.permute(0, 3, 1, 2), ref3) < (2 ** -9 if half and trunk_half else 2 ** -6.5)
 
 
+def test_mbconv_planar_shape_sweep_vs_oracle(dev):
+    """The planar block (expand -> Toeplitz depthwise -> project + residual) on awkward shapes — single rows and
+    columns of tiles, H = 1, one 8-pixel row, batch > 1, sizes straddling the 128-row / 112-column / 256- and
+    128-pixel tile edges — against the oracle block (fp32 CPU), fp16 storage."""
+    import ofa_b200
+    from ofa_b200 import functional as OF
+    ofa_b200.set_compute_dtype(torch.float16)
+    layer = _block_layer(dev).eval()
+    spec = O.SuperNetSpec('s4', FULL['ks_list'], FULL['expand_ratio_list'], FULL['depth_list'], [1])
+    pre = 'blocks.0.mobile_inverted_conv.'
+    short = {k[len(pre):]: v for k, v in spec.param_shapes().items() if k.startswith(pre)}
+    sd = {pre + k: v for k, v in O.synth_state_dict(short, 21).items()}
+    rs = np.random.RandomState(77)
+    shapes = [(1, 1, 8), (1, 8, 8), (2, 3, 16), (1, 129, 8), (1, 5, 120), (3, 17, 24), (1, 130, 232), (1, 64, 112), (2, 40, 104)]
+    for i, (n, h, w) in enumerate(shapes):
+        ks, e = ((7, 6), (5, 4), (3, 3))[i % 3]
+        layer.active_kernel_size, layer.active_expand_ratio = ks, e
+        x = torch.from_numpy(rs.randn(n, 64, h, w).astype(np.float32)).half().float()
+        xd = x.to(dev).half().contiguous(memory_format=torch.channels_last)
+        assert OF.planar_supported(xd, 64, 64 * e, 64)
+        with torch.no_grad():
+            y = layer(xd, xd)                     # block output + identity residual (proxyless_nets.py:50)
+            ref = O.mbconv_block(x, sd, 'blocks.0.', ks, e, FULL['ks_list'])
+        assert relerr(y, ref) < 4e-3, ((n, h, w), ks, e, relerr(y, ref))
+
+
 @pytest.mark.parametrize('dtype', [torch.bfloat16, torch.float16])
 def test_mbconv_planar_equals_nhwc_path(dev, dtype):
     """The planar path and the three NHWC kernels are two implementations of the same block
@@ -841,6 +867,26 @@ def test_fused_adam_matches_torch_adam(dev):
             assert relerr(our_p[k], ref_p[k]) < 2e-6, (step, k)
     assert ours._steps.cpu().tolist().count(3) == 2 and ours._steps.cpu().tolist().count(5) == 5
     assert abs(optim.warmup_lr(0.1, 50, 10, 1, 3, 0.01) - ((1 * 10 + 3 + 1) / 50 * (0.1 - 0.01) + 0.01)) < 1e-12
+
+
+def test_tiled_inference_equals_whole_frame(dev):
+    """§8e: spatial tiles with a 64-pixel LR halo (>= the max sub-network's 51.5-pixel receptive-field radius) are
+    independent units — the tile grid of ofa_b200.parallel reproduces the whole-frame result (eval-mode BN is a
+    per-channel affine), here for all 4 'ranks' of a 2 x 2 grid on one GPU; no collective is involved."""
+    import ofa_b200
+    from ofa_b200 import parallel as P
+    ofa_b200.set_compute_dtype(torch.float16)
+    net = _build_net('s4', [1, 2], 53, dev)
+    net.set_active_subnet(ks=7, e=6, d=4, pixel_d=2)
+    x = torch.rand(1, 3, 160, 176, device=dev)
+    with torch.no_grad():
+        whole = net(x)
+        out = None
+        for rank in range(4):
+            out, mine = P.tiled_forward(net, x, 2, 2, halo=P.S4_HALO_LR, scale=4, rank=rank, world=4, out=out)
+            assert len(mine) == 1
+    # identical arithmetic per pixel up to the order in which the depthwise tiles accumulate their column chunks
+    assert relerr(out, whole) < 2e-3
 
 
 def test_empty_batch_returns_empty(dev):
