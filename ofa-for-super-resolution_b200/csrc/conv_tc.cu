@@ -255,7 +255,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     // ===================== MMA issuer =====================
     // The whole warp walks the loops (warp-uniform control flow, so descriptors live in uniform
     // registers); only the tcgen05 instructions are predicated on one lane.
-    const uint32_t leader = (lane == 0) ? 1u : 0u;
     const uint32_t idesc = ptx::umma_idesc_f16(128, p.BN, p.f16 ? 0 : 1, p.f16 ? 0 : 1, 0, 0);
     const uint32_t sbo_a = (uint32_t)p.halo_w * 128;
     const uint32_t sB_addr = ptx::smem_u32(sB);
@@ -295,21 +294,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                 const uint64_t da = ptx::umma_desc_sw128(a_row + (uint32_t)(m * MT_COLS * 128), sbo_a);
 #pragma unroll
                 for (int k = 0; k < BK / 16; ++k)
-                  ptx::umma_bf16_pred(d_tmem + (uint32_t)(m * p.BN), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2),
-                                      idesc, first | (uint32_t)k, leader);
+                  ptx::umma_elect(d_tmem + (uint32_t)(m * p.BN), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2),
+                                      idesc, first | (uint32_t)k);
               }
               first = 1;
               if (!p.b_resident) {
-                ptx::umma_commit_pred(&b_empty[bs], leader);
+                ptx::umma_commit_elect(&b_empty[bs]);
                 if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
               }
             }
           }
-          if (s == p.inner_splits - 1) ptx::umma_commit_pred(&a_empty[a_cur], leader);
+          if (s == p.inner_splits - 1) ptx::umma_commit_elect(&a_empty[a_cur]);
           if (++a_cur == p.a_stages) { a_cur = 0; a_cur_ph ^= 1; }
         }
         if (s == p.inner_splits - 1) { as = a_cur; aph = a_cur_ph; }
-        ptx::umma_commit_pred(&tfull[acc], leader);
+        ptx::umma_commit_elect(&tfull[acc]);
         if (++acc == 2) { acc = 0; accph ^= 1; }
       }
     }

@@ -116,7 +116,6 @@ conv_out_rows_kernel(const __grid_constant__ CUtensorMap tm_x, const ConvOutPara
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    const uint32_t leader = (lane == 0) ? 1u : 0u;
     const int fmt = p.f16 ? 0 : 1;
     const uint32_t idesc = ptx::umma_idesc_f16(128, 16, fmt, fmt, 0, 0);
     const uint32_t sA_addr = ptx::smem_u32(sA), sB_addr = ptx::smem_u32(sB);
@@ -148,16 +147,16 @@ conv_out_rows_kernel(const __grid_constant__ CUtensorMap tm_x, const ConvOutPara
           const uint64_t db = ptx::umma_desc_sw128(sB_addr + (uint32_t)(ky * 2048), 1024);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            ptx::umma_bf16_pred(d0, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (uint32_t)(ky | k), leader);
+            ptx::umma_elect(d0, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (uint32_t)(ky | k));
         }
-        ptx::umma_commit_pred(&tfull[acc], leader);
-        ptx::umma_commit_pred(&empty[head], leader);          // the oldest row is not used by later output rows
+        ptx::umma_commit_elect(&tfull[acc]);
+        ptx::umma_commit_elect(&empty[head]);          // the oldest row is not used by later output rows
         if (++head == CO_RING) head = 0;
         if (++acc == CO_ACC) { acc = 0; accph ^= 1; }
       }
       // the 2R halo rows at the bottom of the block are still resident: release them
       for (int q = 0; q < 2 * R; ++q) {
-        ptx::umma_commit_pred(&empty[head], leader);
+        ptx::umma_commit_elect(&empty[head]);
         if (++head == CO_RING) head = 0;
       }
     }

@@ -124,7 +124,6 @@ expand_planar_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    const uint32_t leader = (lane == 0) ? 1u : 0u;
     const int xfmt = p.xf16 ? 0 : 1;
     const uint32_t idesc = ptx::umma_idesc_f16(128, EX_NPIX, xfmt, xfmt, 0, 0);
     const uint32_t sW_addr = ptx::smem_u32(sW), sX_addr = ptx::smem_u32(sX);
@@ -140,10 +139,10 @@ expand_planar_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         const uint64_t db = ptx::umma_desc_sw128(sX_addr + (uint32_t)(s * EX_X_BYTES), 1024);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          ptx::umma_bf16_pred(tmem_base + (uint32_t)(acc * 256), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
-                              (uint32_t)k, leader);
-        if (m == p.mt - 1) ptx::umma_commit_pred(&x_empty[s], leader);
-        ptx::umma_commit_pred(&tfull[acc], leader);
+          ptx::umma_elect(tmem_base + (uint32_t)(acc * 256), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                              (uint32_t)k);
+        if (m == p.mt - 1) ptx::umma_commit_elect(&x_empty[s]);
+        ptx::umma_commit_elect(&tfull[acc]);
         if (++acc == 2) { acc = 0; accph ^= 1; }
       }
       if (++s == EX_X_STAGES) { s = 0; ph ^= 1; }
@@ -320,7 +319,6 @@ dw_planar_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    const uint32_t leader = (lane == 0) ? 1u : 0u;
     constexpr int fmt = F16 ? 0 : 1;
     constexpr uint32_t idesc32_tall = ptx::umma_idesc_f16(128, 32, fmt, fmt, 0, 0);
     constexpr uint32_t idesc_first_tall = ptx::umma_idesc_f16(128, DW_ACC_COLS, fmt, fmt, 0, 0);
@@ -338,7 +336,7 @@ dw_planar_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       const uint32_t idesc_first = shrt ? idesc_first_short : idesc_first_tall;
       if (pc != cur_pc) {
         if (cur_pc >= 0) {
-          ptx::umma_commit_pred(&b_empty[bi], leader);     // all MMAs reading the old filter tiles are done
+          ptx::umma_commit_elect(&b_empty[bi]);     // all MMAs reading the old filter tiles are done
           if (++bi == 2) { bi = 0; bph ^= 1; }
         }
         ptx::mbar_wait(&b_full[bi], bph);
@@ -363,13 +361,13 @@ dw_planar_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           // chunk j: atom j / 4, 32 bytes per chunk inside the 128-byte swizzled row, shifted down dy rows
           const uint64_t da = da0 + (uint64_t)(((j >> 2) * DW_ATOM_STRIDE + dy * 128 + (j & 3) * 32) >> 4);
           if (dy == 0 && j == 0)
-            ptx::umma_bf16_pred(d0, da, dbf, idesc_first, 0u, leader);
+            ptx::umma_elect(d0, da, dbf, idesc_first, 0u);
           else if (j < nch)
-            ptx::umma_bf16_pred(d0 + (uint32_t)(16 * j), da, db0 + (uint64_t)((dy * 1024) >> 4), idesc32, 1u, leader);
+            ptx::umma_elect(d0 + (uint32_t)(16 * j), da, db0 + (uint64_t)((dy * 1024) >> 4), idesc32, 1u);
         }
       }
-      ptx::umma_commit_pred(&a_empty[s], leader);
-      ptx::umma_commit_pred(&tfull[acc], leader);
+      ptx::umma_commit_elect(&a_empty[s]);
+      ptx::umma_commit_elect(&tfull[acc]);
       if (++s == DW_A_STAGES) { s = 0; ph ^= 1; }
       if (++acc == DW_ACC_STAGES) { acc = 0; accph ^= 1; }
     }
@@ -553,7 +551,6 @@ project_planar_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
       }
     }
   } else if (warp == 1) {
-    const uint32_t leader = (lane == 0) ? 1u : 0u;
     const int fmt = p.f16 ? 0 : 1;
     const uint32_t idesc = ptx::umma_idesc_f16(128, 64, fmt, fmt, /*A MN-major*/ 1, 0);
     const uint32_t sA_addr = ptx::smem_u32(sA), sW_addr = ptx::smem_u32(sW);
@@ -572,12 +569,12 @@ project_planar_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
         for (int k = 0; k < 4; ++k) {
           // 16 channels = two 8-deep K groups (1024 bytes each); the two 64-pixel atoms are 8192 bytes apart
           const uint64_t da = ptx::umma_desc(a0 + (uint32_t)(k * 2048), 8192, 1024, 2);
-          ptx::umma_bf16_pred(d0, da, db + (uint64_t)(k * 2), idesc, (uint32_t)(kc | k), leader);
+          ptx::umma_elect(d0, da, db + (uint64_t)(k * 2), idesc, (uint32_t)(kc | k));
         }
-        ptx::umma_commit_pred(&a_empty[s], leader);
+        ptx::umma_commit_elect(&a_empty[s]);
         if (++s == PJ_A_STAGES) { s = 0; ph ^= 1; }
       }
-      ptx::umma_commit_pred(&tfull[acc], leader);
+      ptx::umma_commit_elect(&tfull[acc]);
       if (++acc == PJ_ACC_STAGES) { acc = 0; accph ^= 1; }
     }
   } else {

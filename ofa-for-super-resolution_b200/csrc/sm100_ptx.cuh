@@ -130,24 +130,26 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// same, issued only by the lane(s) whose `pred` is non-zero — lets the surrounding control flow stay
-// warp-uniform (operands then sit in uniform registers instead of a per-MMA R2UR waterfall)
-__device__ __forceinline__ void umma_bf16_pred(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                               uint32_t accumulate, uint32_t pred) {
+// The issue pattern every kernel here uses: the WHOLE warp walks the MMA loop (warp-uniform control flow, so the
+// descriptors stay in uniform registers) and elect.sync picks the one lane that issues the instruction.  elect.sync
+// returns the same lane on every call of a converged warp, which tcgen05.commit relies on (it tracks the MMAs of
+// the issuing thread).
+__device__ __forceinline__ void umma_elect(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                           uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p, q;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "elect.sync _|q, 0xffffffff;\n\t"
       "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(pred)
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void umma_commit_pred(uint64_t* bar, uint32_t pred) {
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
   asm volatile(
       "{\n\t.reg .pred q;\n\t"
       "elect.sync _|q, 0xffffffff;\n\t"
       "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
-      ::"r"(smem_u32(bar)), "r"(pred)
+      ::"r"(smem_u32(bar))
       : "memory");
 }
 // arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed

@@ -107,7 +107,6 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_m, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    const uint32_t leader = (lane == 0) ? 1u : 0u;
     const int fmt = p.f16 ? 0 : 1;
     const uint32_t idesc = ptx::umma_idesc_f16(128, 64, fmt, fmt, /*A MN-major*/ 1, /*B MN-major*/ 1);
     const uint32_t smem_addr = ptx::smem_u32(smem);
@@ -130,14 +129,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_m, const __grid_constant_
           const uint64_t da = ptx::umma_desc(a_base + (uint32_t)(j * 2 * WG_TW * 128), WG_ATOM_BYTES, WG_TW * 128, 2);
           const uint64_t db = ptx::umma_desc(nb + (uint32_t)(((2 * j + ky) * halo_w + kx) * 128), 0,
                                              (uint32_t)(halo_w * 128), 2);
-          ptx::umma_bf16_pred(tmem_base + (uint32_t)(i * 64), da, db, idesc, acc_flag | (uint32_t)j, leader);
+          ptx::umma_elect(tmem_base + (uint32_t)(i * 64), da, db, idesc, acc_flag | (uint32_t)j);
         }
       }
       acc_flag = 1;
-      ptx::umma_commit_pred(&empty[s], leader);
+      ptx::umma_commit_elect(&empty[s]);
       if (++s == WG_STAGES) { s = 0; ph ^= 1; }
     }
-    ptx::umma_commit_pred(done, leader);
+    ptx::umma_commit_elect(done);
   } else if (t_begin < t_end) {
     // ===================== epilogue: add this CTA's partial into the weight-gradient slice =====================
     const int quarter = warp & 3;
