@@ -63,6 +63,7 @@ __global__ void pack_block_weights_kernel(const float* __restrict__ w_exp, long 
 // ==================================================================================================
 constexpr int EX_NPIX = 256;                 // pixels per tile = UMMA N
 constexpr int EX_X_STAGES = 3;
+constexpr int EX_SBUFS = 2;                  // store staging buffers per epilogue warp (TMA stores in flight)
 constexpr int EX_X_BYTES = EX_NPIX * 128;    // 32 KiB
 constexpr int EX_EPI_WARPS = 8;
 constexpr int EX_THREADS = 64 + 32 * EX_EPI_WARPS;
@@ -84,8 +85,8 @@ expand_planar_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
   uint8_t* sW = smem;                                              // mt x 16 KiB, resident
   uint8_t* sX = sW + EX_MAX_MT * 16384;                            // pixel-tile ring
-  uint8_t* sS = sX + EX_X_STAGES * EX_X_BYTES;                     // 8 warps x 2 x 4 KiB staging
-  uint64_t* x_full = reinterpret_cast<uint64_t*>(sS + EX_EPI_WARPS * 2 * EX_SBUF_BYTES);
+  uint8_t* sS = sX + EX_X_STAGES * EX_X_BYTES;                     // 8 warps x EX_SBUFS x 4 KiB staging
+  uint64_t* x_full = reinterpret_cast<uint64_t*>(sS + EX_EPI_WARPS * EX_SBUFS * EX_SBUF_BYTES);
   uint64_t* x_empty = x_full + EX_X_STAGES;
   uint64_t* tfull = x_empty + EX_X_STAGES;
   uint64_t* tempty = tfull + 2;
@@ -151,7 +152,7 @@ expand_planar_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     const int ew = warp - 2;
     const int quarter = warp & 3;
     const int half = ew >> 2;                       // which 128 accumulator columns
-    uint8_t* sbuf = sS + ew * 2 * EX_SBUF_BYTES;
+    uint8_t* sbuf = sS + ew * EX_SBUFS * EX_SBUF_BYTES;
     int acc = 0, sb = 0; uint32_t accph = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int n = t / p.tiles_per_img, p0 = (t - n * p.tiles_per_img) * EX_NPIX;
@@ -174,7 +175,7 @@ expand_planar_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
             ptx::tmem_ld16(t_addr + (uint32_t)(bx * 64 + 32), v + 32);
             ptx::tmem_ld16(t_addr + (uint32_t)(bx * 64 + 48), v + 48);
             ptx::tmem_ld_wait();
-            if (lane == 0) ptx::tma_store_wait_read<1>();         // staging buffer `sb` is free again
+            if (lane == 0) ptx::tma_store_wait_read<EX_SBUFS - 1>();   // staging buffer `sb` is free again
             __syncwarp();
             uint8_t* dst = sbuf + sb * EX_SBUF_BYTES + lane * 128;
 #pragma unroll
@@ -196,7 +197,7 @@ expand_planar_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
               ptx::tma_store_3d(&tm_y, sbuf + sb * EX_SBUF_BYTES, px, c_warp, n);
               ptx::tma_store_commit();
             }
-            sb ^= 1;
+            if (++sb == EX_SBUFS) sb = 0;
           }
         }
         ptx::tc_fence_before();
@@ -694,7 +695,7 @@ int launch_expand_planar(const void* x, void* y, const void* wexp_p, int N, int 
     uint32_t box[3] = {64, 32, 1};
     if ((rc = encode_tmap(&ty, dt16(f16), 3, y, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   }
-  const size_t smem = 1024 + EX_MAX_MT * 16384 + EX_X_STAGES * EX_X_BYTES + EX_EPI_WARPS * 2 * EX_SBUF_BYTES + 256;
+  const size_t smem = 1024 + EX_MAX_MT * 16384 + EX_X_STAGES * EX_X_BYTES + EX_EPI_WARPS * EX_SBUFS * EX_SBUF_BYTES + 256;
   int grid = sm_count();
   const int tiles = N * p.tiles_per_img;
   if (grid > tiles) grid = tiles;
