@@ -306,6 +306,25 @@ __global__ void affine_act_nhwc_kernel(TV x, TV y, Epi epi, unsigned pairs, unsi
   }
 }
 
+// dense-NHWC PixelShuffle(2) / PixelUnshuffle(2) reorder (no affine, no residual): 32-bit index arithmetic, the
+// thread index runs over the OUTPUT so stores are coalesced
+__global__ void reorder_nhwc_kernel(TV x, TV y, int store, unsigned total) {
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned oc = i % (unsigned)y.c;
+    unsigned r = i / (unsigned)y.c;
+    const unsigned ow = r % (unsigned)y.w; r /= (unsigned)y.w;
+    const unsigned oh = r % (unsigned)y.h, n = r / (unsigned)y.h;
+    unsigned c, h, w;
+    if (store == OFA_STORE_PIXELSHUFFLE2) {          // out[n, c', 2h+i, 2w+j] = in[n, 4c'+2i+j, h, w]
+      c = 4 * oc + 2 * (oh & 1) + (ow & 1); h = oh >> 1; w = ow >> 1;
+    } else {                                          // out[n, 4c+2y+x, h', w'] = in[n, c, 2h'+y, 2w'+x]
+      c = oc >> 2; h = 2 * oh + ((oc >> 1) & 1); w = 2 * ow + (oc & 1);
+    }
+    const long long xo = ((long long)(n * x.h + h) * x.w + w) * x.c + c;
+    y.st(i, x.ld(xo));
+  }
+}
+
 __global__ void affine_act_kernel(TV x, TV y, Epi epi, int store, int c_is_inner) {
   const long long total = (long long)x.n * x.c * x.h * x.w;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -341,6 +360,11 @@ int launch_affine_act(const TV& x, const TV& y, const Epi& epi, int store, cudaS
       (!epi.res.ptr || tv_pair_ok(epi.res))) {
     affine_act_nhwc_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, y, epi, (unsigned)(total / 2), (unsigned)(x.c / 2));
     return check_launch("affine_act_nhwc_kernel");
+  }
+  if (store != OFA_STORE_PLAIN && total < (1ll << 31) && tv_nhwc_dense(x) && tv_nhwc_dense(y) && !epi.res.ptr &&
+      !epi.gamma && !epi.beta && !epi.mean && !epi.var && epi.act == OFA_ACT_NONE) {
+    reorder_nhwc_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, y, store, (unsigned)total);
+    return check_launch("reorder_nhwc_kernel");
   }
   affine_act_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, y, epi, store, x.sc == 1);
   return check_launch("affine_act_kernel");
@@ -419,12 +443,23 @@ bn_stats_partial_nhwc_kernel(TV x, float* __restrict__ part, long long per_split
   const long long p_lo = (long long)blockIdx.y * per_split;
   const long long p_hi = p_lo + per_split < P ? p_lo + per_split : P;
   Wf w0 = {0.f, 0.f, 0.f}, w1 = {0.f, 0.f, 0.f};
-  if (c < x.c)
+  if (c < x.c && p_lo + pl < p_hi) {
+    // sums of (v - pivot) and (v - pivot)^2 around the thread's first element: no division per element, no
+    // cancellation problem (the pivot is a sample of the same channel); converted to (n, mean, M2) once
+    const float2 piv = tv_ld2(x, (p_lo + pl) * x.c + c);
+    float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f, cnt = 0.f;
+#pragma unroll 4
     for (long long p = p_lo + pl; p < p_hi; p += BN_PL) {
       const float2 v = tv_ld2(x, p * x.c + c);
-      wf_add(w0, v.x);
-      wf_add(w1, v.y);
+      const float d0 = v.x - piv.x, d1 = v.y - piv.y;
+      s0 += d0; q0 = fmaf(d0, d0, q0);
+      s1 += d1; q1 = fmaf(d1, d1, q1);
+      cnt += 1.f;
     }
+    w0.n = w1.n = cnt;
+    w0.mean = piv.x + s0 / cnt; w0.m2 = q0 - s0 * s0 / cnt;
+    w1.mean = piv.y + s1 / cnt; w1.m2 = q1 - s1 * s1 / cnt;
+  }
   red[pl][2 * cl] = w0;
   red[pl][2 * cl + 1] = w1;
   __syncthreads();
@@ -436,6 +471,47 @@ bn_stats_partial_nhwc_kernel(TV x, float* __restrict__ part, long long per_split
       float* o = part + ((size_t)blockIdx.y * x.c + cc) * 3;
       o[0] = t.n; o[1] = t.mean; o[2] = t.m2;
     }
+  }
+}
+
+// thin tensors (C <= 8: the 3-channel images): every thread walks pixels and keeps all channels in registers —
+// the 32-channels-per-block mapping above would leave 29 of 32 lanes idle
+constexpr int BN_SMALLC = 8;
+
+__global__ void __launch_bounds__(BN_THREADS)
+bn_stats_partial_smallc_kernel(TV x, float* __restrict__ part, long long per_split) {
+  __shared__ Wf red[BN_THREADS / 32][BN_SMALLC];
+  const long long HW = (long long)x.h * x.w;
+  const long long P = HW * x.n;
+  const long long p_lo = (long long)blockIdx.y * per_split;
+  const long long p_hi = p_lo + per_split < P ? p_lo + per_split : P;
+  Wf w[BN_SMALLC];
+#pragma unroll
+  for (int c = 0; c < BN_SMALLC; ++c) w[c] = {0.f, 0.f, 0.f};
+  for (long long p = p_lo + threadIdx.x; p < p_hi; p += BN_THREADS) {
+    int n, h, ww;
+    pix_decode(p, HW, x.w, n, h, ww);
+#pragma unroll
+    for (int c = 0; c < BN_SMALLC; ++c)
+      if (c < x.c) wf_add(w[c], x.ld(x.off(n, c, h, ww)));
+  }
+#pragma unroll
+  for (int c = 0; c < BN_SMALLC; ++c) {
+    for (int o = 16; o > 0; o >>= 1) {
+      Wf t;
+      t.n = __shfl_down_sync(0xffffffffu, w[c].n, o);
+      t.mean = __shfl_down_sync(0xffffffffu, w[c].mean, o);
+      t.m2 = __shfl_down_sync(0xffffffffu, w[c].m2, o);
+      wf_merge(w[c], t);
+    }
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][c] = w[c];
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < x.c) {
+    Wf t = red[0][threadIdx.x];
+    for (int i = 1; i < BN_THREADS / 32; ++i) wf_merge(t, red[i][threadIdx.x]);
+    float* o = part + ((size_t)blockIdx.y * x.c + threadIdx.x) * 3;
+    o[0] = t.n; o[1] = t.mean; o[2] = t.m2;
   }
 }
 
@@ -494,7 +570,11 @@ int launch_bn_stats(const TV& x, float* mean, float* var, cudaStream_t st) {
   keep_async_pool_resident();
   OFA_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&part), (size_t)splits * x.c * 3 * sizeof(float), st));
   int rc;
-  if (tv_pair_ok(x)) {
+  if (x.c <= BN_SMALLC) {
+    dim3 grid(1, splits);
+    bn_stats_partial_smallc_kernel<<<grid, BN_THREADS, 0, st>>>(x, part, per_split);
+    rc = check_launch("bn_stats_partial_smallc_kernel");
+  } else if (tv_pair_ok(x)) {
     dim3 grid((x.c + 2 * BN_CH - 1) / (2 * BN_CH), splits);
     bn_stats_partial_nhwc_kernel<<<grid, BN_THREADS, 0, st>>>(x, part, per_split);
     rc = check_launch("bn_stats_partial_nhwc_kernel");
@@ -591,6 +671,7 @@ bn_bwd_reduce_partial_nhwc_kernel(TV x, TV dy, const float* __restrict__ gamma, 
     const float be0 = beta ? beta[c] : 0.f, be1 = beta ? beta[c + 1] : 0.f;
     const float m0 = mean[c], m1 = mean[c + 1];
     const float r0 = rsqrtf(var[c] + eps), r1 = rsqrtf(var[c + 1] + eps);
+#pragma unroll 4
     for (long long p = p_lo + pl; p < p_hi; p += BN_PL) {
       const long long o = p * x.c + c;
       const float2 xv = tv_ld2(x, o), gv = tv_ld2(dy, o);
@@ -612,6 +693,56 @@ bn_bwd_reduce_partial_nhwc_kernel(TV x, TV dy, const float* __restrict__ gamma, 
       o[0] = (float)t0;
       o[1] = (float)t1;
     }
+  }
+}
+
+__global__ void __launch_bounds__(BN_THREADS)
+bn_bwd_reduce_partial_smallc_kernel(TV x, TV dy, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                    const float* __restrict__ mean, const float* __restrict__ var, float eps, int act,
+                                    float* __restrict__ part, long long per_split) {
+  __shared__ float red0[BN_THREADS / 32][BN_SMALLC];
+  __shared__ float red1[BN_THREADS / 32][BN_SMALLC];
+  const long long HW = (long long)x.h * x.w;
+  const long long P = HW * x.n;
+  const long long p_lo = (long long)blockIdx.y * per_split;
+  const long long p_hi = p_lo + per_split < P ? p_lo + per_split : P;
+  float s0[BN_SMALLC], s1[BN_SMALLC], g[BN_SMALLC], b[BN_SMALLC], m[BN_SMALLC], rs[BN_SMALLC];
+#pragma unroll
+  for (int c = 0; c < BN_SMALLC; ++c) {
+    s0[c] = s1[c] = 0.f;
+    const bool ok = c < x.c;
+    g[c] = (ok && gamma) ? gamma[c] : 1.f;
+    b[c] = (ok && beta) ? beta[c] : 0.f;
+    m[c] = ok ? mean[c] : 0.f;
+    rs[c] = ok ? rsqrtf(var[c] + eps) : 1.f;
+  }
+  for (long long p = p_lo + threadIdx.x; p < p_hi; p += BN_THREADS) {
+    int n, h, w;
+    pix_decode(p, HW, x.w, n, h, w);
+#pragma unroll
+    for (int c = 0; c < BN_SMALLC; ++c)
+      if (c < x.c) {
+        const float xhat = (x.ld(x.off(n, c, h, w)) - m[c]) * rs[c];
+        const float dz = dy.ld(dy.off(n, c, h, w)) * act_grad(fmaf(g[c], xhat, b[c]), act);
+        s0[c] += dz;
+        s1[c] = fmaf(dz, xhat, s1[c]);
+      }
+  }
+#pragma unroll
+  for (int c = 0; c < BN_SMALLC; ++c) {
+    for (int o = 16; o > 0; o >>= 1) {
+      s0[c] += __shfl_down_sync(0xffffffffu, s0[c], o);
+      s1[c] += __shfl_down_sync(0xffffffffu, s1[c], o);
+    }
+    if ((threadIdx.x & 31) == 0) { red0[threadIdx.x >> 5][c] = s0[c]; red1[threadIdx.x >> 5][c] = s1[c]; }
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < x.c) {
+    double t0 = 0.0, t1 = 0.0;
+    for (int i = 0; i < BN_THREADS / 32; ++i) { t0 += red0[i][threadIdx.x]; t1 += red1[i][threadIdx.x]; }
+    float* o = part + ((size_t)blockIdx.y * x.c + threadIdx.x) * 2;
+    o[0] = (float)t0;
+    o[1] = (float)t1;
   }
 }
 
@@ -639,7 +770,12 @@ int launch_bn_bwd_reduce(const TV& x, const TV& dy, const float* gamma, const fl
   keep_async_pool_resident();
   OFA_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&part), (size_t)splits * x.c * 2 * sizeof(float), st));
   int rc;
-  if (tv_pair_ok(x) && tv_pair_ok(dy)) {
+  if (x.c <= BN_SMALLC) {
+    dim3 grid(1, splits);
+    bn_bwd_reduce_partial_smallc_kernel<<<grid, BN_THREADS, 0, st>>>(x, dy, gamma, beta, mean, var, eps, act, part,
+                                                                    per_split);
+    rc = check_launch("bn_bwd_reduce_partial_smallc_kernel");
+  } else if (tv_pair_ok(x) && tv_pair_ok(dy)) {
     dim3 grid((x.c + 2 * BN_CH - 1) / (2 * BN_CH), splits);
     bn_bwd_reduce_partial_nhwc_kernel<<<grid, BN_THREADS, 0, st>>>(x, dy, gamma, beta, mean, var, eps, act, part,
                                                                   per_split);
@@ -803,11 +939,17 @@ dw_bwd_filter_nhwc_kernel(TV x, TV dy, float* __restrict__ dw, int pix_per_block
   float2 acc[KS * KS];
 #pragma unroll
   for (int j = 0; j < KS * KS; ++j) acc[j] = make_float2(0.f, 0.f);
-  if (c < C)
+  if (c < C) {
+    // 32-bit element offsets (launch checks P * C < 2^31); 16-bit or fp32 pairs through one typed pointer
+    const bool f32 = x.dtype == OFA_F32;
+    const bool h16 = x.dtype == OFA_F16;
+    const uint32_t* x16 = reinterpret_cast<const uint32_t*>(x.ptr);
+    const float2* x32 = reinterpret_cast<const float2*>(x.ptr);
     for (int p = p_begin + pl; p < p_end; p += BN_PL) {
       const int n = p / HW, r = p - n * HW;
       const int h = r / W, w = r - h * W;
       const float2 g = tv_ld2(dy, (long long)p * C + c);
+      const int base = (p * C + c) >> 1;                   // pair index of the centre element
 #pragma unroll
       for (int ky = 0; ky < KS; ++ky) {
         const int ih = h + ky - R;
@@ -816,12 +958,14 @@ dw_bwd_filter_nhwc_kernel(TV x, TV dy, float* __restrict__ dw, int pix_per_block
         for (int kx = 0; kx < KS; ++kx) {
           const int iw = w + kx - R;
           if (iw < 0 || iw >= W) continue;
-          const float2 v = tv_ld2(x, (long long)(p + (ky - R) * W + (kx - R)) * C + c);
+          const int o = base + (((ky - R) * W + (kx - R)) * C >> 1);
+          const float2 v = f32 ? x32[o] : unpack16(x16[o], h16);
           acc[ky * KS + kx].x = fmaf(v.x, g.x, acc[ky * KS + kx].x);
           acc[ky * KS + kx].y = fmaf(v.y, g.y, acc[ky * KS + kx].y);
         }
       }
     }
+  }
 #pragma unroll
   for (int j = 0; j < KS * KS; ++j) {
     red[pl][2 * cl] = acc[j].x;
@@ -845,7 +989,7 @@ int launch_dw_bwd_filter(const TV& x, const TV& dy, int ks, float* dw, cudaStrea
   if (e != cudaSuccess) return fail(OFA_ERR_CUDA, "memset dw: %s", cudaGetErrorString(e));
   long long P = (long long)x.n * x.h * x.w;
   if (P == 0) return OFA_OK;
-  if (tv_pair_ok(x) && tv_pair_ok(dy) && P < (1ll << 30)) {
+  if (tv_pair_ok(x) && tv_pair_ok(dy) && P * x.c < (1ll << 31)) {
     const int cb2 = (x.c + 2 * BN_CH - 1) / (2 * BN_CH);
     long long sp = (long long)sm_count() * 8 / cb2;
     if (sp < 1) sp = 1;

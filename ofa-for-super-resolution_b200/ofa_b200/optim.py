@@ -80,8 +80,15 @@ class FusedAdam:
             else:
                 assert p.grad.dtype == torch.float32 and p.grad.is_contiguous()
                 ptrs.append(p.grad.data_ptr())
-        # pageable source: the copy is staged before copy_ returns, so the list can change next step
-        self._grad_dev.copy_(torch.tensor(ptrs, dtype=torch.int64))
+        if torch.cuda.is_current_stream_capturing():
+            # CUDA-graph capture of a whole training step: the gradient buffers live in the graph's private pool, so
+            # their addresses are the same on every replay; the table is uploaded from a pinned buffer that is not
+            # touched again after capture
+            self._grad_pinned = torch.tensor(ptrs, dtype=torch.int64).pin_memory()
+            self._grad_dev.copy_(self._grad_pinned, non_blocking=True)
+        else:
+            # pageable source: the copy is staged before copy_ returns, so the list can change next step
+            self._grad_dev.copy_(torch.tensor(ptrs, dtype=torch.int64))
         dev = self.params[0].device
         B.check(B.lib().ofa_adam_step(self._table.data_ptr(), self._chunks.data_ptr(), len(self.params),
                                       self._chunks.shape[0], self._grad_dev.data_ptr(), self._steps.data_ptr(),

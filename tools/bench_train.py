@@ -20,6 +20,7 @@ ap.add_argument('--steps', type=int, default=5)
 ap.add_argument('--max-subnet', dest='max', action='store_true', help='max subnet instead of sampled ones')
 ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
 ap.add_argument('--verbose', action='store_true')
+ap.add_argument('--graph', action='store_true', help='capture the whole step (fwd + bwd + Adam) of the fixed max subnet in a CUDA graph')
 a = ap.parse_args()
 rank = int(os.environ.get('RANK', '0')); world = int(os.environ.get('WORLD_SIZE', '1'))
 local_rank = int(os.environ.get('LOCAL_RANK', '0'))
@@ -71,6 +72,20 @@ def step(i):
 for i in range(2):
     step(i)
 torch.cuda.synchronize()
+if a.graph:
+    assert a.max and world == 1, '--graph captures a fixed sub-network on one GPU'
+    net.zero_grad(set_to_none=True)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        step_body = lambda: (torch.nn.functional.mse_loss(net(lr_img), hr_img).backward(), opt.step())
+        step_body()
+    torch.cuda.current_stream().wait_stream(s)
+    net.zero_grad(set_to_none=True)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        step_body()
+    step = lambda i: graph.replay()
 B.launch_count_reset()
 t0 = time.perf_counter()
 per_step = []

@@ -1,6 +1,6 @@
 import sys, runpy, torch
-sys.argv = ['bench_train.py', '--steps', '1']
+sys.argv = ['bench_train.py', '--steps', '1', '--max-subnet']
 from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     runpy.run_path('/root/repo/tools/bench_train.py', run_name='__main__')
-print(prof.key_averages().table(sort_by='cuda_time_total', row_limit=14, max_name_column_width=60))
+print(prof.key_averages().table(sort_by='cuda_time_total', row_limit=24, max_name_column_width=60))
