@@ -3,6 +3,7 @@
 // TMA kernels of the bf16 inference path live in conv_tc.cu and dw_fast.cu.
 #include "ofa_common.cuh"
 #include "kernels.h"
+#include "sm100_ptx.cuh"
 
 namespace ofa {
 
@@ -427,7 +428,7 @@ bn_stats_partial_kernel(TV x, float* __restrict__ part, int splits, long long pe
     if (cc < x.c) {
       Wf t = red[0][threadIdx.x];
       for (int i = 1; i < BN_PL; ++i) wf_merge(t, red[i][threadIdx.x]);
-      float* o = part + ((size_t)blockIdx.y * x.c + cc) * 3;
+      float* o = part + ((size_t)cc * gridDim.y + blockIdx.y) * 3;
       o[0] = t.n; o[1] = t.mean; o[2] = t.m2;
     }
   }
@@ -468,7 +469,7 @@ bn_stats_partial_nhwc_kernel(TV x, float* __restrict__ part, long long per_split
     if (cc < x.c) {
       Wf t = red[0][threadIdx.x];
       for (int i = 1; i < BN_PL; ++i) wf_merge(t, red[i][threadIdx.x]);
-      float* o = part + ((size_t)blockIdx.y * x.c + cc) * 3;
+      float* o = part + ((size_t)cc * gridDim.y + blockIdx.y) * 3;
       o[0] = t.n; o[1] = t.mean; o[2] = t.m2;
     }
   }
@@ -510,27 +511,45 @@ bn_stats_partial_smallc_kernel(TV x, float* __restrict__ part, long long per_spl
   if ((int)threadIdx.x < x.c) {
     Wf t = red[0][threadIdx.x];
     for (int i = 1; i < BN_THREADS / 32; ++i) wf_merge(t, red[i][threadIdx.x]);
-    float* o = part + ((size_t)blockIdx.y * x.c + threadIdx.x) * 3;
+    float* o = part + ((size_t)threadIdx.x * gridDim.y + blockIdx.y) * 3;
     o[0] = t.n; o[1] = t.mean; o[2] = t.m2;
   }
 }
 
-__global__ void bn_stats_final_kernel(const float* __restrict__ part, int splits, int C, float* __restrict__ mean,
-                                      float* __restrict__ var) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per channel: lanes stride over the splits, fixed-order shuffle tree -> deterministic; sums in double,
+// no serial chain of divisions (the splits can number a few hundred)
+constexpr int BN_FIN_THREADS = 256;
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(BN_FIN_THREADS)
+bn_stats_final_kernel(const float* __restrict__ part, int splits, int C, float* __restrict__ mean,
+                      float* __restrict__ var) {
+  const int c = blockIdx.x * (BN_FIN_THREADS / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (c >= C) return;
-  double n = 0.0, m = 0.0, m2 = 0.0;
-  for (int s = 0; s < splits; ++s) {
-    const float* o = part + ((size_t)s * C + c) * 3;
-    const double bn = o[0], bm = o[1], b2 = o[2];
-    if (bn == 0.0) continue;
-    const double nn = n + bn, d = bm - m;
-    m += d * (bn / nn);
-    m2 += b2 + d * d * (n * bn / nn);
-    n = nn;
+  double n = 0.0, sm = 0.0;
+  for (int s = lane; s < splits; s += 32) {
+    const float* o = part + ((size_t)c * splits + s) * 3;
+    n += (double)o[0];
+    sm += (double)o[0] * (double)o[1];
   }
-  mean[c] = (float)m;
-  var[c] = (float)(n > 0.0 ? m2 / n : 0.0);
+  n = warp_sum_d(n);
+  sm = warp_sum_d(sm);
+  const double m = n > 0.0 ? sm / n : 0.0;
+  double m2 = 0.0;
+  for (int s = lane; s < splits; s += 32) {
+    const float* o = part + ((size_t)c * splits + s) * 3;
+    const double d = (double)o[1] - m;
+    m2 += (double)o[2] + (double)o[0] * d * d;
+  }
+  m2 = warp_sum_d(m2);
+  if (lane == 0) {
+    mean[c] = (float)m;
+    var[c] = (float)(n > 0.0 ? m2 / n : 0.0);
+  }
 }
 
 // Stream-ordered scratch (cudaMallocAsync) for the split reductions.  The default memory pool releases its memory
@@ -549,15 +568,17 @@ static void keep_async_pool_resident() {
   done[dev] = true;
 }
 
-// pixel splits of a per-channel reduction: enough blocks to fill the GPU, at least ~4k pixels each
+// pixel splits of a per-channel reduction: 8 blocks of 256 threads per SM (the reductions are latency-bound loads,
+// so they want every warp slot), at least 64 pixels each
 static int bn_splits(const TV& x, long long* per_split) {
   const long long P = (long long)x.n * x.h * x.w;
-  const int groups = (x.c + BN_CH - 1) / BN_CH;
+  const int ch_per_block = x.c <= BN_SMALLC ? x.c : tv_pair_ok(x) ? 2 * BN_CH : BN_CH;
+  const int groups = (x.c + ch_per_block - 1) / ch_per_block;
   long long want = (8LL * sm_count() + groups - 1) / groups;
-  long long maxs = (P + 255) / 256;
+  long long maxs = (P + 63) / 64;
   if (want > maxs) want = maxs;
   if (want < 1) want = 1;
-  if (want > 48) want = 48;     // the finalize kernel walks the splits serially per channel
+  if (want > 1024) want = 1024;
   *per_split = (P + want - 1) / want;
   return (int)((P + *per_split - 1) / *per_split);
 }
@@ -584,7 +605,7 @@ int launch_bn_stats(const TV& x, float* mean, float* var, cudaStream_t st) {
     rc = check_launch("bn_stats_partial_kernel");
   }
   if (!rc) {
-    bn_stats_final_kernel<<<(x.c + 127) / 128, 128, 0, st>>>(part, splits, x.c, mean, var);
+    bn_stats_final_kernel<<<(x.c + BN_FIN_THREADS / 32 - 1) / (BN_FIN_THREADS / 32), BN_FIN_THREADS, 0, st>>>(part, splits, x.c, mean, var);
     rc = check_launch("bn_stats_final_kernel");
   }
   cudaFreeAsync(part, st);
@@ -647,7 +668,7 @@ bn_bwd_reduce_partial_kernel(TV x, TV dy, const float* __restrict__ gamma, const
     if (cc < x.c) {
       double t0 = 0.0, t1 = 0.0;
       for (int i = 0; i < BN_PL; ++i) { t0 += red0[i][threadIdx.x]; t1 += red1[i][threadIdx.x]; }
-      float* o = part + ((size_t)blockIdx.y * x.c + cc) * 2;
+      float* o = part + ((size_t)cc * gridDim.y + blockIdx.y) * 2;
       o[0] = (float)t0;
       o[1] = (float)t1;
     }
@@ -689,7 +710,7 @@ bn_bwd_reduce_partial_nhwc_kernel(TV x, TV dy, const float* __restrict__ gamma, 
     if (cc < x.c) {
       double t0 = 0.0, t1 = 0.0;
       for (int i = 0; i < BN_PL; ++i) { t0 += red0[i][threadIdx.x]; t1 += red1[i][threadIdx.x]; }
-      float* o = part + ((size_t)blockIdx.y * x.c + cc) * 2;
+      float* o = part + ((size_t)cc * gridDim.y + blockIdx.y) * 2;
       o[0] = (float)t0;
       o[1] = (float)t1;
     }
@@ -740,24 +761,29 @@ bn_bwd_reduce_partial_smallc_kernel(TV x, TV dy, const float* __restrict__ gamma
   if ((int)threadIdx.x < x.c) {
     double t0 = 0.0, t1 = 0.0;
     for (int i = 0; i < BN_THREADS / 32; ++i) { t0 += red0[i][threadIdx.x]; t1 += red1[i][threadIdx.x]; }
-    float* o = part + ((size_t)blockIdx.y * x.c + threadIdx.x) * 2;
+    float* o = part + ((size_t)threadIdx.x * gridDim.y + blockIdx.y) * 2;
     o[0] = (float)t0;
     o[1] = (float)t1;
   }
 }
 
-__global__ void bn_bwd_reduce_final_kernel(const float* __restrict__ part, int splits, int C,
-                                           float* __restrict__ sum_dz, float* __restrict__ sum_dz_xhat) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(BN_FIN_THREADS)
+bn_bwd_reduce_final_kernel(const float* __restrict__ part, int splits, int C, float* __restrict__ sum_dz,
+                           float* __restrict__ sum_dz_xhat) {
+  const int c = blockIdx.x * (BN_FIN_THREADS / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (c >= C) return;
   double t0 = 0.0, t1 = 0.0;
-  for (int s = 0; s < splits; ++s) {
-    const float* o = part + ((size_t)s * C + c) * 2;
+  for (int s = lane; s < splits; s += 32) {
+    const float* o = part + ((size_t)c * splits + s) * 2;
     t0 += o[0];
     t1 += o[1];
   }
-  sum_dz[c] = (float)t0;
-  sum_dz_xhat[c] = (float)t1;
+  t0 = warp_sum_d(t0);
+  t1 = warp_sum_d(t1);
+  if (lane == 0) {
+    sum_dz[c] = (float)t0;
+    sum_dz_xhat[c] = (float)t1;
+  }
 }
 
 int launch_bn_bwd_reduce(const TV& x, const TV& dy, const float* gamma, const float* beta,
@@ -787,7 +813,7 @@ int launch_bn_bwd_reduce(const TV& x, const TV& dy, const float* gamma, const fl
     rc = check_launch("bn_bwd_reduce_partial_kernel");
   }
   if (!rc) {
-    bn_bwd_reduce_final_kernel<<<(x.c + 127) / 128, 128, 0, st>>>(part, splits, x.c, sum_dz, sum_dz_xhat);
+    bn_bwd_reduce_final_kernel<<<(x.c + BN_FIN_THREADS / 32 - 1) / (BN_FIN_THREADS / 32), BN_FIN_THREADS, 0, st>>>(part, splits, x.c, sum_dz, sum_dz_xhat);
     rc = check_launch("bn_bwd_reduce_final_kernel");
   }
   cudaFreeAsync(part, st);
@@ -924,63 +950,111 @@ dw_bwd_filter_kernel(TV x, TV dy, float* __restrict__ dw, long long pix_per_bloc
   }
 }
 
-// dense-NHWC variant: lane = channel pair, 32-bit pixel arithmetic, paired loads (the re-reads of x hit L1)
+// dense-NHWC variant: a thread owns (channel pair, filter row ky, row group) and walks along an image row with a
+// KS-wide register window of x, so a pixel costs one x load, one dy load and KS paired FMAs (the one-thread-per-
+// pixel form above issues KS*KS loads per pixel and keeps KS*KS accumulators live).  The window rotates by static
+// register renaming: the walk is unrolled KS steps.  Rows of x are re-read by the KS filter rows out of L1/L2.
 template <int KS>
-__global__ void __launch_bounds__(BN_THREADS)
-dw_bwd_filter_nhwc_kernel(TV x, TV dy, float* __restrict__ dw, int pix_per_block) {
-  __shared__ float red[BN_PL][2 * BN_CH + 1];
-  const int cl = threadIdx.x % BN_CH, pl = threadIdx.x / BN_CH;
-  const int c = (blockIdx.x * BN_CH + cl) * 2;
+struct DwRows {
+  static constexpr int RG = KS == 3 ? 4 : 2;             // row groups per block
+  static constexpr int THREADS = 32 * KS * RG;
+  static constexpr int BLOCKS_PER_SM = KS == 7 ? 2 : 3;   // what the register count allows without spills
+};
+
+template <bool F32> struct PairRaw;                      // a channel pair as loaded: fp32x2, or two 16-bit values packed
+template <> struct PairRaw<true> {
+  typedef float2 T;
+  static __device__ __forceinline__ T zero() { return make_float2(0.f, 0.f); }
+  static __device__ __forceinline__ float2 f2(T v, bool) { return v; }
+};
+template <> struct PairRaw<false> {
+  typedef uint32_t T;
+  static __device__ __forceinline__ T zero() { return 0u; }
+  static __device__ __forceinline__ float2 f2(T v, bool h16) { return unpack16(v, h16); }
+};
+
+template <int KS, bool F32>
+__global__ void __launch_bounds__(DwRows<KS>::THREADS, DwRows<KS>::BLOCKS_PER_SM)
+dw_bwd_filter_rows_kernel(TV x, TV dy, float* __restrict__ dw, int rows_per_block) {
+  typedef typename PairRaw<F32>::T Raw;
+  constexpr int R = KS / 2, RG = DwRows<KS>::RG, T = KS * KS;
+  __shared__ float red[RG][64][T];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ky = warp % KS, rg = warp / KS;
   const int H = x.h, W = x.w, C = x.c;
-  const int HW = H * W, P = HW * x.n;
-  const int p_begin = blockIdx.y * pix_per_block;
-  const int p_end = min(p_begin + pix_per_block, P);
-  constexpr int R = KS / 2;
-  float2 acc[KS * KS];
+  const int c = (blockIdx.x * 32 + lane) * 2;
+  const int rows = x.n * H;
+  const int r_begin = blockIdx.y * rows_per_block;
+  const int r_end = min(r_begin + rows_per_block, rows);
+  float2 acc[KS];
 #pragma unroll
-  for (int j = 0; j < KS * KS; ++j) acc[j] = make_float2(0.f, 0.f);
+  for (int j = 0; j < KS; ++j) acc[j] = make_float2(0.f, 0.f);
   if (c < C) {
-    // 32-bit element offsets (launch checks P * C < 2^31); 16-bit or fp32 pairs through one typed pointer
-    const bool f32 = x.dtype == OFA_F32;
-    const bool h16 = x.dtype == OFA_F16;
-    const uint32_t* x16 = reinterpret_cast<const uint32_t*>(x.ptr);
-    const float2* x32 = reinterpret_cast<const float2*>(x.ptr);
-    for (int p = p_begin + pl; p < p_end; p += BN_PL) {
-      const int n = p / HW, r = p - n * HW;
-      const int h = r / W, w = r - h * W;
-      const float2 g = tv_ld2(dy, (long long)p * C + c);
-      const int base = (p * C + c) >> 1;                   // pair index of the centre element
+    const int C2 = C >> 1;                               // pair stride between pixels
+    const bool h16 = x.dtype == OFA_F16;                 // (x and dy have the same type on this path)
+    const Raw* xp = reinterpret_cast<const Raw*>(x.ptr) + (c >> 1);
+    const Raw* gp = reinterpret_cast<const Raw*>(dy.ptr) + (c >> 1);
+    for (int r = r_begin + rg; r < r_end; r += RG) {
+      const int ih = r % H + ky - R;
+      if (ih < 0 || ih >= H) continue;
+      const Raw* xr = xp + (r + ky - R) * W * C2;        // x[n, ih, 0, c]
+      const Raw* gr = gp + r * W * C2;
+      float2 win[KS];                                    // win[j] = x[ih, w0 + j - R] at the top of a pass
 #pragma unroll
-      for (int ky = 0; ky < KS; ++ky) {
-        const int ih = h + ky - R;
-        if (ih < 0 || ih >= H) continue;
+      for (int j = 0; j < KS; ++j) {
+        const int iw = j - R;
+        Raw v = PairRaw<F32>::zero();
+        if (iw >= 0 && iw < W) v = xr[iw * C2];
+        win[j] = PairRaw<F32>::f2(v, h16);
+      }
+      for (int w0 = 0; w0 < W; w0 += KS) {
+        // one pass = KS steps along the row; all 2*KS loads are issued before the first FMA needs them
+        Raw g[KS], nx[KS];
 #pragma unroll
-        for (int kx = 0; kx < KS; ++kx) {
-          const int iw = w + kx - R;
-          if (iw < 0 || iw >= W) continue;
-          const int o = base + (((ky - R) * W + (kx - R)) * C >> 1);
-          const float2 v = f32 ? x32[o] : unpack16(x16[o], h16);
-          acc[ky * KS + kx].x = fmaf(v.x, g.x, acc[ky * KS + kx].x);
-          acc[ky * KS + kx].y = fmaf(v.y, g.y, acc[ky * KS + kx].y);
+        for (int u = 0; u < KS; ++u) {
+          g[u] = PairRaw<F32>::zero();
+          nx[u] = PairRaw<F32>::zero();
+          if (w0 + u < W) g[u] = gr[(w0 + u) * C2];
+          if (w0 + u + 1 + R < W) nx[u] = xr[(w0 + u + 1 + R) * C2];   // the column entering the window after step u
+        }
+#pragma unroll
+        for (int u = 0; u < KS; ++u) {
+          const float2 gv = PairRaw<F32>::f2(g[u], h16);  // zero past the end of the row
+#pragma unroll
+          for (int kx = 0; kx < KS; ++kx) ptx::ffma2(acc[kx], win[(u + kx) % KS], gv);
+          win[u] = PairRaw<F32>::f2(nx[u], h16);
         }
       }
     }
   }
 #pragma unroll
-  for (int j = 0; j < KS * KS; ++j) {
-    red[pl][2 * cl] = acc[j].x;
-    red[pl][2 * cl + 1] = acc[j].y;
-    __syncthreads();
-    if (threadIdx.x < 2 * BN_CH) {
-      const int cc = blockIdx.x * 2 * BN_CH + threadIdx.x;
-      if (cc < C) {
-        float t = 0.f;
-        for (int i = 0; i < BN_PL; ++i) t += red[i][threadIdx.x];
-        atomicAdd(&dw[(size_t)cc * KS * KS + j], t);
-      }
-    }
-    __syncthreads();
+  for (int kx = 0; kx < KS; ++kx) {
+    red[rg][2 * lane][ky * KS + kx] = acc[kx].x;
+    red[rg][2 * lane + 1][ky * KS + kx] = acc[kx].y;
   }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 64 * T; i += DwRows<KS>::THREADS) {
+    const int cc = blockIdx.x * 64 + i / T;
+    if (cc >= C) break;
+    float t = 0.f;
+#pragma unroll
+    for (int g = 0; g < RG; ++g) t += (&red[g][0][0])[i];
+    atomicAdd(&dw[(size_t)blockIdx.x * 64 * T + i], t);
+  }
+}
+
+template <int KS>
+static void launch_dw_rows(const TV& x, const TV& dy, float* dw, cudaStream_t st) {
+  const int cb = (x.c + 63) / 64;
+  const int rows = x.n * x.h;
+  int sp = sm_count() * DwRows<KS>::BLOCKS_PER_SM / cb;
+  if (sp < 1) sp = 1;
+  int rpb = (rows + sp - 1) / sp;
+  if (rpb < DwRows<KS>::RG) rpb = DwRows<KS>::RG;
+  sp = (rows + rpb - 1) / rpb;
+  dim3 grid(cb, (unsigned)sp);
+  if (x.dtype == OFA_F32) dw_bwd_filter_rows_kernel<KS, true><<<grid, DwRows<KS>::THREADS, 0, st>>>(x, dy, dw, rpb);
+  else dw_bwd_filter_rows_kernel<KS, false><<<grid, DwRows<KS>::THREADS, 0, st>>>(x, dy, dw, rpb);
 }
 
 int launch_dw_bwd_filter(const TV& x, const TV& dy, int ks, float* dw, cudaStream_t st) {
@@ -989,21 +1063,14 @@ int launch_dw_bwd_filter(const TV& x, const TV& dy, int ks, float* dw, cudaStrea
   if (e != cudaSuccess) return fail(OFA_ERR_CUDA, "memset dw: %s", cudaGetErrorString(e));
   long long P = (long long)x.n * x.h * x.w;
   if (P == 0) return OFA_OK;
-  if (tv_pair_ok(x) && tv_pair_ok(dy) && P * x.c < (1ll << 31)) {
-    const int cb2 = (x.c + 2 * BN_CH - 1) / (2 * BN_CH);
-    long long sp = (long long)sm_count() * 8 / cb2;
-    if (sp < 1) sp = 1;
-    long long ppb2 = (P + sp - 1) / sp;
-    if (ppb2 < 64) ppb2 = 64;
-    sp = (P + ppb2 - 1) / ppb2;
-    dim3 grid2(cb2, (unsigned)sp);
+  if (tv_pair_ok(x) && tv_pair_ok(dy) && x.dtype == dy.dtype && P * x.c < (1ll << 31)) {
     switch (ks) {
-      case 3: dw_bwd_filter_nhwc_kernel<3><<<grid2, BN_THREADS, 0, st>>>(x, dy, dw, (int)ppb2); break;
-      case 5: dw_bwd_filter_nhwc_kernel<5><<<grid2, BN_THREADS, 0, st>>>(x, dy, dw, (int)ppb2); break;
-      case 7: dw_bwd_filter_nhwc_kernel<7><<<grid2, BN_THREADS, 0, st>>>(x, dy, dw, (int)ppb2); break;
+      case 3: launch_dw_rows<3>(x, dy, dw, st); break;
+      case 5: launch_dw_rows<5>(x, dy, dw, st); break;
+      case 7: launch_dw_rows<7>(x, dy, dw, st); break;
       default: return fail(OFA_ERR_UNSUPPORTED, "depthwise kernel size %d", ks);
     }
-    return check_launch("dw_bwd_filter_nhwc_kernel");
+    return check_launch("dw_bwd_filter_rows_kernel");
   }
   int cb = (x.c + BN_CH - 1) / BN_CH;
   long long splits = (long long)sm_count() * 4 / cb;

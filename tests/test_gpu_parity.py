@@ -162,6 +162,42 @@ def test_dw_fast_bf16(dev, ks, shape):
     assert relerr(got, got_s) < 2 ** -7
 
 
+@pytest.mark.parametrize('ks', [3, 5, 7])
+@pytest.mark.parametrize('shape', [(2, 40, 13, 9), (3, 192, 24, 24), (1, 200, 5, 2), (2, 384, 7, 31)])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_dw_backward_nhwc(dev, ks, shape, dtype):
+    """(a14) depthwise backward on dense NHWC tensors (the row-walk filter-gradient kernel, the data gradient and
+    the chain rule through the 7->5->3 transforms) against autograd on the oracle's statement of the forward.
+    Ragged cases: C not a multiple of 64, W smaller than the filter, rows shared between row groups."""
+    from ofa_b200 import functional as OF, backend as B
+    import ofa_b200
+    ofa_b200.set_impl(B.IMPL_AUTO)
+    n, C, H, W = shape
+    w7, m75, m53 = dw_weights(11, dev)
+    x = rnd(n, C, H, W, seed=12)
+    gy = rnd(n, C, H, W, seed=13)
+    if dtype == torch.bfloat16:
+        x, gy = bf16r(x), bf16r(gy)
+    leaves = [t.clone().requires_grad_(True) for t in (x, w7, m75, m53)]
+    filt = O.active_filter(leaves[1], {'7to5_matrix': leaves[2], '5to3_matrix': leaves[3]}, [3, 5, 7], C, ks)
+    O.dw_conv(leaves[0], filt).backward(gy)
+    xd = x.to(dev).to(dtype).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    wd = [t.to(dev).requires_grad_(True) for t in (w7, m75, m53)]
+    y = OF.dw_conv(xd, wd[0], wd[1], wd[2], ks, True)
+    y.backward(gy.to(dev).to(dtype).contiguous(memory_format=torch.channels_last))
+    tol = 1e-4 if dtype == torch.float32 else 2 ** -7
+    assert relerr(xd.grad, leaves[0].grad) < tol
+    assert relerr(wd[0].grad, leaves[1].grad) < 1e-4          # fp32 accumulation of exactly representable products
+    if ks < 7:
+        assert relerr(wd[1].grad, leaves[2].grad) < 1e-4
+    else:
+        assert wd[1].grad is None and leaves[2].grad is None
+    if ks == 3:
+        assert relerr(wd[2].grad, leaves[3].grad) < 1e-4
+    else:
+        assert wd[2].grad is None and leaves[3].grad is None
+
+
 # =================================================================================================
 # (a3, a4, a9-a11) dense conv — CUDA-core path and tcgen05 path
 # =================================================================================================
