@@ -17,7 +17,9 @@
 namespace ofa {
 namespace {
 
-constexpr int TH = 8, TW = 32, CH = 64, RUN = 16;
+constexpr int TH = 8, TW = 32, CH = 64;
+// output pixels per pass: acc[RUN] + in[RUN + KS - 1] channel pairs must stay in registers (16 spilled at ks >= 5)
+template <int KS> struct DwRun { static constexpr int RUN = KS == 3 ? 16 : 8; };
 constexpr int THREADS = 256;
 
 struct DwParams {
@@ -133,12 +135,13 @@ dw_fast_kernel(const __grid_constant__ CUtensorMap tmap_x, const DwParams p) {
   const float2 sc = make_float2(s_scale[2 * lane], s_scale[2 * lane + 1]);
   const float2 sh = make_float2(s_shift[2 * lane], s_shift[2 * lane + 1]);
   const float2* filt2 = reinterpret_cast<const float2*>(filt);  // [KS*KS][32]
+  constexpr int RUN = DwRun<KS>::RUN;
 #pragma unroll 1
-  for (int x0 = 0; x0 < TW; x0 += RUN) {
+  for (int x0 = 0; x0 < TW && w0 + x0 < p.W; x0 += RUN) {
     float2 acc[RUN];
 #pragma unroll
     for (int i = 0; i < RUN; ++i) acc[i] = make_float2(0.f, 0.f);
-#pragma unroll
+#pragma unroll(KS == 7 ? 1 : KS)                       // ks = 7 fully unrolled hoists 7 rows of loads and spills
     for (int ky = 0; ky < KS; ++ky) {
       const uint32_t* row = tile + ((warp + ky) * L::HALO_W + x0) * 32 + lane;
       float2 in[RUN + KS - 1];

@@ -307,6 +307,50 @@ __global__ void affine_act_nhwc_kernel(TV x, TV y, Epi epi, unsigned pairs, unsi
   }
 }
 
+// 16-bit dense NHWC, C % 8 == 0: a thread owns one group of 8 channels (one 16-byte vector per pixel) for the whole
+// launch -- the grid stride is a multiple of the vectors per pixel -- so the per-channel scale / shift are computed
+// once into registers, and a pixel's 8 channels move as one 16-byte load and one 16-byte store.
+inline bool tv_vec8_ok(const TV& t) {
+  return t.dtype != OFA_F32 && tv_nhwc_dense(t) && (t.c % 8 == 0) && (reinterpret_cast<uintptr_t>(t.ptr) % 16 == 0);
+}
+inline unsigned vec8_blocks(unsigned long long nvec, unsigned V, int threads, int blocks_per_sm) {
+  unsigned a = V, b = (unsigned)threads;
+  while (b) { const unsigned t = a % b; a = b; b = t; }
+  const unsigned m = V / a;                               // blocks must come in multiples of V / gcd(V, threads)
+  unsigned long long blocks = (nvec + threads - 1) / threads;
+  const unsigned long long cap = (unsigned long long)sm_count() * blocks_per_sm;   // one resident wave
+  if (blocks > cap) blocks = cap / m * m >= m ? cap / m * m : m;
+  return (unsigned)((blocks + m - 1) / m * m);
+}
+
+template <bool HAS_RES>
+__global__ void __launch_bounds__(256)
+affine_act_vec8_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const uint4* __restrict__ res, Epi epi,
+                       int f16, unsigned nvec, unsigned V) {
+  const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c0 = 8 * (int)(gid % V);
+  float sc[8], sh[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) epi_scale_shift(epi, c0 + k, sc[k], sh[k]);
+  const int act = epi.act;
+  for (unsigned i = gid; i < nvec; i += gridDim.x * blockDim.x) {
+    const uint4 v = x[i];
+    uint4 r = make_uint4(0u, 0u, 0u, 0u);
+    if (HAS_RES) r = res[i];
+    const uint32_t in[4] = {v.x, v.y, v.z, v.w}, rr[4] = {r.x, r.y, r.z, r.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float2 f = unpack16(in[k], f16);
+      f.x = apply_act(fmaf(f.x, sc[2 * k], sh[2 * k]), act);
+      f.y = apply_act(fmaf(f.y, sc[2 * k + 1], sh[2 * k + 1]), act);
+      if (HAS_RES) { const float2 q = unpack16(rr[k], f16); f.x += q.x; f.y += q.y; }
+      o[k] = pack16(f.x, f.y, f16);
+    }
+    y[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 // dense-NHWC PixelShuffle(2) / PixelUnshuffle(2) reorder (no affine, no residual): 32-bit index arithmetic, the
 // thread index runs over the OUTPUT so stores are coalesced
 __global__ void reorder_nhwc_kernel(TV x, TV y, int store, unsigned total) {
@@ -357,6 +401,19 @@ int launch_affine_act(const TV& x, const TV& y, const Epi& epi, int store, cudaS
   long long blocks = (total + 255) / 256;
   long long cap = (long long)sm_count() * 16;
   if (blocks > cap) blocks = cap;
+  if (store == OFA_STORE_PLAIN && total < (1ll << 34) && tv_vec8_ok(x) && tv_vec8_ok(y) && y.dtype == x.dtype &&
+      (!epi.res.ptr || (tv_vec8_ok(epi.res) && epi.res.dtype == x.dtype))) {
+    const unsigned nvec = (unsigned)(total / 8), V = (unsigned)(x.c / 8);
+    const unsigned nb = vec8_blocks(nvec, V, 256, 8);
+    const uint4* xp = reinterpret_cast<const uint4*>(x.ptr);
+    uint4* yp = reinterpret_cast<uint4*>(y.ptr);
+    if (epi.res.ptr)
+      affine_act_vec8_kernel<true><<<nb, 256, 0, st>>>(xp, yp, reinterpret_cast<const uint4*>(epi.res.ptr), epi,
+                                                       x.dtype == OFA_F16, nvec, V);
+    else
+      affine_act_vec8_kernel<false><<<nb, 256, 0, st>>>(xp, yp, nullptr, epi, x.dtype == OFA_F16, nvec, V);
+    return check_launch("affine_act_vec8_kernel");
+  }
   if (store == OFA_STORE_PLAIN && total < (1ll << 32) && tv_pair_ok(x) && tv_pair_ok(y) &&
       (!epi.res.ptr || tv_pair_ok(epi.res))) {
     affine_act_nhwc_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, y, epi, (unsigned)(total / 2), (unsigned)(x.c / 2));
@@ -475,6 +532,54 @@ bn_stats_partial_nhwc_kernel(TV x, float* __restrict__ part, long long per_split
   }
 }
 
+// 16-bit dense NHWC, C % 8 == 0, C <= 2048: thread = (group of 8 channels, pixel lane), one 16-byte load per pixel;
+// blockDim = V * (256 / V) with V = C / 8, so a block spans all channels and 256 / V pixel lanes
+__global__ void __launch_bounds__(256)
+bn_stats_partial_vec8_kernel(const uint4* __restrict__ x, int f16, int V, long long P, float* __restrict__ part,
+                             long long per_split) {
+  __shared__ float red[3][2048];
+  const int cg = threadIdx.x % V, pl = threadIdx.x / V, PL = blockDim.x / V, C = 8 * V;
+  const long long p_lo = (long long)blockIdx.y * per_split;
+  const long long p_hi = p_lo + per_split < P ? p_lo + per_split : P;
+  // sums of (v - pivot) and (v - pivot)^2 around the block's first pixel (a sample of the same channel: no
+  // cancellation problem, no division per element); the pixel lanes then combine by plain sums
+  float piv[8], sd[8], sq[8];
+  {
+    const uint4 v = x[p_lo * V + cg];
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const float2 f = unpack16(w[k], f16); piv[2 * k] = f.x; piv[2 * k + 1] = f.y; }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) sd[k] = sq[k] = 0.f;
+#pragma unroll 4
+  for (long long p = p_lo + pl; p < p_hi; p += PL) {
+    const uint4 v = x[p * V + cg];
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = unpack16(w[k], f16);
+      const float d0 = f.x - piv[2 * k], d1 = f.y - piv[2 * k + 1];
+      sd[2 * k] += d0; sq[2 * k] = fmaf(d0, d0, sq[2 * k]);
+      sd[2 * k + 1] += d1; sq[2 * k + 1] = fmaf(d1, d1, sq[2 * k + 1]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { red[0][pl * C + 8 * cg + k] = sd[k]; red[1][pl * C + 8 * cg + k] = sq[k]; }
+  if (pl == 0) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) red[2][8 * cg + k] = piv[k];
+  }
+  __syncthreads();
+  const float cnt = (float)(p_hi - p_lo);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float S = 0.f, Q = 0.f;
+    for (int i = 0; i < PL; ++i) { S += red[0][i * C + c]; Q += red[1][i * C + c]; }
+    float* o = part + ((size_t)c * gridDim.y + blockIdx.y) * 3;
+    o[0] = cnt; o[1] = red[2][c] + S / cnt; o[2] = Q - S * S / cnt;
+  }
+}
+
 // thin tensors (C <= 8: the 3-channel images): every thread walks pixels and keeps all channels in registers —
 // the 32-channels-per-block mapping above would leave 29 of 32 lanes idle
 constexpr int BN_SMALLC = 8;
@@ -568,13 +673,19 @@ static void keep_async_pool_resident() {
   done[dev] = true;
 }
 
+static bool bn_vec8_ok(const TV& t) {
+  return tv_vec8_ok(t) && t.c <= 2048 && (long long)t.n * t.h * t.w * (t.c / 8) < (1ll << 40);
+}
+
 // pixel splits of a per-channel reduction: 8 blocks of 256 threads per SM (the reductions are latency-bound loads,
 // so they want every warp slot), at least 64 pixels each
-static int bn_splits(const TV& x, long long* per_split) {
+static int bn_splits(const TV& x, long long* per_split, int vec8_blocks_per_sm) {
   const long long P = (long long)x.n * x.h * x.w;
-  const int ch_per_block = x.c <= BN_SMALLC ? x.c : tv_pair_ok(x) ? 2 * BN_CH : BN_CH;
+  const bool v8 = bn_vec8_ok(x);
+  const int ch_per_block = (x.c <= BN_SMALLC || v8) ? x.c : tv_pair_ok(x) ? 2 * BN_CH : BN_CH;
   const int groups = (x.c + ch_per_block - 1) / ch_per_block;
-  long long want = (8LL * sm_count() + groups - 1) / groups;
+  // one resident wave of blocks (a second, partial wave costs as much as the first on these short kernels)
+  long long want = ((long long)(v8 ? vec8_blocks_per_sm : 8) * sm_count() + groups - 1) / groups;
   long long maxs = (P + 63) / 64;
   if (want > maxs) want = maxs;
   if (want < 1) want = 1;
@@ -586,7 +697,7 @@ static int bn_splits(const TV& x, long long* per_split) {
 int launch_bn_stats(const TV& x, float* mean, float* var, cudaStream_t st) {
   if (x.c == 0) return OFA_OK;
   long long per_split = 0;
-  const int splits = bn_splits(x, &per_split);
+  const int splits = bn_splits(x, &per_split, 4);
   float* part = nullptr;
   keep_async_pool_resident();
   OFA_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&part), (size_t)splits * x.c * 3 * sizeof(float), st));
@@ -595,6 +706,13 @@ int launch_bn_stats(const TV& x, float* mean, float* var, cudaStream_t st) {
     dim3 grid(1, splits);
     bn_stats_partial_smallc_kernel<<<grid, BN_THREADS, 0, st>>>(x, part, per_split);
     rc = check_launch("bn_stats_partial_smallc_kernel");
+  } else if (bn_vec8_ok(x)) {
+    const int V = x.c / 8;
+    dim3 grid(1, splits);
+    bn_stats_partial_vec8_kernel<<<grid, V * (256 / V), 0, st>>>(reinterpret_cast<const uint4*>(x.ptr),
+                                                                x.dtype == OFA_F16, V, (long long)x.n * x.h * x.w,
+                                                                part, per_split);
+    rc = check_launch("bn_stats_partial_vec8_kernel");
   } else if (tv_pair_ok(x)) {
     dim3 grid((x.c + 2 * BN_CH - 1) / (2 * BN_CH), splits);
     bn_stats_partial_nhwc_kernel<<<grid, BN_THREADS, 0, st>>>(x, part, per_split);
@@ -717,6 +835,51 @@ bn_bwd_reduce_partial_nhwc_kernel(TV x, TV dy, const float* __restrict__ gamma, 
   }
 }
 
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_partial_vec8_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy, int f16, int V,
+                                  long long P, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                  const float* __restrict__ mean, const float* __restrict__ var, float eps, int act,
+                                  float* __restrict__ part, long long per_split) {
+  __shared__ float red[2][2048];
+  const int cg = threadIdx.x % V, pl = threadIdx.x / V, PL = blockDim.x / V, C = 8 * V;
+  const long long p_lo = (long long)blockIdx.y * per_split;
+  const long long p_hi = p_lo + per_split < P ? p_lo + per_split : P;
+  float rstd[8], nm[8], g[8], b[8], s0[8], s1[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = 8 * cg + k;
+    g[k] = gamma ? gamma[c] : 1.f;
+    b[k] = beta ? beta[c] : 0.f;
+    rstd[k] = rsqrtf(var[c] + eps);
+    nm[k] = -mean[c] * rstd[k];
+    s0[k] = s1[k] = 0.f;
+  }
+#pragma unroll 2
+  for (long long p = p_lo + pl; p < p_hi; p += PL) {
+    const uint4 xv = x[p * V + cg], gv = dy[p * V + cg];
+    const uint32_t xi[4] = {xv.x, xv.y, xv.z, xv.w}, gi[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 xf = unpack16(xi[k], f16), gf = unpack16(gi[k], f16);
+      const float h0 = fmaf(xf.x, rstd[2 * k], nm[2 * k]), h1 = fmaf(xf.y, rstd[2 * k + 1], nm[2 * k + 1]);
+      const float d0 = gf.x * act_grad(fmaf(g[2 * k], h0, b[2 * k]), act);
+      const float d1 = gf.y * act_grad(fmaf(g[2 * k + 1], h1, b[2 * k + 1]), act);
+      s0[2 * k] += d0; s1[2 * k] = fmaf(d0, h0, s1[2 * k]);
+      s0[2 * k + 1] += d1; s1[2 * k + 1] = fmaf(d1, h1, s1[2 * k + 1]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { red[0][pl * C + 8 * cg + k] = s0[k]; red[1][pl * C + 8 * cg + k] = s1[k]; }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float t0 = 0.f, t1 = 0.f;
+    for (int i = 0; i < PL; ++i) { t0 += red[0][i * C + c]; t1 += red[1][i * C + c]; }
+    float* o = part + ((size_t)c * gridDim.y + blockIdx.y) * 2;
+    o[0] = t0;
+    o[1] = t1;
+  }
+}
+
 __global__ void __launch_bounds__(BN_THREADS)
 bn_bwd_reduce_partial_smallc_kernel(TV x, TV dy, const float* __restrict__ gamma, const float* __restrict__ beta,
                                     const float* __restrict__ mean, const float* __restrict__ var, float eps, int act,
@@ -791,7 +954,7 @@ int launch_bn_bwd_reduce(const TV& x, const TV& dy, const float* gamma, const fl
                          float* sum_dz_xhat, cudaStream_t st) {
   if (x.c == 0) return OFA_OK;
   long long per_split = 0;
-  const int splits = bn_splits(x, &per_split);
+  const int splits = bn_splits(x, &per_split, 3);
   float* part = nullptr;
   keep_async_pool_resident();
   OFA_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&part), (size_t)splits * x.c * 2 * sizeof(float), st));
@@ -801,6 +964,13 @@ int launch_bn_bwd_reduce(const TV& x, const TV& dy, const float* gamma, const fl
     bn_bwd_reduce_partial_smallc_kernel<<<grid, BN_THREADS, 0, st>>>(x, dy, gamma, beta, mean, var, eps, act, part,
                                                                     per_split);
     rc = check_launch("bn_bwd_reduce_partial_smallc_kernel");
+  } else if (bn_vec8_ok(x) && tv_vec8_ok(dy) && dy.dtype == x.dtype) {
+    const int V = x.c / 8;
+    dim3 grid(1, splits);
+    bn_bwd_reduce_partial_vec8_kernel<<<grid, V * (256 / V), 0, st>>>(
+        reinterpret_cast<const uint4*>(x.ptr), reinterpret_cast<const uint4*>(dy.ptr), x.dtype == OFA_F16, V,
+        (long long)x.n * x.h * x.w, gamma, beta, mean, var, eps, act, part, per_split);
+    rc = check_launch("bn_bwd_reduce_partial_vec8_kernel");
   } else if (tv_pair_ok(x) && tv_pair_ok(dy)) {
     dim3 grid((x.c + 2 * BN_CH - 1) / (2 * BN_CH), splits);
     bn_bwd_reduce_partial_nhwc_kernel<<<grid, BN_THREADS, 0, st>>>(x, dy, gamma, beta, mean, var, eps, act, part,
@@ -877,6 +1047,44 @@ __global__ void bn_bwd_apply_nhwc_kernel(TV x, TV dy, TV dx, const float* __rest
   }
 }
 
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_vec8_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy, uint4* __restrict__ dx,
+                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                         const float* __restrict__ mean, const float* __restrict__ var, float eps, int act,
+                         int training, const float* __restrict__ sum_dz, const float* __restrict__ sum_dz_xhat,
+                         float invP, int f16, unsigned nvec, unsigned V) {
+  const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c0 = 8 * (int)(gid % V);
+  // dx = a * (dz - k1 - xhat * k2),  xhat = x * rstd + nm,  z = g * xhat + b
+  float rstd[8], nm[8], g[8], b[8], a[8], k1[8], k2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = c0 + k;
+    g[k] = gamma ? gamma[c] : 1.f;
+    b[k] = beta ? beta[c] : 0.f;
+    rstd[k] = var ? rsqrtf(var[c] + eps) : 1.f;
+    nm[k] = -(mean ? mean[c] : 0.f) * rstd[k];
+    a[k] = g[k] * rstd[k];
+    k1[k] = training ? sum_dz[c] * invP : 0.f;
+    k2[k] = training ? sum_dz_xhat[c] * invP : 0.f;
+  }
+  for (unsigned i = gid; i < nvec; i += gridDim.x * blockDim.x) {
+    const uint4 xv = x[i], gv = dy[i];
+    const uint32_t xi[4] = {xv.x, xv.y, xv.z, xv.w}, gi[4] = {gv.x, gv.y, gv.z, gv.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 xf = unpack16(xi[k], f16), gf = unpack16(gi[k], f16);
+      const float h0 = fmaf(xf.x, rstd[2 * k], nm[2 * k]), h1 = fmaf(xf.y, rstd[2 * k + 1], nm[2 * k + 1]);
+      const float d0 = gf.x * act_grad(fmaf(g[2 * k], h0, b[2 * k]), act);
+      const float d1 = gf.y * act_grad(fmaf(g[2 * k + 1], h1, b[2 * k + 1]), act);
+      o[k] = pack16(a[2 * k] * (d0 - k1[2 * k] - h0 * k2[2 * k]),
+                    a[2 * k + 1] * (d1 - k1[2 * k + 1] - h1 * k2[2 * k + 1]), f16);
+    }
+    dx[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 int launch_bn_bwd_apply(const TV& x, const TV& dy, const TV& dx, const float* gamma, const float* beta,
                         const float* mean, const float* var, float eps, int act, int training,
                         const float* sum_dz, const float* sum_dz_xhat, cudaStream_t st) {
@@ -885,6 +1093,15 @@ int launch_bn_bwd_apply(const TV& x, const TV& dy, const TV& dx, const float* ga
   long long blocks = (total + 255) / 256;
   long long cap = (long long)sm_count() * 16;
   if (blocks > cap) blocks = cap;
+  if (total < (1ll << 34) && tv_vec8_ok(x) && tv_vec8_ok(dy) && tv_vec8_ok(dx) && dy.dtype == x.dtype &&
+      dx.dtype == x.dtype) {
+    const unsigned nvec = (unsigned)(total / 8), V = (unsigned)(x.c / 8);
+    bn_bwd_apply_vec8_kernel<<<vec8_blocks(nvec, V, 256, 3), 256, 0, st>>>(
+        reinterpret_cast<const uint4*>(x.ptr), reinterpret_cast<const uint4*>(dy.ptr), reinterpret_cast<uint4*>(dx.ptr),
+        gamma, beta, mean, var, eps, act, training, sum_dz, sum_dz_xhat,
+        1.f / (float)((long long)x.n * x.h * x.w), x.dtype == OFA_F16, nvec, V);
+    return check_launch("bn_bwd_apply_vec8_kernel");
+  }
   if (total < (1ll << 32) && tv_pair_ok(x) && tv_pair_ok(dy) && tv_pair_ok(dx)) {
     bn_bwd_apply_nhwc_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, dy, dx, gamma, beta, mean, var, eps, act, training,
                                                                sum_dz, sum_dz_xhat, (unsigned)(total / 2),

@@ -265,6 +265,15 @@ class ConvFn(torch.autograd.Function):
                     cache._key, cache._buf, cache.cin_pad, cache.cout_pad = key, buf, cin_pad_b, cout_pad_b
                 a = _conv_args(dy, dx, None, cout, cin, ks, B.STORE_PLAIN, None, cache._buf, cache.cin_pad, cache.cout_pad)
                 B.check(L.ofa_conv_fwd(byref(a), B.IMPL_FAST, st))
+            elif (_state['train_dtype'] != torch.float32 and cout <= 4 and cin == 64 and ks in (3, 5)
+                  and dx.dtype != torch.float32 and w.is_contiguous()):
+                # thin output (64 -> 3 at the SR resolution): its data gradient is a 3 -> 64 conv of dY with the rotated,
+                # transposed slice -- the stem kernel, reading the fp32 master through swapped / negative strides
+                last = (ks - 1) * sh + (ks - 1) * sw
+                a = _conv_args(dy, dx, None, cout, cin, ks, B.STORE_PLAIN)
+                a.w = w.data_ptr() + 4 * last
+                a.w_so, a.w_si, a.w_sh, a.w_sw = si, so, -sh, -sw
+                B.check(L.ofa_conv_fwd(byref(a), B.IMPL_AUTO, st))
             else:
                 tdx = B.t4(dx)
                 B.check(L.ofa_conv_bwd_data(byref(tdy), byref(tdx), B.fptr(w), so, si, sh, sw, cin, cout, ks, st))
