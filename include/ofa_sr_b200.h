@@ -302,6 +302,34 @@ int ofa_adam_step(const OfaAdamTensor* table_dev, const int32_t* chunks_dev, int
                   const float* const* grads_dev, int32_t* steps_dev, float lr, float beta1, float beta2,
                   float eps, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * (training side) SR data preparation on the device — what the reference's data-loader workers
+ * do per sample with Pillow / torchvision: ofa/imagenet_codebase/data_providers/div2k_setxx.py:166-171 (RandomCrop,
+ * RandomHorizontalFlip, RandomRotation), :288-298 (L2 / L4 = Scale(1/2), Scale(1/4) with Image.BICUBIC, ToTensor),
+ * :355-380 (Scale).  Bit-exact against Pillow's libImaging (Resample.c, Geometry.c) and torchvision's ToTensor.
+ * uint8 images are pixel-interleaved RGB, [N][H][W][3]; fp32 outputs are planar [N][3][H][W] = value / 255.
+ *
+ * ofa_resample_ksize / ofa_resample_build_table: HOST functions; the per-output-index window (xmin, count) and the
+ *   22-bit fixed-point bicubic coefficients Pillow's precompute_coeffs + normalize_coeffs_8bpc produce for resizing
+ *   an axis of in_size to out_size.  bounds_host: int32[out_size][2], kk_host: int32[out_size][ksize].  The caller
+ *   copies them to the device once per (in_size, out_size) and owns them (the library keeps no table cache).
+ * ofa_bicubic_resize_u8: img.resize((out_w, out_h), Image.BICUBIC) for a batch: horizontal pass into `tmp`
+ *   ([N][H][out_w][3] uint8 scratch), vertical pass into out_u8 and / or out_f32 (either may be NULL).
+ * ofa_sr_augment_u8: one size x size patch per sample: crop at (row i, column j) of the sample's source image
+ *   (src + n * sample_stride bytes, [h][w][3]), optional left-right flip, rotation.
+ *   params: DEVICE int32[N][10] = { i, j, flip, mode, a0, a1, a2, a3, a4, a5 }; mode 0 none, 1 = 180 deg, 2 / 3 =
+ *   90 / 270 deg (Pillow's transposes, square patches), 4 = affine nearest-neighbour walk with the 16.16
+ *   fixed-point inverse matrix of Geometry.c (the host computes it: ofa_b200/data.py rotation_params).
+ * ------------------------------------------------------------------------------------------- */
+int32_t ofa_resample_ksize(int32_t in_size, int32_t out_size);
+int ofa_resample_build_table(int32_t in_size, int32_t out_size, int32_t* bounds_host, int32_t* kk_host);
+int ofa_bicubic_resize_u8(const uint8_t* src, int32_t n, int32_t h, int32_t w, int32_t out_h, int32_t out_w,
+                          const int32_t* bounds_h, const int32_t* kk_h, int32_t ksize_h, const int32_t* bounds_v,
+                          const int32_t* kk_v, int32_t ksize_v, uint8_t* tmp, uint8_t* out_u8, float* out_f32,
+                          void* stream);
+int ofa_sr_augment_u8(const uint8_t* src, int64_t sample_stride, int32_t n, int32_t h, int32_t w,
+                      const int32_t* params, int32_t size, uint8_t* out_u8, float* out_f32, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

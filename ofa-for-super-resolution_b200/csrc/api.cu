@@ -427,6 +427,40 @@ int ofa_psnr_y_sse(const OfaTensor4* a, const OfaTensor4* b, int64_t* sse_per_im
   return launch_psnr_y_sse(make_tv(a), make_tv(b), reinterpret_cast<long long*>(sse_per_image), (cudaStream_t)stream);
 }
 
+int32_t ofa_resample_ksize(int32_t in_size, int32_t out_size) { return resample_ksize(in_size, out_size); }
+
+int ofa_resample_build_table(int32_t in_size, int32_t out_size, int32_t* bounds_host, int32_t* kk_host) {
+  OFA_REQUIRE(in_size > 0 && out_size > 0, "ofa_resample_build_table: sizes must be positive");
+  OFA_REQUIRE(bounds_host && kk_host, "ofa_resample_build_table: null output");
+  return resample_build_table(in_size, out_size, bounds_host, kk_host);
+}
+
+int ofa_bicubic_resize_u8(const uint8_t* src, int32_t n, int32_t h, int32_t w, int32_t out_h, int32_t out_w,
+                          const int32_t* bounds_h, const int32_t* kk_h, int32_t ksize_h, const int32_t* bounds_v,
+                          const int32_t* kk_v, int32_t ksize_v, uint8_t* tmp, uint8_t* out_u8, float* out_f32,
+                          void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  OFA_REQUIRE(n >= 0 && h > 0 && w > 0 && out_h > 0 && out_w > 0, "ofa_bicubic_resize_u8: bad sizes");
+  if (n == 0) return OFA_OK;
+  OFA_REQUIRE(src && tmp && (out_u8 || out_f32), "ofa_bicubic_resize_u8: null pointer");
+  OFA_REQUIRE(bounds_h && kk_h && bounds_v && kk_v, "ofa_bicubic_resize_u8: null coefficient table");
+  OFA_REQUIRE(ksize_h == resample_ksize(w, out_w) && ksize_v == resample_ksize(h, out_h),
+              "ofa_bicubic_resize_u8: table built for other sizes (ksize %d / %d)", ksize_h, ksize_v);
+  return launch_bicubic_resize_u8(src, n, h, w, out_h, out_w, bounds_h, kk_h, ksize_h, bounds_v, kk_v, ksize_v, tmp,
+                                  out_u8, out_f32, (cudaStream_t)stream);
+}
+
+int ofa_sr_augment_u8(const uint8_t* src, int64_t sample_stride, int32_t n, int32_t h, int32_t w,
+                      const int32_t* params, int32_t size, uint8_t* out_u8, float* out_f32, void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  OFA_REQUIRE(n >= 0 && h > 0 && w > 0 && size > 0 && size <= h && size <= w, "ofa_sr_augment_u8: bad sizes");
+  if (n == 0) return OFA_OK;
+  OFA_REQUIRE(src && params && (out_u8 || out_f32), "ofa_sr_augment_u8: null pointer");
+  return launch_sr_augment_u8(src, sample_stride, n, w, params, size, out_u8, out_f32, (cudaStream_t)stream);
+}
+
 int ofa_dw_bwd_filter(const OfaTensor4* x, const OfaTensor4* dy, int32_t ks, float* dw_active, void* stream) {
   int rc = require_device();
   if (rc) return rc;

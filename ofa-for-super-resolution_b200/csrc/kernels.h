@@ -69,4 +69,13 @@ int launch_dw_planar(const void* x, void* y, int N, int C, int H, int W, const f
 int launch_project_planar(const void* x, const void* res, void* y, const void* wproj_p, int N, int HW, int mid,
                           int trunk_f16, int f16, const OfaBn* bn, cudaStream_t st);
 
+// ---- data_prep.cu : SR data preparation (Pillow-exact bicubic resampling, crop / flip / rotate, ToTensor) ----
+int resample_ksize(int in_size, int out_size);
+int resample_build_table(int in_size, int out_size, int32_t* bounds_host, int32_t* kk_host);
+int launch_bicubic_resize_u8(const uint8_t* src, int N, int H, int W, int oh, int ow, const int32_t* bounds_h,
+                             const int32_t* kk_h, int ksize_h, const int32_t* bounds_v, const int32_t* kk_v,
+                             int ksize_v, uint8_t* tmp, uint8_t* out_u8, float* out_f32, cudaStream_t st);
+int launch_sr_augment_u8(const uint8_t* src, long long sample_stride, int N, int W, const int32_t* params, int S,
+                         uint8_t* out_u8, float* out_f32, cudaStream_t st);
+
 }  // namespace ofa

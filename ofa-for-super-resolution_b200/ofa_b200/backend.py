@@ -106,6 +106,12 @@ SYMBOLS = {
                                     c_void_p, c_void_p, c_void_p]),
     'ofa_bn_bwd_apply': (c_int32, [_T4, _T4, _T4, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int32,
                                    c_int32, c_void_p, c_void_p, c_void_p]),
+    'ofa_resample_ksize': (c_int32, [c_int32, c_int32]),
+    'ofa_resample_build_table': (c_int32, [c_int32, c_int32, c_void_p, c_void_p]),
+    'ofa_bicubic_resize_u8': (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,
+                                        c_int32, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'ofa_sr_augment_u8': (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p,
+                                    c_void_p, c_void_p]),
 }
 
 _lib = None
