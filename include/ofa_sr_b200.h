@@ -44,6 +44,7 @@ extern "C" {
 #define OFA_ACT_RELU6 1
 #define OFA_ACT_HSWISH 2
 #define OFA_ACT_RELU 3
+#define OFA_ACT_HSIGMOID 4 /* relu6(x + 3) / 6 — the gate of the squeeze-and-excite module (ofa/utils.py:345-352) */
 
 /* store modes of a ConvLayer's third op (ofa/layers.py:94-98 + ofa/utils.py:259-260,383-410) */
 #define OFA_STORE_PLAIN 0
@@ -329,6 +330,42 @@ int ofa_bicubic_resize_u8(const uint8_t* src, int32_t n, int32_t h, int32_t w, i
                           void* stream);
 int ofa_sr_augment_u8(const uint8_t* src, int64_t sample_stride, int32_t n, int32_t h, int32_t w,
                       const int32_t* params, int32_t size, uint8_t* out_u8, float* out_f32, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ *  the MobileNetV3 flavour of the elastic modules — ops the SR nets do not exercise.
+ * Exact fp32 CUDA-core kernels; row-major fp32 matrices with explicit leading dimensions (elements).
+ *
+ * ofa_linear_fwd        DynamicLinear.forward (dynamic_op.py:115-136) and the two 1x1 convs of DynamicSE on the pooled
+ *                       [N, C, 1, 1] tensor (:175-200): y[n, o] = act(bias[o] + sum_i x[n, i] * w[o * ldw + i]); the
+ *                       active slice w[:out, :in] is addressed in place through ldw (the reference copies it).
+ * ofa_act_bwd_from_output   dz = dy * act'(z), derivative taken from the OUTPUT (ReLU / ReLU6 / h-sigmoid)
+ * ofa_linear_bwd_data   dx[n, i] = sum_o dz[n, o] * w[o * ldw + i]
+ * ofa_linear_bwd_weight dw[o * lddw + i] = sum_n dz[n, o] * x[n, i] (overwrites the active slice), db[o] = sum_n dz
+ * ofa_plane_mean        pooled[n * C + c] = mean over (h, w) of x — SEModule's x.mean(3).mean(2) (ofa/utils.py:371)
+ * ofa_plane_dot         out[n * C + c] = sum over (h, w) of x * dy — gradient of the gate in y = x * s
+ * ofa_channel_scale     y[n, c, h, w] = x[n, c, h, w] * s[n * C + c] (+ add[n * C + c] when not NULL) — `x * y` of
+ *                       SEModule.forward (:373), and with (dy, s, dpooled / HW) its input gradient
+ * ofa_dw_strided_*      DynamicSeparableConv2d.forward with stride > 1 (dynamic_op.py:73-84; same padding ks // 2,
+ *                       output (H - 1) / stride + 1) on the explicit active filter [C][ks * ks] that
+ *                       ofa_dw_active_filter produced; the filter gradient is overwritten (not accumulated) and
+ *                       continues through ofa_dw_active_filter_bwd.
+ * ------------------------------------------------------------------------------------------- */
+int ofa_linear_fwd(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, int32_t n,
+                   int32_t in_features, int32_t out_features, int32_t act, float* y, int64_t ldy, void* stream);
+int ofa_act_bwd_from_output(const float* dy, const float* y, int32_t act, float* dz, int64_t total, void* stream);
+int ofa_linear_bwd_data(const float* dz, int64_t lddz, const float* w, int64_t ldw, int32_t n, int32_t in_features,
+                        int32_t out_features, float* dx, int64_t lddx, void* stream);
+int ofa_linear_bwd_weight(const float* dz, int64_t lddz, const float* x, int64_t ldx, int32_t n, int32_t in_features,
+                          int32_t out_features, float* dw, int64_t lddw, float* db, void* stream);
+int ofa_plane_mean(const OfaTensor4* x, float* pooled, void* stream);
+int ofa_plane_dot(const OfaTensor4* x, const OfaTensor4* dy, float* out, void* stream);
+int ofa_channel_scale(const OfaTensor4* x, const OfaTensor4* y, const float* s, const float* add, void* stream);
+int ofa_dw_strided_fwd(const OfaTensor4* x, const OfaTensor4* y, const float* filt, int32_t ks, int32_t stride,
+                       const OfaEpilogue* epi, void* stream);
+int ofa_dw_strided_bwd_data(const OfaTensor4* dy, const OfaTensor4* dx, const float* filt, int32_t ks, int32_t stride,
+                            void* stream);
+int ofa_dw_strided_bwd_filter(const OfaTensor4* x, const OfaTensor4* dy, int32_t ks, int32_t stride, float* dfilt,
+                              void* stream);
 
 #ifdef __cplusplus
 }

@@ -69,7 +69,7 @@ static int same_shape(const OfaTensor4* a, const OfaTensor4* b, const char* what
 
 static int check_epi(const OfaEpilogue* e, const OfaTensor4* y) {
   if (!e) return OFA_OK;
-  OFA_REQUIRE(e->act >= OFA_ACT_NONE && e->act <= OFA_ACT_RELU, "bad activation code %d", e->act);
+  OFA_REQUIRE(e->act >= OFA_ACT_NONE && e->act <= OFA_ACT_HSIGMOID, "bad activation code %d", e->act);
   if (e->residual) {
     int rc = check_tensor(e->residual, "residual");
     if (rc) return rc;
@@ -425,6 +425,122 @@ int ofa_psnr_y_sse(const OfaTensor4* a, const OfaTensor4* b, int64_t* sse_per_im
   OFA_REQUIRE(sse_per_image != nullptr, "ofa_psnr_y_sse: null output");
   OFA_REQUIRE((long long)a->h * a->w < (1ll << 31), "ofa_psnr_y_sse: image too large");
   return launch_psnr_y_sse(make_tv(a), make_tv(b), reinterpret_cast<long long*>(sse_per_image), (cudaStream_t)stream);
+}
+
+int ofa_linear_fwd(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, int32_t n,
+                   int32_t in_features, int32_t out_features, int32_t act, float* y, int64_t ldy, void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  OFA_REQUIRE(n >= 0 && in_features >= 0 && out_features >= 0, "ofa_linear_fwd: negative size");
+  if (n == 0 || out_features == 0) return OFA_OK;
+  OFA_REQUIRE(x && w && y, "ofa_linear_fwd: null pointer");
+  OFA_REQUIRE(ldx >= in_features && ldw >= in_features && ldy >= out_features, "ofa_linear_fwd: leading dimension too small");
+  OFA_REQUIRE(act >= OFA_ACT_NONE && act <= OFA_ACT_HSIGMOID, "bad activation code %d", act);
+  return launch_linear_fwd(x, ldx, w, ldw, bias, n, in_features, out_features, act, y, ldy, (cudaStream_t)stream);
+}
+
+int ofa_act_bwd_from_output(const float* dy, const float* y, int32_t act, float* dz, int64_t total, void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  if (total == 0) return OFA_OK;
+  OFA_REQUIRE(dy && y && dz && total > 0, "ofa_act_bwd_from_output: bad arguments");
+  OFA_REQUIRE(act == OFA_ACT_NONE || act == OFA_ACT_RELU || act == OFA_ACT_RELU6 || act == OFA_ACT_HSIGMOID,
+              "ofa_act_bwd_from_output: activation %d has no derivative in terms of its output", act);
+  return launch_act_bwd_from_output(dy, y, act, dz, total, (cudaStream_t)stream);
+}
+
+int ofa_linear_bwd_data(const float* dz, int64_t lddz, const float* w, int64_t ldw, int32_t n, int32_t in_features,
+                        int32_t out_features, float* dx, int64_t lddx, void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  if (n == 0 || in_features == 0) return OFA_OK;
+  OFA_REQUIRE(dz && w && dx && n > 0 && in_features > 0 && out_features >= 0, "ofa_linear_bwd_data: bad arguments");
+  return launch_linear_bwd_data(dz, lddz, w, ldw, n, in_features, out_features, dx, lddx, (cudaStream_t)stream);
+}
+
+int ofa_linear_bwd_weight(const float* dz, int64_t lddz, const float* x, int64_t ldx, int32_t n, int32_t in_features,
+                          int32_t out_features, float* dw, int64_t lddw, float* db, void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  if (out_features == 0) return OFA_OK;
+  OFA_REQUIRE(dz && x && dw && n >= 0 && in_features >= 0 && out_features > 0, "ofa_linear_bwd_weight: bad arguments");
+  return launch_linear_bwd_weight(dz, lddz, x, ldx, n, in_features, out_features, dw, lddw, db, (cudaStream_t)stream);
+}
+
+int ofa_plane_mean(const OfaTensor4* x, float* pooled, void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  if ((rc = check_tensor(x, "x"))) return rc;
+  OFA_REQUIRE(pooled != nullptr, "ofa_plane_mean: null output");
+  OFA_REQUIRE((long long)x->h * x->w > 0 && (long long)x->h * x->w < (1ll << 31), "ofa_plane_mean: bad plane size");
+  TV tx = make_tv(x);
+  return launch_plane_reduce(tx, nullptr, 1.f / (float)((long long)x->h * x->w), pooled, (cudaStream_t)stream);
+}
+
+int ofa_plane_dot(const OfaTensor4* x, const OfaTensor4* dy, float* out, void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  if ((rc = check_tensor(x, "x"))) return rc;
+  if ((rc = check_tensor(dy, "dy"))) return rc;
+  if ((rc = same_shape(x, dy, "plane_dot x vs dy"))) return rc;
+  OFA_REQUIRE(out != nullptr, "ofa_plane_dot: null output");
+  TV tx = make_tv(x), tdy = make_tv(dy);
+  return launch_plane_reduce(tx, &tdy, 1.f, out, (cudaStream_t)stream);
+}
+
+int ofa_channel_scale(const OfaTensor4* x, const OfaTensor4* y, const float* s, const float* add, void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  if ((rc = check_tensor(x, "x"))) return rc;
+  if ((rc = check_tensor(y, "y"))) return rc;
+  if ((rc = same_shape(x, y, "channel_scale x vs y"))) return rc;
+  OFA_REQUIRE(s != nullptr, "ofa_channel_scale: null scale");
+  return launch_channel_scale(make_tv(x), make_tv(y), s, add, (cudaStream_t)stream);
+}
+
+static int dw_strided_shapes(const OfaTensor4* big, const OfaTensor4* small, int32_t ks, int32_t stride) {
+  OFA_REQUIRE(ks == 3 || ks == 5 || ks == 7, "kernel size must be 3, 5 or 7 (got %d)", ks);
+  OFA_REQUIRE(stride >= 1 && stride <= 4, "depthwise stride must be 1..4 (got %d)", stride);
+  OFA_REQUIRE(small->n == big->n && small->c == big->c && small->h == (big->h - 1) / stride + 1 &&
+                  small->w == (big->w - 1) / stride + 1,
+              "strided depthwise: output must be [%d, %d, %d, %d]", big->n, big->c, (big->h - 1) / stride + 1,
+              (big->w - 1) / stride + 1);
+  return OFA_OK;
+}
+
+int ofa_dw_strided_fwd(const OfaTensor4* x, const OfaTensor4* y, const float* filt, int32_t ks, int32_t stride,
+                       const OfaEpilogue* epi, void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  if ((rc = check_tensor(x, "x"))) return rc;
+  if ((rc = check_tensor(y, "y"))) return rc;
+  OFA_REQUIRE(filt != nullptr, "ofa_dw_strided_fwd: null filter");
+  if ((rc = dw_strided_shapes(x, y, ks, stride))) return rc;
+  if ((rc = check_epi(epi, y))) return rc;
+  OFA_REQUIRE(!epi || !epi->residual, "ofa_dw_strided_fwd: no residual on a strided layer");
+  return launch_dw_strided_fwd(make_tv(x), make_tv(y), filt, ks, stride, make_epi(epi), (cudaStream_t)stream);
+}
+
+int ofa_dw_strided_bwd_data(const OfaTensor4* dy, const OfaTensor4* dx, const float* filt, int32_t ks, int32_t stride,
+                            void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  if ((rc = check_tensor(dy, "dy"))) return rc;
+  if ((rc = check_tensor(dx, "dx"))) return rc;
+  OFA_REQUIRE(filt != nullptr, "ofa_dw_strided_bwd_data: null filter");
+  if ((rc = dw_strided_shapes(dx, dy, ks, stride))) return rc;
+  return launch_dw_strided_bwd_data(make_tv(dy), make_tv(dx), filt, ks, stride, (cudaStream_t)stream);
+}
+
+int ofa_dw_strided_bwd_filter(const OfaTensor4* x, const OfaTensor4* dy, int32_t ks, int32_t stride, float* dfilt,
+                              void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  if ((rc = check_tensor(x, "x"))) return rc;
+  if ((rc = check_tensor(dy, "dy"))) return rc;
+  OFA_REQUIRE(dfilt != nullptr, "ofa_dw_strided_bwd_filter: null output");
+  if ((rc = dw_strided_shapes(x, dy, ks, stride))) return rc;
+  return launch_dw_strided_bwd_filter(make_tv(x), make_tv(dy), ks, stride, dfilt, (cudaStream_t)stream);
 }
 
 int32_t ofa_resample_ksize(int32_t in_size, int32_t out_size) { return resample_ksize(in_size, out_size); }

@@ -78,4 +78,18 @@ int launch_bicubic_resize_u8(const uint8_t* src, int N, int H, int W, int oh, in
 int launch_sr_augment_u8(const uint8_t* src, long long sample_stride, int N, int W, const int32_t* params, int S,
                          uint8_t* out_u8, float* out_f32, cudaStream_t st);
 
+// ---- mbv3_ops.cu : squeeze-and-excite, sliced linear, strided depthwise (exact fp32 CUDA-core kernels) ----
+int launch_linear_fwd(const float* x, long long ldx, const float* w, long long ldw, const float* bias, int N, int in,
+                      int out, int act, float* y, long long ldy, cudaStream_t st);
+int launch_linear_bwd_data(const float* dz, long long lddz, const float* w, long long ldw, int N, int in, int out,
+                           float* dx, long long lddx, cudaStream_t st);
+int launch_linear_bwd_weight(const float* dz, long long lddz, const float* x, long long ldx, int N, int in, int out,
+                             float* dw, long long lddw, float* db, cudaStream_t st);
+int launch_act_bwd_from_output(const float* dy, const float* y, int act, float* dz, long long total, cudaStream_t st);
+int launch_plane_reduce(const TV& x, const TV* dy, float scale, float* out, cudaStream_t st);
+int launch_channel_scale(const TV& x, const TV& y, const float* s, const float* add, cudaStream_t st);
+int launch_dw_strided_fwd(const TV& x, const TV& y, const float* f, int ks, int stride, const Epi& epi, cudaStream_t st);
+int launch_dw_strided_bwd_data(const TV& dy, const TV& dx, const float* f, int ks, int stride, cudaStream_t st);
+int launch_dw_strided_bwd_filter(const TV& x, const TV& dy, int ks, int stride, float* df, cudaStream_t st);
+
 }  // namespace ofa

@@ -15,7 +15,7 @@ _LIB_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'lib')
 LIB_PATH = os.path.join(_LIB_DIR, 'libofa_sr_b200.so')
 
 OFA_F32, OFA_BF16, OFA_F16 = 0, 1, 2
-ACT_NONE, ACT_RELU6, ACT_HSWISH, ACT_RELU = 0, 1, 2, 3
+ACT_NONE, ACT_RELU6, ACT_HSWISH, ACT_RELU, ACT_HSIGMOID = 0, 1, 2, 3, 4
 STORE_PLAIN, STORE_PIXELSHUFFLE2, STORE_PIXELUNSHUFFLE2 = 0, 1, 2
 IMPL_AUTO, IMPL_SIMT, IMPL_FAST, IMPL_NHWC = 0, 1, 2, 3
 
@@ -106,6 +106,19 @@ SYMBOLS = {
                                     c_void_p, c_void_p, c_void_p]),
     'ofa_bn_bwd_apply': (c_int32, [_T4, _T4, _T4, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int32,
                                    c_int32, c_void_p, c_void_p, c_void_p]),
+    'ofa_linear_fwd': (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                                 c_void_p, c_int64, c_void_p]),
+    'ofa_act_bwd_from_output': (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int64, c_void_p]),
+    'ofa_linear_bwd_data': (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p,
+                                      c_int64, c_void_p]),
+    'ofa_linear_bwd_weight': (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p,
+                                        c_int64, c_void_p, c_void_p]),
+    'ofa_plane_mean': (c_int32, [_T4, c_void_p, c_void_p]),
+    'ofa_plane_dot': (c_int32, [_T4, _T4, c_void_p, c_void_p]),
+    'ofa_channel_scale': (c_int32, [_T4, _T4, c_void_p, c_void_p, c_void_p]),
+    'ofa_dw_strided_fwd': (c_int32, [_T4, _T4, c_void_p, c_int32, c_int32, _EP, c_void_p]),
+    'ofa_dw_strided_bwd_data': (c_int32, [_T4, _T4, c_void_p, c_int32, c_int32, c_void_p]),
+    'ofa_dw_strided_bwd_filter': (c_int32, [_T4, _T4, c_int32, c_int32, c_void_p, c_void_p]),
     'ofa_resample_ksize': (c_int32, [c_int32, c_int32]),
     'ofa_resample_build_table': (c_int32, [c_int32, c_int32, c_void_p, c_void_p]),
     'ofa_bicubic_resize_u8': (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,

@@ -14,14 +14,14 @@ from collections import OrderedDict
 import torch
 import torch.nn as nn
 
-from ...layers import MBInvertedConvLayer, ConvLayer, _split_act
-from ...utils import MyModule, int2list, get_net_device, build_activation, make_divisible
+from ...layers import MBInvertedConvLayer, ConvLayer, LinearLayer, _split_act
+from ...utils import MyModule, int2list, get_net_device, build_activation, make_divisible, SEModule
 from ..utils import adjust_bn_according_to_idx, copy_bn
-from .dynamic_op import DynamicSeparableConv2d, DynamicPointConv2d, DynamicBatchNorm2d
+from .dynamic_op import DynamicSeparableConv2d, DynamicPointConv2d, DynamicBatchNorm2d, DynamicLinear, DynamicSE
 from ... import functional as OF
 from ... import backend as B
 
-__all__ = ['DynamicMBConvLayer', 'DynamicConvLayer']
+__all__ = ['DynamicMBConvLayer', 'DynamicConvLayer', 'DynamicLinearLayer']
 
 
 class DynamicMBConvLayer(MyModule):
@@ -36,8 +36,6 @@ class DynamicMBConvLayer(MyModule):
         self.stride = stride
         self.act_func = act_func
         self.use_se = use_se
-        if use_se or stride != 1:
-            raise NotImplementedError('SE / strided elastic MBConv are not part of the SR nets (SURVEY §8f rank 4)')
 
         max_middle_channel = round(max(self.in_channel_list) * max(self.expand_ratio_list))
         has_act = build_activation(self.act_func, inplace=True) is not None
@@ -55,6 +53,8 @@ class DynamicMBConvLayer(MyModule):
                                            max_middle_channel)
         self.depth_conv = seq(DynamicSeparableConv2d(max_middle_channel, self.kernel_size_list, self.stride),
                               max_middle_channel)
+        if self.use_se:
+            self.depth_conv.add_module('se', DynamicSE(max_middle_channel))
         self.point_linear = nn.Sequential(OrderedDict([
             ('conv', DynamicPointConv2d(max_middle_channel, max(self.out_channel_list))),
             ('bn', DynamicBatchNorm2d(max(self.out_channel_list))),
@@ -87,7 +87,7 @@ class DynamicMBConvLayer(MyModule):
         bn_ex = self.inverted_bottleneck.bn.bn if self.inverted_bottleneck is not None else None
         hooked = DynamicBatchNorm2d.SET_RUNNING_STATISTICS or OF.bn_hooked(bn_ex, bn_dw, bn_pl)
 
-        if OF.inference_mode_active(self) and not hooked:
+        if OF.inference_mode_active(self) and not hooked and not self.use_se and self.stride == 1:
             if self.inverted_bottleneck is not None:
                 mid = self.inverted_bottleneck.conv.active_out_channel
                 exp = self.inverted_bottleneck.conv
@@ -114,6 +114,8 @@ class DynamicMBConvLayer(MyModule):
             h = DynamicBatchNorm2d.bn_forward(h, self.inverted_bottleneck.bn.bn, mid, act)
         h = dwm(h)
         h = DynamicBatchNorm2d.bn_forward(h, bn_dw, mid, act)
+        if self.use_se:
+            h = self.depth_conv.se(h)
         h = self.point_linear.conv(h)
         return DynamicBatchNorm2d.bn_forward(h, bn_pl, cout, B.ACT_NONE, residual)
 
@@ -151,6 +153,13 @@ class DynamicMBConvLayer(MyModule):
         sub_layer.depth_conv.conv.weight.data.copy_(
             self.depth_conv.conv.get_active_filter(middle_channel, self.active_kernel_size).data)
         copy_bn(sub_layer.depth_conv.bn, self.depth_conv.bn.bn)
+        if self.use_se:
+            se_mid = make_divisible(middle_channel // SEModule.REDUCTION, divisor=8)
+            src, dst = self.depth_conv.se.fc, sub_layer.depth_conv.se.fc
+            dst.reduce.weight.data.copy_(src.reduce.weight.data[:se_mid, :middle_channel, :, :])
+            dst.reduce.bias.data.copy_(src.reduce.bias.data[:se_mid])
+            dst.expand.weight.data.copy_(src.expand.weight.data[:middle_channel, :se_mid, :, :])
+            dst.expand.bias.data.copy_(src.expand.bias.data[:middle_channel])
         sub_layer.point_linear.conv.weight.data.copy_(
             self.point_linear.conv.conv.weight.data[:self.active_out_channel, :middle_channel, :, :])
         copy_bn(sub_layer.point_linear.bn, self.point_linear.bn.bn)
@@ -170,6 +179,18 @@ class DynamicMBConvLayer(MyModule):
         adjust_bn_according_to_idx(self.depth_conv.bn.bn, sorted_idx)
         dw = self.depth_conv.conv.conv
         dw.weight.data = torch.index_select(dw.weight.data, 0, sorted_idx)
+        if self.use_se:
+            # expand: output dim follows the middle channels; reduce: input dim; then the SE middle channels are
+            # sorted by their own importance (dynamic_layers.py:175-189)
+            se_expand, se_reduce = self.depth_conv.se.fc.expand, self.depth_conv.se.fc.reduce
+            se_expand.weight.data = torch.index_select(se_expand.weight.data, 0, sorted_idx)
+            se_expand.bias.data = torch.index_select(se_expand.bias.data, 0, sorted_idx)
+            se_reduce.weight.data = torch.index_select(se_reduce.weight.data, 1, sorted_idx)
+            se_importance = torch.sum(torch.abs(se_expand.weight.data), dim=(0, 2, 3))
+            _, se_idx = torch.sort(se_importance, dim=0, descending=True)
+            se_expand.weight.data = torch.index_select(se_expand.weight.data, 1, se_idx)
+            se_reduce.weight.data = torch.index_select(se_reduce.weight.data, 0, se_idx)
+            se_reduce.bias.data = torch.index_select(se_reduce.bias.data, 0, se_idx)
         if self.inverted_bottleneck is not None:
             adjust_bn_according_to_idx(self.inverted_bottleneck.bn.bn, sorted_idx)
             ib = self.inverted_bottleneck.conv.conv
@@ -240,4 +261,53 @@ class DynamicConvLayer(MyModule):
         sub_layer.conv.weight.data.copy_(self.conv.conv.weight.data[:self.active_out_channel, :in_channel, :, :])
         if self.use_bn:
             copy_bn(sub_layer.bn, self.bn.bn)
+        return sub_layer
+
+
+class DynamicLinearLayer(MyModule):
+    """dynamic_layers.py:270-322: [dropout ->] DynamicLinear over the active input width."""
+
+    def __init__(self, in_features_list, out_features, bias=True, dropout_rate=0):
+        super().__init__()
+        self.in_features_list = in_features_list
+        self.out_features = out_features
+        self.bias = bias
+        self.dropout_rate = dropout_rate
+        if self.dropout_rate > 0:
+            self.dropout = nn.Dropout(self.dropout_rate, inplace=True)
+        else:
+            self.dropout = None
+        self.linear = DynamicLinear(max_in_features=max(self.in_features_list), max_out_features=self.out_features,
+                                    bias=self.bias)
+
+    def forward(self, x):
+        if self.dropout is not None:
+            x = self.dropout(x)
+        return self.linear(x)
+
+    @property
+    def module_str(self):
+        return 'DyLinear(%d)' % self.out_features
+
+    @property
+    def config(self):
+        return {
+            'name': DynamicLinear.__name__,      # (sic) the reference stores the op's class name here
+            'in_features_list': self.in_features_list,
+            'out_features': self.out_features,
+            'bias': self.bias,
+        }
+
+    @staticmethod
+    def build_from_config(config):
+        return DynamicLinearLayer(**config)
+
+    def get_active_subnet(self, in_features, preserve_weight=True):
+        sub_layer = LinearLayer(in_features, self.out_features, self.bias, dropout_rate=self.dropout_rate)
+        sub_layer = sub_layer.to(get_net_device(self))
+        if not preserve_weight:
+            return sub_layer
+        sub_layer.linear.weight.data.copy_(self.linear.linear.weight.data[:self.out_features, :in_features])
+        if self.bias:
+            sub_layer.linear.bias.data.copy_(self.linear.linear.bias.data[:self.out_features])
         return sub_layer

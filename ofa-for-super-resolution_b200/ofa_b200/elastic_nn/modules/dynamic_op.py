@@ -13,11 +13,11 @@ import torch
 import torch.nn as nn
 from torch.nn.parameter import Parameter
 
-from ...utils import get_same_padding, sub_filter_start_end
+from ...utils import get_same_padding, sub_filter_start_end, make_divisible, SEModule
 from ... import functional as OF
 from ... import backend as B
 
-__all__ = ['DynamicSeparableConv2d', 'DynamicPointConv2d', 'DynamicBatchNorm2d']
+__all__ = ['DynamicSeparableConv2d', 'DynamicPointConv2d', 'DynamicBatchNorm2d', 'DynamicLinear', 'DynamicSE']
 
 
 class DynamicSeparableConv2d(nn.Module):
@@ -54,8 +54,8 @@ class DynamicSeparableConv2d(nn.Module):
         return m_big, m_small
 
     def _check_supported(self, kernel_size):
-        if self.stride != 1 or self.dilation != 1:
-            raise NotImplementedError('the B200 depthwise kernel covers stride 1 / dilation 1 (all SR nets)')
+        if self.dilation != 1 or self.stride not in (1, 2, 3, 4):
+            raise NotImplementedError('the B200 depthwise kernels cover dilation 1 and strides 1..4')
         if not set(self._ks_set) <= {3, 5, 7}:
             raise NotImplementedError('kernel sizes must come from {3, 5, 7}, got %s' % (self._ks_set,))
         if kernel_size not in self._ks_set and kernel_size != max(self.kernel_size_list):
@@ -78,7 +78,7 @@ class DynamicSeparableConv2d(nn.Module):
         get_same_padding(kernel_size)  # asserts an odd size, like the reference
         m75, m53 = self._matrices()
         transform_on = self.KERNEL_TRANSFORM_MODE is not None
-        return OF.dw_conv(x, self.conv.weight, m75, m53, kernel_size, transform_on)
+        return OF.dw_conv(x, self.conv.weight, m75, m53, kernel_size, transform_on, self.stride)
 
 
 class DynamicPointConv2d(nn.Module):
@@ -106,6 +106,23 @@ class DynamicPointConv2d(nn.Module):
         return OF.conv2d(x, self.conv.weight, in_channel, out_channel, self.kernel_size)
 
 
+class DynamicLinear(nn.Module):
+    """dynamic_op.py:115-136: F.linear(x, W[:out, :in], b[:out]) with the slice addressed in place."""
+
+    def __init__(self, max_in_features, max_out_features, bias=True):
+        super().__init__()
+        self.max_in_features = max_in_features
+        self.max_out_features = max_out_features
+        self.bias = bias
+        self.linear = nn.Linear(self.max_in_features, self.max_out_features, self.bias)
+        self.active_out_features = self.max_out_features
+
+    def forward(self, x, out_features=None):
+        if out_features is None:
+            out_features = self.active_out_features
+        return OF.linear(x, self.linear.weight, self.linear.bias if self.bias else None, out_features)
+
+
 class DynamicBatchNorm2d(nn.Module):
     SET_RUNNING_STATISTICS = False
 
@@ -125,3 +142,16 @@ class DynamicBatchNorm2d(nn.Module):
     def forward(self, x):
         feature_dim = x.size(1)
         return self.bn_forward(x, self.bn, feature_dim)
+
+
+class DynamicSE(SEModule):
+    """dynamic_op.py:175-200: squeeze-and-excite on the active channel prefix; the reduce / expand 1x1 convs are sliced
+    to [:num_mid, :C] and [:C, :num_mid] with num_mid = make_divisible(C // reduction, 8)."""
+
+    def __init__(self, max_channel):
+        super().__init__(max_channel)
+
+    def forward(self, x):
+        in_channel = x.size(1)
+        num_mid = make_divisible(in_channel // self.reduction, divisor=8)
+        return self._se(x, num_mid)

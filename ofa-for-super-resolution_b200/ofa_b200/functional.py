@@ -142,25 +142,175 @@ class DwConvFn(torch.autograd.Function):
             dwa = torch.empty((c, ks * ks), dtype=torch.float32, device=x.device)
             tx = B.t4(x)
             B.check(L.ofa_dw_bwd_filter(byref(tx), byref(tdy), ks, dwa.data_ptr(), st))
-            dw7 = torch.zeros_like(w7)
-            use75 = transform_on and ks < kmax and m75 is not None
-            use53 = transform_on and ks < kmax and ks == 3 and m53 is not None
-            dm75 = torch.zeros_like(m75) if m75 is not None else None
-            dm53 = torch.zeros_like(m53) if m53 is not None else None
-            B.check(L.ofa_dw_active_filter_bwd(B.fptr(w7), kmax, p75, p53, int(bool(transform_on)), ks, c,
-                                               dwa.data_ptr(), dw7.data_ptr(),
-                                               dm75.data_ptr() if dm75 is not None else None,
-                                               dm53.data_ptr() if dm53 is not None else None, st))
-            # matrices that did not take part get no gradient (autograd of the reference leaves them None)
-            if not use75:
-                dm75 = None
-            if not use53:
-                dm53 = None
+            dw7, dm75, dm53 = _dw_filter_chain(dwa, w7, m75, m53, transform_on, ks, c, st)
         return dx, dw7, dm75, dm53, None, None
 
 
-def dw_conv(x, w7, m75, m53, ks, transform_on):
+def _dw_filter_chain(dwa, w7, m75, m53, transform_on, ks, c, st):
+    """Gradient of the [C, ks*ks] active filter back to the stored 7x7 weights and the learned transform matrices
+    (chain rule through dynamic_op.py:46-71)."""
+    kmax = w7.shape[-1]
+    p75, p53 = _transform_ptrs(m75, m53)
+    dw7 = torch.zeros_like(w7)
+    use75 = transform_on and ks < kmax and m75 is not None
+    use53 = transform_on and ks < kmax and ks == 3 and m53 is not None
+    dm75 = torch.zeros_like(m75) if m75 is not None else None
+    dm53 = torch.zeros_like(m53) if m53 is not None else None
+    B.check(B.lib().ofa_dw_active_filter_bwd(B.fptr(w7), kmax, p75, p53, int(bool(transform_on)), ks, c,
+                                             dwa.data_ptr(), dw7.data_ptr(),
+                                             dm75.data_ptr() if dm75 is not None else None,
+                                             dm53.data_ptr() if dm53 is not None else None, st))
+    return dw7, (dm75 if use75 else None), (dm53 if use53 else None)
+
+
+class DwStridedConvFn(torch.autograd.Function):
+    """Elastic depthwise conv with stride > 1 (DynamicSeparableConv2d built with stride 2 in the MobileNetV3-style
+    nets, dynamic_op.py:73-84): same padding ks // 2, output (H - 1) // stride + 1.  Exact fp32-accumulate CUDA-core
+    kernels on the materialised active filter."""
+
+    @staticmethod
+    def forward(ctx, x, w7, m75, m53, ks, transform_on, stride):
+        n, c, h, w = x.shape
+        filt = dw_active_filter(w7.detach(), m75, m53, transform_on, ks, c)
+        y = B.new_nhwc(n, c, (h - 1) // stride + 1, (w - 1) // stride + 1, x.dtype, x.device)
+        tx, ty = B.t4(x), B.t4(y)
+        B.check(B.lib().ofa_dw_strided_fwd(byref(tx), byref(ty), filt.data_ptr(), ks, stride, None, _stream(x)))
+        ctx.save_for_backward(x, w7, m75, m53, filt)
+        ctx.cfg = (ks, transform_on, stride)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w7, m75, m53, filt = ctx.saved_tensors
+        ks, transform_on, stride = ctx.cfg
+        n, c, h, w = x.shape
+        L, st = B.lib(), _stream(x)
+        tdy = B.t4(dy)
+        dx = dw7 = dm75 = dm53 = None
+        if ctx.needs_input_grad[0]:
+            dx = B.new_nhwc(n, c, h, w, x.dtype, dy.device)
+            tdx = B.t4(dx)
+            B.check(L.ofa_dw_strided_bwd_data(byref(tdy), byref(tdx), filt.data_ptr(), ks, stride, st))
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
+            dwa = torch.empty((c, ks * ks), dtype=torch.float32, device=x.device)
+            tx = B.t4(x)
+            B.check(L.ofa_dw_strided_bwd_filter(byref(tx), byref(tdy), ks, stride, dwa.data_ptr(), st))
+            dw7, dm75, dm53 = _dw_filter_chain(dwa, w7, m75, m53, transform_on, ks, c, st)
+        return dx, dw7, dm75, dm53, None, None, None
+
+
+def dw_conv(x, w7, m75, m53, ks, transform_on, stride=1):
+    if stride != 1:
+        return DwStridedConvFn.apply(x, w7, m75, m53, ks, transform_on, stride)
     return DwConvFn.apply(x, w7, m75, m53, ks, transform_on)
+
+
+# =================================================================================================
+# sliced fully connected layer and squeeze-and-excite (SURVEY §8f rank 4)
+# =================================================================================================
+
+def _linear_fwd(x, w, ldw, bias, in_f, out_f, act):
+    n = x.shape[0]
+    y = torch.empty((n, out_f), dtype=torch.float32, device=x.device)
+    B.check(B.lib().ofa_linear_fwd(x.data_ptr(), x.stride(0), B.fptr(w), ldw, _null_or(bias), n, in_f, out_f, act,
+                                   y.data_ptr(), out_f, _stream(x)))
+    return y
+
+
+def _linear_bwd(dz, x, w, ldw, in_f, out_f, want_dx, has_bias):
+    """(dx, dw_full, db_full): gradients of y = x w[:out,:in]^T + b[:out]; dw / db are full-size, zero outside the slice."""
+    L, st = B.lib(), _stream(dz)
+    n = dz.shape[0]
+    dx = None
+    if want_dx:
+        dx = torch.empty((n, in_f), dtype=torch.float32, device=dz.device)
+        B.check(L.ofa_linear_bwd_data(dz.data_ptr(), dz.stride(0), B.fptr(w), ldw, n, in_f, out_f, dx.data_ptr(), in_f, st))
+    dw = torch.zeros_like(w)
+    db = torch.zeros(w.shape[0], dtype=torch.float32, device=w.device) if has_bias else None
+    B.check(L.ofa_linear_bwd_weight(dz.data_ptr(), dz.stride(0), x.data_ptr(), x.stride(0), n, in_f, out_f,
+                                    dw.data_ptr(), ldw, db.data_ptr() if has_bias else None, st))
+    return dx, dw, db
+
+
+def _as_rows(x):
+    if not x.is_cuda:
+        raise RuntimeError('libofa_sr_b200 has no CPU path: tensor is on %s' % x.device)
+    assert x.dim() == 2
+    if x.dtype != torch.float32 or x.stride(1) != 1:
+        x = x.float().contiguous()
+    return x
+
+
+class LinearFn(torch.autograd.Function):
+    """DynamicLinear.forward (dynamic_op.py:115-136): F.linear(x, W[:out, :in], b[:out]) with the slice addressed in place."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, out_f):
+        x = _as_rows(x)
+        in_f = x.shape[1]
+        ctx.save_for_backward(x, w)
+        ctx.cfg = (in_f, out_f, bias is not None)
+        return _linear_fwd(x, w, w.stride(0), bias, in_f, out_f, B.ACT_NONE)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        in_f, out_f, has_bias = ctx.cfg
+        dx, dw, db = _linear_bwd(_as_rows(dy), x, w, w.stride(0), in_f, out_f, ctx.needs_input_grad[0], has_bias)
+        return dx, dw, db, None
+
+
+def linear(x, w, bias, out_features):
+    return LinearFn.apply(x, w, bias, out_features)
+
+
+class SEFn(torch.autograd.Function):
+    """DynamicSE.forward (dynamic_op.py:175-200): y = x * h_sigmoid(W_e[:C,:mid] relu(W_r[:mid,:C] mean_hw(x) + b_r) + b_e).
+    The 1x1 convs act on the pooled [N, C] matrix, i.e. they are sliced linear layers on the conv weights viewed
+    as [out_max, in_max] matrices."""
+
+    @staticmethod
+    def forward(ctx, x, w_r, b_r, w_e, b_e, mid):
+        n, c, h, w = x.shape
+        L, st = B.lib(), _stream(x)
+        tx = B.t4(x)
+        pooled = torch.empty((n, c), dtype=torch.float32, device=x.device)
+        B.check(L.ofa_plane_mean(byref(tx), pooled.data_ptr(), st))
+        h1 = _linear_fwd(pooled, w_r, w_r.stride(0), b_r, c, mid, B.ACT_RELU)
+        gate = _linear_fwd(h1, w_e, w_e.stride(0), b_e, mid, c, B.ACT_HSIGMOID)
+        y = B.new_nhwc(n, c, h, w, x.dtype, x.device)
+        ty = B.t4(y)
+        B.check(L.ofa_channel_scale(byref(tx), byref(ty), gate.data_ptr(), None, st))
+        ctx.save_for_backward(x, w_r, w_e, pooled, h1, gate)
+        ctx.cfg = (mid, b_r is not None, b_e is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w_r, w_e, pooled, h1, gate = ctx.saved_tensors
+        mid, has_br, has_be = ctx.cfg
+        n, c, h, w = x.shape
+        L, st = B.lib(), _stream(x)
+        tx, tdy = B.t4(x), B.t4(dy)
+        dgate = torch.empty((n, c), dtype=torch.float32, device=x.device)
+        B.check(L.ofa_plane_dot(byref(tx), byref(tdy), dgate.data_ptr(), st))
+        dz2 = torch.empty_like(dgate)
+        B.check(L.ofa_act_bwd_from_output(dgate.data_ptr(), gate.data_ptr(), B.ACT_HSIGMOID, dz2.data_ptr(), n * c, st))
+        dh1, dw_e, db_e = _linear_bwd(dz2, h1, w_e, w_e.stride(0), mid, c, True, has_be)
+        dz1 = torch.empty_like(dh1)
+        B.check(L.ofa_act_bwd_from_output(dh1.data_ptr(), h1.data_ptr(), B.ACT_RELU, dz1.data_ptr(), n * mid, st))
+        dpool, dw_r, db_r = _linear_bwd(dz1, pooled, w_r, w_r.stride(0), c, mid, True, has_br)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dpool.mul_(1.0 / (h * w))             # the mean's gradient, spread over the plane by the kernel below
+            dx = B.new_nhwc(n, c, h, w, x.dtype, x.device)
+            tdx = B.t4(dx)
+            B.check(L.ofa_channel_scale(byref(tdy), byref(tdx), gate.data_ptr(), dpool.data_ptr(), st))
+        return dx, dw_r, db_r, dw_e, db_e, None
+
+
+def squeeze_excite(x, w_reduce, b_reduce, w_expand, b_expand, mid):
+    return SEFn.apply(x, w_reduce, b_reduce, w_expand, b_expand, mid)
 
 
 # =================================================================================================

@@ -15,11 +15,11 @@ from collections import OrderedDict
 import torch
 import torch.nn as nn
 
-from .utils import MyModule, build_activation, get_same_padding
+from .utils import MyModule, build_activation, get_same_padding, SEModule
 from . import functional as OF
 from . import backend as B
 
-__all__ = ['set_layer_from_config', 'ConvLayer', 'IdentityLayer', 'ZeroLayer', 'MBInvertedConvLayer',
+__all__ = ['set_layer_from_config', 'ConvLayer', 'IdentityLayer', 'LinearLayer', 'ZeroLayer', 'MBInvertedConvLayer',
            'MobileInvertedResidualBlock']
 
 _FUSABLE_ACTS = {None: B.ACT_NONE, 'relu6': B.ACT_RELU6, 'relu': B.ACT_RELU, 'h_swish': B.ACT_HSWISH}
@@ -32,6 +32,7 @@ def set_layer_from_config(layer_config):
     name2layer = {
         ConvLayer.__name__: ConvLayer,
         IdentityLayer.__name__: IdentityLayer,
+        LinearLayer.__name__: LinearLayer,
         ZeroLayer.__name__: ZeroLayer,
         MBInvertedConvLayer.__name__: MBInvertedConvLayer,
     }
@@ -169,6 +170,49 @@ class IdentityLayer(MyModule):
         return IdentityLayer(**config)
 
 
+class LinearLayer(MyModule):
+    """Static fully connected layer (ofa/layers.py:335-418) in the only configuration the elastic nets build —
+    [dropout ->] linear, no BatchNorm1d, no activation (DynamicLinearLayer.get_active_subnet, classifier heads) —
+    on the library's sliced-linear kernel."""
+
+    def __init__(self, in_features, out_features, bias=True, use_bn=False, act_func=None, dropout_rate=0,
+                 ops_order='weight_bn_act'):
+        super().__init__()
+        if use_bn or act_func is not None:
+            raise NotImplementedError('LinearLayer with BatchNorm1d / activation is not used by the elastic nets')
+        self.in_features = in_features
+        self.out_features = out_features
+        self.bias = bias
+        self.use_bn = use_bn
+        self.act_func = act_func
+        self.dropout_rate = dropout_rate
+        self.ops_order = ops_order
+        if self.dropout_rate > 0:
+            self.dropout = nn.Dropout(self.dropout_rate, inplace=True)
+        self.linear = nn.Linear(self.in_features, self.out_features, self.bias)
+
+    def forward(self, x):
+        if self.dropout_rate > 0:
+            x = self.dropout(x)
+        return OF.linear(x, self.linear.weight, self.linear.bias if self.bias else None, self.out_features)
+
+    @property
+    def module_str(self):
+        return '%dx%d_Linear' % (self.in_features, self.out_features)
+
+    @property
+    def config(self):
+        return {
+            'name': LinearLayer.__name__, 'in_features': self.in_features, 'out_features': self.out_features,
+            'bias': self.bias, 'use_bn': self.use_bn, 'act_func': self.act_func, 'dropout_rate': self.dropout_rate,
+            'ops_order': self.ops_order,
+        }
+
+    @staticmethod
+    def build_from_config(config):
+        return LinearLayer(**config)
+
+
 class ZeroLayer(MyModule):
     def __init__(self, stride):
         super().__init__()
@@ -206,8 +250,6 @@ class MBInvertedConvLayer(MyModule):
         self.mid_channels = mid_channels
         self.act_func = act_func
         self.use_se = use_se
-        if use_se or stride != 1:
-            raise NotImplementedError('SE / strided MBConv are not part of the SR nets (SURVEY §8f rank 4)')
         feature_dim = round(self.in_channels * self.expand_ratio) if self.mid_channels is None else self.mid_channels
         self._feature_dim = feature_dim
         if self.expand_ratio == 1:
@@ -219,11 +261,14 @@ class MBInvertedConvLayer(MyModule):
                 ('act', build_activation(self.act_func, inplace=True)),
             ]))
         pad = get_same_padding(self.kernel_size)
-        self.depth_conv = nn.Sequential(OrderedDict([
+        depth_conv_modules = [
             ('conv', nn.Conv2d(feature_dim, feature_dim, kernel_size, stride, pad, groups=feature_dim, bias=False)),
             ('bn', nn.BatchNorm2d(feature_dim)),
             ('act', build_activation(self.act_func, inplace=True)),
-        ]))
+        ]
+        if self.use_se:
+            depth_conv_modules.append(('se', SEModule(feature_dim)))
+        self.depth_conv = nn.Sequential(OrderedDict(depth_conv_modules))
         self.point_linear = nn.Sequential(OrderedDict([
             ('conv', nn.Conv2d(feature_dim, out_channels, 1, 1, 0, bias=False)),
             ('bn', nn.BatchNorm2d(out_channels)),
@@ -238,6 +283,17 @@ class MBInvertedConvLayer(MyModule):
             self.inverted_bottleneck.bn if self.inverted_bottleneck is not None else None, self.depth_conv.bn,
             self.point_linear.bn)
         dw = self.depth_conv.conv.weight
+        if self.use_se or self.stride != 1:
+            # MobileNetV3 flavour: unfused kernels, same in train and eval mode
+            if self.inverted_bottleneck is not None:
+                x = OF.conv2d(x, self.inverted_bottleneck.conv.weight, self.in_channels, mid, 1)
+                x = OF.bn_act(x, self.inverted_bottleneck.bn, mid, act)
+            x = OF.dw_conv(x, dw, None, None, self.kernel_size, False, self.stride)
+            x = OF.bn_act(x, self.depth_conv.bn, mid, act)
+            if self.use_se:
+                x = self.depth_conv.se(x)
+            x = OF.conv2d(x, self.point_linear.conv.weight, mid, self.out_channels, 1)
+            return OF.bn_act(x, self.point_linear.bn, self.out_channels, B.ACT_NONE, residual)
         if infer:
             if self.inverted_bottleneck is not None:
                 x = OF.conv_bn_act_infer(x, self.inverted_bottleneck.conv.weight, self.in_channels, mid, 1,
@@ -257,6 +313,8 @@ class MBInvertedConvLayer(MyModule):
     def module_str(self):
         expand_ratio = self.expand_ratio if self.mid_channels is None else self.mid_channels // self.in_channels
         s = '%dx%d_MBConv%d_%s' % (self.kernel_size, self.kernel_size, expand_ratio, self.act_func.upper())
+        if self.use_se:
+            s = 'SE_' + s
         return s + '_O%d' % self.out_channels
 
     @property

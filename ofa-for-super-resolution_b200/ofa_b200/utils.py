@@ -24,7 +24,7 @@ import torch.nn.functional as F
 
 __all__ = [
     'make_divisible', 'int2list', 'sub_filter_start_end', 'get_same_padding', 'build_activation',
-    'PixelUnshuffle', 'pixel_unshuffle', 'Hswish', 'Hsigmoid', 'MyModule', 'MyNetwork', 'psnr',
+    'PixelUnshuffle', 'pixel_unshuffle', 'Hswish', 'Hsigmoid', 'SEModule', 'MyModule', 'MyNetwork', 'psnr',
     'tensor2img_np', 'rgb2y', 'get_net_device', 'AverageMeter',
 ]
 
@@ -83,6 +83,33 @@ class Hsigmoid(nn.Module):
 
     def forward(self, x):
         return F.relu6(x + 3., inplace=self.inplace) / 6.
+
+
+class SEModule(nn.Module):
+    """Squeeze-and-excite (ofa/utils.py:354-375): same children (`fc.reduce`, `fc.relu`, `fc.expand`,
+    `fc.h_sigmoid`) so checkpoints interchange; forward is the library's pool / sliced-linear / scale kernels."""
+    REDUCTION = 4
+
+    def __init__(self, channel):
+        super().__init__()
+        from collections import OrderedDict
+        self.channel = channel
+        self.reduction = SEModule.REDUCTION
+        num_mid = make_divisible(self.channel // self.reduction, divisor=8)
+        self.fc = nn.Sequential(OrderedDict([
+            ('reduce', nn.Conv2d(self.channel, num_mid, 1, 1, 0, bias=True)),
+            ('relu', nn.ReLU(inplace=True)),
+            ('expand', nn.Conv2d(num_mid, self.channel, 1, 1, 0, bias=True)),
+            ('h_sigmoid', Hsigmoid(inplace=True)),
+        ]))
+
+    def _se(self, x, num_mid):
+        from . import functional as OF
+        return OF.squeeze_excite(x, self.fc.reduce.weight, self.fc.reduce.bias, self.fc.expand.weight,
+                                 self.fc.expand.bias, num_mid)
+
+    def forward(self, x):
+        return self._se(x, self.fc.reduce.weight.shape[0])
 
 
 def pixel_unshuffle(input, downscale_factor):

@@ -153,6 +153,66 @@ def mbconv_block(x, sd, prefix, ks, expand, ks_set, training=False, momentum=0.1
 
 
 # ---------------------------------------------------------------------------------------------
+# the MobileNetV3 flavour of the elastic modules: SE, h-swish, stride, linear
+# ---------------------------------------------------------------------------------------------
+
+def h_sigmoid(x):
+    """ofa/utils.py:345-352 Hsigmoid"""
+    return F.relu6(x + 3.0) / 6.0
+
+
+def h_swish(x):
+    """ofa/utils.py:334-341 Hswish"""
+    return x * F.relu6(x + 3.0) / 6.0
+
+
+def apply_act(x, act_func):
+    """build_activation vocabulary used by the elastic blocks — ofa/utils.py:242-257"""
+    if act_func is None:
+        return x
+    return {'relu6': relu6, 'relu': F.relu, 'h_swish': h_swish, 'h_sigmoid': h_sigmoid}[act_func](x)
+
+
+def dynamic_se(x, sd, prefix, reduction=4):
+    """DynamicSE.forward — dynamic_op.py:175-200 (SEModule: ofa/utils.py:354-375).  prefix e.g. '...depth_conv.se.'"""
+    C = x.shape[1]
+    num_mid = make_divisible(C // reduction, divisor=8)
+    y = x.mean(3, keepdim=True).mean(2, keepdim=True)
+    y = F.relu(F.conv2d(y, sd[prefix + 'fc.reduce.weight'][:num_mid, :C], sd[prefix + 'fc.reduce.bias'][:num_mid]))
+    y = h_sigmoid(F.conv2d(y, sd[prefix + 'fc.expand.weight'][:C, :num_mid], sd[prefix + 'fc.expand.bias'][:C]))
+    return x * y
+
+
+def dynamic_linear(x, weight, bias, out_features):
+    """DynamicLinear.forward — dynamic_op.py:128-136"""
+    return F.linear(x, weight[:out_features, :x.shape[1]], bias[:out_features] if bias is not None else None)
+
+
+def dynamic_mbconv(x, sd, prefix, ks, expand, out_channel, ks_set, stride=1, act_func='relu6', use_se=False,
+                   training=False, momentum=0.1, eps=1e-5, transform_on=True):
+    """DynamicMBConvLayer.forward in its general form — dynamic_layers.py:14-84: sliced expand -> BN -> act ->
+    elastic depthwise with stride (same padding ks // 2, dynamic_op.py:73-84) -> BN -> act [-> DynamicSE] -> sliced
+    project to `out_channel` -> BN.  No residual (MobileInvertedResidualBlock adds it only when shapes agree)."""
+    cin = x.shape[1]
+    mid = make_divisible(round(cin * expand), 8)
+    h = x
+    if (prefix + 'inverted_bottleneck.conv.conv.weight') in sd:
+        h = sliced_conv(x, sd[prefix + 'inverted_bottleneck.conv.conv.weight'], mid)
+        h = apply_act(batch_norm(h, sd, prefix + 'inverted_bottleneck.bn.bn.', training, momentum, eps), act_func)
+    else:
+        mid = cin
+    mats = {k.split('.')[-1]: v for k, v in sd.items()
+            if k.startswith(prefix + 'depth_conv.conv.') and k.endswith('_matrix')}
+    filt = active_filter(sd[prefix + 'depth_conv.conv.conv.weight'], mats, ks_set, mid, ks, transform_on)
+    h = F.conv2d(h, filt, None, stride, ks // 2, 1, mid)
+    h = apply_act(batch_norm(h, sd, prefix + 'depth_conv.bn.bn.', training, momentum, eps), act_func)
+    if use_se:
+        h = dynamic_se(h, sd, prefix + 'depth_conv.se.')
+    h = sliced_conv(h, sd[prefix + 'point_linear.conv.conv.weight'], out_channel)
+    return batch_norm(h, sd, prefix + 'point_linear.bn.bn.', training, momentum, eps)
+
+
+# ---------------------------------------------------------------------------------------------
 # supernets: topology + sub-network bookkeeping (ofa_mbs4.py:20-178,263-370; ofa_mbx4.py:20-254,345-453)
 # ---------------------------------------------------------------------------------------------
 
