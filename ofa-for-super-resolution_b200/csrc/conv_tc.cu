@@ -433,7 +433,40 @@ bool conv_tc_supported(const OfaConvArgs* a) {
   return true;
 }
 
-int launch_conv_tc(const OfaConvArgs* a, cudaStream_t st) {
+// A 1x1 conv has no spatial structure: when the image edges do not fill the 16 x 16 pixel tiles (the 24 x 24 LR
+// training patches use 56 % of 2 x 2 tiles each), the dense NHWC tensors are re-viewed as ONE image of P / 16 rows
+// by 16 pixels, which tiles exactly.
+static bool flatten_pointwise(const OfaConvArgs* a, OfaConvArgs* flat) {
+  if (a->ks != 1 || a->store != OFA_STORE_PLAIN) return false;
+  if (a->x.h % TILE_H == 0 && a->x.w % TILE_W == 0) return false;
+  const long long P = (long long)a->x.n * a->x.h * a->x.w;
+  if (P % TILE_W != 0 || P / TILE_W >= (1ll << 31)) return false;
+  if (!is_nhwc_dense(&a->x) || !is_nhwc_dense(&a->y)) return false;
+  if (a->epi.residual && !is_nhwc_dense(a->epi.residual)) return false;
+  *flat = *a;
+  auto reshape = [&](OfaTensor4& t) {
+    t.n = 1; t.h = (int32_t)(P / TILE_W); t.w = TILE_W;
+    t.sc = 1; t.sw = t.c; t.sh = (int64_t)TILE_W * t.c; t.sn = P * t.c;
+  };
+  reshape(flat->x);
+  reshape(flat->y);
+  return true;
+}
+
+int launch_conv_tc(const OfaConvArgs* a_in, cudaStream_t st) {
+  OfaConvArgs a_flat;
+  OfaTensor4 res_flat;
+  const OfaConvArgs* a = a_in;
+  if (flatten_pointwise(a_in, &a_flat)) {
+    if (a_in->epi.residual) {
+      res_flat = *a_in->epi.residual;
+      res_flat.n = 1; res_flat.h = a_flat.x.h; res_flat.w = TILE_W;
+      res_flat.sc = 1; res_flat.sw = res_flat.c; res_flat.sh = (int64_t)TILE_W * res_flat.c;
+      res_flat.sn = (int64_t)a_flat.x.h * TILE_W * res_flat.c;
+      a_flat.epi.residual = &res_flat;
+    }
+    a = &a_flat;
+  }
   ConvTcParams p;
   memset(&p, 0, sizeof(p));
   p.N = a->x.n; p.H = a->x.h; p.W = a->x.w;
