@@ -20,6 +20,7 @@ ap.add_argument('--steps', type=int, default=5)
 ap.add_argument('--max-subnet', dest='max', action='store_true', help='max subnet instead of sampled ones')
 ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
 ap.add_argument('--verbose', action='store_true')
+ap.add_argument('--weak', action='store_true', help='weak scaling: --batch patches PER GPU (default: the batch is split over the ranks)')
 ap.add_argument('--graph', action='store_true', help='capture the whole step (fwd + bwd + Adam) of the fixed max subnet in a CUDA graph')
 a = ap.parse_args()
 rank = int(os.environ.get('RANK', '0')); world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -36,7 +37,7 @@ net = OFAMobileNetS4(**{k: list(v) for k, v in cfg.items()})
 spec = O.SuperNetSpec('s4', cfg['ks_list'], cfg['expand_ratio_list'], cfg['depth_list'], [1, 2])
 net.load_state_dict(O.synth_state_dict(spec.param_shapes(), 7))
 net = net.to(dev).train()
-per_rank = a.batch // world                      # batch-sharded data parallelism (strong scaling of one step)
+per_rank = a.batch if a.weak else a.batch // world     # batch-sharded data parallelism (default: strong scaling of one step)
 lr_img = torch.rand(per_rank, 3, 24, 24, device=dev)
 hr_img = torch.rand(per_rank, 3, 96, 96, device=dev)
 from ofa_b200 import optim
@@ -73,17 +74,25 @@ for i in range(2):
     step(i)
 torch.cuda.synchronize()
 if a.graph:
-    assert a.max and world == 1, '--graph captures a fixed sub-network on one GPU'
+    # whole-step capture (forward, backward, gradient all-reduce, fused Adam) of a FIXED sub-network -- the regime of
+    # train_teacher_net_sr_simple.py (max network only); sampled sub-networks change the launch sequence every step
+    assert a.max and world == 1, '--graph captures a fixed sub-network on one GPU (capturing the NCCL exchange hung on 2 GPUs)'
+
+    def step_body():
+        torch.nn.functional.mse_loss(net(lr_img), hr_img).backward()
+        if reducer is not None:
+            reducer.reduce()
+        opt.step()
     net.zero_grad(set_to_none=True)
     s = torch.cuda.Stream()
     s.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(s):
-        step_body = lambda: (torch.nn.functional.mse_loss(net(lr_img), hr_img).backward(), opt.step())
         step_body()
     torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
     net.zero_grad(set_to_none=True)
     graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph):
+    with torch.cuda.graph(graph, capture_error_mode='thread_local'):
         step_body()
     step = lambda i: graph.replay()
 B.launch_count_reset()
@@ -104,6 +113,6 @@ if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dt = float(t.item())
 if rank == 0:
-    print('%d GPU(s)' % world, a.dtype, 'train step: %.2f ms  %.1f patches/s  (%d library launches/step/rank)' % (dt * 1e3, a.batch / dt, B.launch_count() // a.steps))
+    print('%d GPU(s)' % world, a.dtype, 'train step: %.2f ms  %.1f patches/s  (%d library launches/step/rank)' % (dt * 1e3, per_rank * world / dt, B.launch_count() // a.steps))
 if world > 1:
     dist.destroy_process_group()
