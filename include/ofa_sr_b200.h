@@ -160,13 +160,15 @@ int ofa_pack_weight_16(const float* w, int64_t w_so, int64_t w_si, int64_t w_sh,
 /* ---------------------------------------------------------------------------------------------
  * (a5) DynamicBatchNorm2d.bn_forward in TRAINING mode — dynamic_op.py:148-167
  *   stats : per-channel batch mean and BIASED variance over N*H*W (what F.batch_norm normalises with)
- *   update: running = (1-momentum)*running + momentum*{mean, var * P/(P-1)} on the slice [:C]
+ *   update: running = (1-momentum)*running + momentum*{mean, var * P/(P-1)} on the slice [:C]; when
+ *           num_batches_tracked (DEVICE int64, may be NULL) is given it is incremented in the same launch
+ *           (`bn.num_batches_tracked += 1`, dynamic_op.py:156)
  *   apply : y = act(gamma*(x-mean)*rsqrt(var+eps)+beta) is ofa_affine_act with mean/var = batch stats
  * ------------------------------------------------------------------------------------------- */
 int ofa_bn_stats(const OfaTensor4* x, float* mean, float* var_biased, void* stream);
 int ofa_bn_update_running(const float* mean, const float* var_biased, int64_t count,
                           float* running_mean, float* running_var, float momentum, int32_t C,
-                          void* stream);
+                          int64_t* num_batches_tracked, void* stream);
 /* (a5 eval, a6, a8, a10, a11) stand-alone per-channel affine + activation (+ residual) with an
  * optional PixelShuffle / PixelUnshuffle store:  y = store(act(affine(x))) + res */
 int ofa_affine_act(const OfaTensor4* x, const OfaTensor4* y, const OfaEpilogue* epi, int32_t store,

@@ -224,11 +224,12 @@ int ofa_bn_stats(const OfaTensor4* x, float* mean, float* var, void* stream) {
 }
 
 int ofa_bn_update_running(const float* mean, const float* var, int64_t count, float* rm, float* rv,
-                          float momentum, int32_t C, void* stream) {
+                          float momentum, int32_t C, int64_t* num_batches_tracked, void* stream) {
   int rc = require_device();
   if (rc) return rc;
   OFA_REQUIRE(mean && var && rm && rv, "ofa_bn_update_running: null pointer");
-  return launch_bn_update_running(mean, var, count, rm, rv, momentum, C, (cudaStream_t)stream);
+  return launch_bn_update_running(mean, var, count, rm, rv, momentum, C,
+                                  reinterpret_cast<long long*>(num_batches_tracked), (cudaStream_t)stream);
 }
 
 int ofa_affine_act(const OfaTensor4* x, const OfaTensor4* y, const OfaEpilogue* epi, int32_t store, void* stream) {

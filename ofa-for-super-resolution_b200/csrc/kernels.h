@@ -18,7 +18,7 @@ int launch_pack_weight(const float* w, long long w_so, long long w_si, long long
 int launch_affine_act(const TV& x, const TV& y, const Epi& epi, int store, cudaStream_t st);
 int launch_bn_stats(const TV& x, float* mean, float* var, cudaStream_t st);
 int launch_bn_update_running(const float* mean, const float* var, long long count, float* rm, float* rv,
-                             float momentum, int C, cudaStream_t st);
+                             float momentum, int C, long long* num_batches_tracked, cudaStream_t st);
 int launch_bn_bwd_reduce(const TV& x, const TV& dy, const float* gamma, const float* beta,
                          const float* mean, const float* var, float eps, int act, float* sum_dz,
                          float* sum_dz_xhat, cudaStream_t st);

@@ -732,18 +732,19 @@ int launch_bn_stats(const TV& x, float* mean, float* var, cudaStream_t st) {
 
 __global__ void bn_update_running_kernel(const float* __restrict__ mean, const float* __restrict__ var,
                                          float unbias, float* __restrict__ rm, float* __restrict__ rv,
-                                         float momentum, int C) {
+                                         float momentum, int C, long long* __restrict__ num_batches_tracked) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;   // nn.BatchNorm2d's counter, bumped in the same launch
   if (c >= C) return;
   rm[c] = (1.f - momentum) * rm[c] + momentum * mean[c];
   rv[c] = (1.f - momentum) * rv[c] + momentum * (var[c] * unbias);
 }
 
 int launch_bn_update_running(const float* mean, const float* var, long long count, float* rm, float* rv,
-                             float momentum, int C, cudaStream_t st) {
+                             float momentum, int C, long long* num_batches_tracked, cudaStream_t st) {
   if (C == 0) return OFA_OK;
   float unbias = count > 1 ? (float)((double)count / (double)(count - 1)) : 1.f;
-  bn_update_running_kernel<<<(C + 127) / 128, 128, 0, st>>>(mean, var, unbias, rm, rv, momentum, C);
+  bn_update_running_kernel<<<(C + 127) / 128, 128, 0, st>>>(mean, var, unbias, rm, rv, momentum, C, num_batches_tracked);
   return check_launch("bn_update_running_kernel");
 }
 

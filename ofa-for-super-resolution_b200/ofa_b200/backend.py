@@ -78,7 +78,7 @@ SYMBOLS = {
                                      c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     'ofa_bn_stats': (c_int32, [_T4, c_void_p, c_void_p, c_void_p]),
     'ofa_bn_update_running': (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_float, c_int32,
-                                        c_void_p]),
+                                        c_void_p, c_void_p]),
     'ofa_affine_act': (c_int32, [_T4, _T4, _EP, c_int32, c_void_p]),
     'ofa_mbconv_workspace_bytes': (c_int64, [c_int32] * 6),
     'ofa_mbconv_fwd': (c_int32, [POINTER(OfaMBConvArgs), c_int32, c_void_p]),
