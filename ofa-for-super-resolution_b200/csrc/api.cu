@@ -69,7 +69,7 @@ static int same_shape(const OfaTensor4* a, const OfaTensor4* b, const char* what
 
 static int check_epi(const OfaEpilogue* e, const OfaTensor4* y) {
   if (!e) return OFA_OK;
-  OFA_REQUIRE(e->act >= OFA_ACT_NONE && e->act <= OFA_ACT_HSIGMOID, "bad activation code %d", e->act);
+  OFA_REQUIRE(e->act >= OFA_ACT_NONE && e->act <= OFA_ACT_RELU, "bad activation code %d", e->act);
   if (e->residual) {
     int rc = check_tensor(e->residual, "residual");
     if (rc) return rc;

@@ -10,6 +10,13 @@
 
 namespace ofa {
 
+// the epilogue activations plus the squeeze-and-excite gate; h-sigmoid lives here only, so the hot kernels' epilogue
+// switch (apply_act in ofa_common.cuh) stays at three cases
+__device__ __forceinline__ float apply_act_gate(float v, int act) {
+  if (act == OFA_ACT_HSIGMOID) return fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);
+  return apply_act(v, act);
+}
+
 // ---- sliced linear: Y[n, o] = act(b[o] + sum_i X[n, i] * W[o * ldw + i]) -------------------------------------
 // one warp per output element (the layers are [batch, <= 1280] x [<= 1280]: latency-sized, not bandwidth-sized)
 __global__ void linear_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ w,
@@ -24,7 +31,7 @@ __global__ void linear_fwd_kernel(const float* __restrict__ x, long long ldx, co
   for (int i = lane; i < in; i += 32) acc = fmaf(xr[i], wr[i], acc);
 #pragma unroll
   for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
-  if (lane == 0) y[(size_t)n * ldy + o] = apply_act(acc + (bias ? bias[o] : 0.f), act);
+  if (lane == 0) y[(size_t)n * ldy + o] = apply_act_gate(acc + (bias ? bias[o] : 0.f), act);
 }
 
 // dX[n, i] = sum_o dZ[n, o] * W[o * ldw + i]: thread per (n, i), coalesced over i

@@ -151,7 +151,6 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     case OFA_ACT_RELU6: return fminf(fmaxf(v, 0.f), 6.f);
     case OFA_ACT_RELU: return fmaxf(v, 0.f);
     case OFA_ACT_HSWISH: return v * fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);
-    case OFA_ACT_HSIGMOID: return fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);
     default: return v;
   }
 }
@@ -164,7 +163,6 @@ __device__ __forceinline__ float act_grad(float z, int act) {
       if (z <= -3.f) return 0.f;
       if (z >= 3.f) return 1.f;
       return (2.f * z + 3.f) * (1.f / 6.f);
-    case OFA_ACT_HSIGMOID: return (z > -3.f && z < 3.f) ? (1.f / 6.f) : 0.f;
     default: return 1.f;
   }
 }
