@@ -95,6 +95,7 @@ class FlatGradAllReduce:
         self.tail_numel = sum(p.numel() for p in self.tail)
         dev = self.params[0].device if self.params else torch.device('cpu')
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.views = [self.flat[off:off + p.numel()].view(p.shape) for p, off in zip(self.params, self.offsets)]
         self.n_buckets = n_buckets
         self._tail_handles = None
 
@@ -104,12 +105,18 @@ class FlatGradAllReduce:
         return [(cuts[i], cuts[i + 1]) for i in range(self.n_buckets) if cuts[i + 1] > cuts[i]]
 
     def _pack(self, first, last):
-        for p, off in zip(self.params[first:last], self.offsets[first:last]):
-            seg = self.flat[off:off + p.numel()]
-            if p.grad is not None:
-                seg.copy_(p.grad.reshape(-1))
-            else:
-                seg.zero_()
+        """Gradients of params[first:last] -> their slots of the flat buffer: one zero fill of the segment (inactive
+        blocks contribute zeros) and ONE multi-tensor copy of the gradients that exist (a per-parameter copy loop
+        costs ~10 us of host time per parameter: more than the whole all-reduce)."""
+        if last <= first:
+            return
+        lo = self.offsets[first]
+        hi = self.offsets[last - 1] + self.params[last - 1].numel()
+        self.flat[lo:hi].zero_()
+        dst = [v for p, v in zip(self.params[first:last], self.views[first:last]) if p.grad is not None]
+        src = [p.grad for p in self.params[first:last] if p.grad is not None]
+        if dst:
+            torch._foreach_copy_(dst, src)
 
     def _launch(self, lo, hi):
         import torch.distributed as dist
@@ -143,9 +150,10 @@ class FlatGradAllReduce:
         self.flat.div_(world)
         # every rank sampled the same sub-network (identical `random` seeds), so a parameter without a gradient has
         # none on any rank: it stays None and the optimizer skips it, exactly as in the single-GPU reference
-        for p, off in zip(self.params, self.offsets):
-            if p.grad is not None:
-                p.grad.copy_(self.flat[off:off + p.numel()].view_as(p))
+        dst = [p.grad for p in self.params if p.grad is not None]
+        src = [v for p, v in zip(self.params, self.views) if p.grad is not None]
+        if dst:
+            torch._foreach_copy_(dst, src)
 
 
 def s4_tail_parameters(net):
