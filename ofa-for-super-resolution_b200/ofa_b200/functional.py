@@ -475,8 +475,8 @@ class BnActFn(torch.autograd.Function):
         st = _stream(x)
         tx = B.t4(x)
         if training:
-            mean = torch.empty(c, dtype=torch.float32, device=x.device)
-            var = torch.empty(c, dtype=torch.float32, device=x.device)
+            stats = torch.empty((2, c), dtype=torch.float32, device=x.device)
+            mean, var = stats[0], stats[1]
             B.check(L.ofa_bn_stats(byref(tx), mean.data_ptr(), var.data_ptr(), st))
             if running_mean is not None and momentum is not None and momentum != 0.0:
                 B.check(L.ofa_bn_update_running(mean.data_ptr(), var.data_ptr(), n * h * w,
