@@ -977,3 +977,78 @@ def test_bad_arguments_are_reported(dev):
     assert rc == 1 and b'kernel size' in B.lib().ofa_last_error()
     with pytest.raises(RuntimeError):
         B.check(rc)
+
+
+# =================================================================================================
+# BASELINE.json's full sizes, through size-independent properties
+# =================================================================================================
+def test_full_size_frame_c2_window_vs_oracle_and_tiling(dev):
+    """configs[1] at its full size: S4 max sub-network, LR 960x540 -> 3840x2160, fp16 storage.
+    (1) Locality: in eval mode BatchNorm is a per-channel affine, so the SR output over a window depends only on the
+        LR pixels within the receptive field (< 64 LR pixels).  The oracle runs on a 224x224 LR crop (96x96 window +
+        64 halo) -- seconds on the CPU -- and must agree with that window of the full-frame CUDA result; one window
+        in the interior, one in the bottom-right corner (ragged depthwise tiles, zero padding).
+    (2) The frame computed as 2 x 4 tiles with halo equals the frame computed whole."""
+    import ofa_b200
+    from ofa_b200 import parallel as P
+    ofa_b200.set_compute_dtype(torch.float16)
+    net = _build_net('s4', [1, 2], 61, dev)
+    spec = O.SuperNetSpec('s4', FULL['ks_list'], FULL['expand_ratio_list'], FULL['depth_list'], [1, 2])
+    sd = O.synth_state_dict(spec.param_shapes(), 61)
+    sub = dict(ks=7, e=6, d=4, pixel_d=2)
+    net.set_active_subnet(**sub)
+    spec.set_active_subnet(**sub)
+    H, W, halo, win = 540, 960, P.S4_HALO_LR, 96
+    x = torch.from_numpy(np.random.RandomState(12).rand(1, 3, H, W).astype(np.float32))
+    with torch.no_grad():
+        y = net(x.to(dev))
+        assert tuple(y.shape) == (1, 3, 4 * H, 4 * W) and bool(torch.isfinite(y).all())
+        for (h0, w0) in ((208, 400), (H - win, W - win)):
+            i0, i1 = max(0, h0 - halo), min(H, h0 + win + halo)
+            j0, j1 = max(0, w0 - halo), min(W, w0 + win + halo)
+            ref = O.supernet_forward(x[:, :, i0:i1, j0:j1], sd, spec)
+            ref_win = ref[:, :, 4 * (h0 - i0):4 * (h0 - i0 + win), 4 * (w0 - j0):4 * (w0 - j0 + win)]
+            got_win = y[:, :, 4 * h0:4 * (h0 + win), 4 * w0:4 * (w0 + win)]
+            assert relerr(got_win, ref_win) < 1e-2, (h0, w0)
+        out = None
+        for rank in range(8):
+            out, mine = P.tiled_forward(net, x.to(dev), 2, 4, halo=halo, scale=4, rank=rank, world=8, out=out)
+            assert len(mine) == 1
+        assert relerr(out, y) < 2e-3
+
+
+def test_full_size_training_step_c3_bf16_vs_exact_path(dev):
+    """configs[2] at its full size: batch 64 of 96x96 HR patches (24x24 LR in), S4 max sub-network, one
+    forward + backward.  The bf16 tensor-core path against the exact fp32 CUDA-core path of the same library (which
+    the small-size tests pin to the oracle): loss within 2 %, whole-gradient cosine > 0.93 and norm within 5 %,
+    BatchNorm running statistics within 1 %; and the gradient is the same whether the batch is fed NCHW or
+    channels-last."""
+    import ofa_b200
+    rs = np.random.RandomState(21)
+    x = torch.from_numpy(rs.rand(64, 3, 24, 24).astype(np.float32)).to(dev)
+    tgt = torch.from_numpy(rs.rand(64, 3, 96, 96).astype(np.float32)).to(dev)
+    results = {}
+    try:
+        for mode, dt in (('fp32', torch.float32), ('bf16', torch.bfloat16), ('bf16_cl', torch.bfloat16)):
+            ofa_b200.set_train_dtype(dt)
+            net = _build_net('s4', [1, 2], 83, dev).train()
+            net.set_active_subnet(ks=7, e=6, d=4, pixel_d=2)
+            xin = x.contiguous(memory_format=torch.channels_last) if mode == 'bf16_cl' else x
+            loss = torch.nn.functional.mse_loss(net(xin), tgt)
+            loss.backward()
+            grads = torch.cat([p.grad.flatten().double() for p in net.parameters() if p.grad is not None])
+            stats = torch.cat([b.flatten().double() for n, b in net.named_buffers() if n.endswith('running_var')])
+            results[mode] = (float(loss.detach()), grads, stats)
+    finally:
+        ofa_b200.set_train_dtype(torch.float32)
+    l32, g32, s32 = results['fp32']
+    l16, g16, s16 = results['bf16']
+    assert abs(l16 - l32) <= 2e-2 * l32
+    assert g16.shape == g32.shape
+    cos = float(g16 @ g32) / (float(g16.norm()) * float(g32.norm()))
+    assert cos > 0.93, cos
+    assert abs(float(g16.norm()) - float(g32.norm())) <= 5e-2 * float(g32.norm())
+    assert float((s16 - s32).abs().max() / s32.abs().max()) < 1e-2
+    l_cl, g_cl, _ = results['bf16_cl']
+    assert abs(l_cl - l16) <= 1e-3 * l16
+    assert float(g_cl @ g16) / (float(g_cl.norm()) * float(g16.norm())) > 0.999
