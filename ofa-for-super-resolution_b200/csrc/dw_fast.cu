@@ -17,10 +17,15 @@
 namespace ofa {
 namespace {
 
-constexpr int TH = 8, TW = 32, CH = 64;
+constexpr int CH = 64;
+// tile = TH output rows (one warp each) x TW output columns; {8, 32} for frames, {12, 24} when the image divides into
+// such tiles (the 24 x 24 LR training patches: 2 tiles per image instead of 3 with a quarter of each wasted, and 24
+// instead of 16 resident warps per SM at the same two CTAs)
 // output pixels per pass: acc[RUN] + in[RUN + KS - 1] channel pairs must stay in registers (16 spilled at ks >= 5)
-template <int KS> struct DwRun { static constexpr int RUN = KS == 3 ? 16 : 8; };
-constexpr int THREADS = 256;
+template <int KS, int TW> struct DwRun {
+  static constexpr int RUN = (KS == 3 && TW % 16 == 0) ? 16 : 8;
+  static_assert(TW % RUN == 0, "passes must tile the row exactly: a partial pass would read past the halo row");
+};
 
 struct DwParams {
   int N, H, W, C;
@@ -35,7 +40,7 @@ struct DwParams {
   int tiles_w, tiles_h;
 };
 
-template <int KS>
+template <int KS, int TH, int TW>
 struct DwSmem {
   static constexpr int HALO_H = TH + KS - 1;
   static constexpr int HALO_W = TW + KS - 1;
@@ -53,10 +58,11 @@ __device__ __forceinline__ float2 bf2_unpack(uint32_t u) {
   return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
 }
 
-template <int KS>
-__global__ void __launch_bounds__(THREADS, 2)
+template <int KS, int TH, int TW>
+__global__ void __launch_bounds__(32 * TH, 2)
 dw_fast_kernel(const __grid_constant__ CUtensorMap tmap_x, const DwParams p) {
-  using L = DwSmem<KS>;
+  using L = DwSmem<KS, TH, TW>;
+  constexpr int THREADS = 32 * TH;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((128u - (ptx::smem_u32(smem_raw) & 127u)) & 127u);   // keeps the shared address space
   const uint32_t* tile = reinterpret_cast<const uint32_t*>(smem);           // [HALO_H][HALO_W][32] words
@@ -135,7 +141,7 @@ dw_fast_kernel(const __grid_constant__ CUtensorMap tmap_x, const DwParams p) {
   const float2 sc = make_float2(s_scale[2 * lane], s_scale[2 * lane + 1]);
   const float2 sh = make_float2(s_shift[2 * lane], s_shift[2 * lane + 1]);
   const float2* filt2 = reinterpret_cast<const float2*>(filt);  // [KS*KS][32]
-  constexpr int RUN = DwRun<KS>::RUN;
+  constexpr int RUN = DwRun<KS, TW>::RUN;
 #pragma unroll 1
   for (int x0 = 0; x0 < TW && w0 + x0 < p.W; x0 += RUN) {
     float2 acc[RUN];
@@ -169,13 +175,28 @@ dw_fast_kernel(const __grid_constant__ CUtensorMap tmap_x, const DwParams p) {
   }
 }
 
-template <int KS>
-int launch_ks(const CUtensorMap& tm, const DwParams& p, cudaStream_t st) {
-  using L = DwSmem<KS>;
-  OFA_CUDA(cudaFuncSetAttribute(dw_fast_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+template <int KS, int TH, int TW>
+int launch_tile(const OfaTensor4* x, DwParams& p, cudaStream_t st) {
+  using L = DwSmem<KS, TH, TW>;
+  p.tiles_w = (p.W + TW - 1) / TW;
+  p.tiles_h = (p.H + TH - 1) / TH;
+  CUtensorMap tm;
+  uint64_t dims[4] = {(uint64_t)p.C, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.N};
+  uint64_t strides[3] = {(uint64_t)p.C * 2, (uint64_t)p.W * p.C * 2, (uint64_t)p.H * p.W * p.C * 2};
+  uint32_t box[4] = {CH, (uint32_t)(TW + KS - 1), (uint32_t)(TH + KS - 1), 1};
+  int rc = encode_tmap(&tm, p.f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x->ptr, dims,
+                       strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+  if (rc) return rc;
+  OFA_CUDA(cudaFuncSetAttribute(dw_fast_kernel<KS, TH, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
   dim3 grid((unsigned)(p.N * p.tiles_w * p.tiles_h), p.C / CH);
-  dw_fast_kernel<KS><<<grid, THREADS, L::TOTAL, st>>>(tm, p);
+  dw_fast_kernel<KS, TH, TW><<<grid, 32 * TH, L::TOTAL, st>>>(tm, p);
   return check_launch("dw_fast_kernel");
+}
+
+template <int KS>
+int launch_ks(const OfaTensor4* x, DwParams& p, cudaStream_t st) {
+  if (p.H % 12 == 0 && p.W % 24 == 0 && (p.H % 8 != 0 || p.W % 32 != 0)) return launch_tile<KS, 12, 24>(x, p, st);
+  return launch_tile<KS, 8, 32>(x, p, st);
 }
 
 }  // namespace
@@ -206,19 +227,10 @@ int launch_dw_fast(const OfaTensor4* x, const OfaTensor4* y, const float* w7, in
   }
   p.y = reinterpret_cast<uint16_t*>(y->ptr);
   p.f16 = x->dtype == OFA_F16 ? 1 : 0;
-  p.tiles_w = (p.W + TW - 1) / TW;
-  p.tiles_h = (p.H + TH - 1) / TH;
-  CUtensorMap tm;
-  uint64_t dims[4] = {(uint64_t)p.C, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.N};
-  uint64_t strides[3] = {(uint64_t)p.C * 2, (uint64_t)p.W * p.C * 2, (uint64_t)p.H * p.W * p.C * 2};
-  uint32_t box[4] = {CH, (uint32_t)(TW + ks - 1), (uint32_t)(TH + ks - 1), 1};
-  int rc = encode_tmap(&tm, p.f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x->ptr, dims, strides, box,
-                       CU_TENSOR_MAP_SWIZZLE_NONE);
-  if (rc) return rc;
   switch (ks) {
-    case 3: return launch_ks<3>(tm, p, st);
-    case 5: return launch_ks<5>(tm, p, st);
-    default: return launch_ks<7>(tm, p, st);
+    case 3: return launch_ks<3>(x, p, st);
+    case 5: return launch_ks<5>(x, p, st);
+    default: return launch_ks<7>(x, p, st);
   }
 }
 

@@ -138,7 +138,7 @@ def test_fp16_net_on_ragged_width_uses_nhwc_kernels(dev):
 
 
 @pytest.mark.parametrize('ks', [3, 5, 7])
-@pytest.mark.parametrize('shape', [(1, 64, 8, 32), (2, 192, 19, 45), (1, 384, 40, 70)])
+@pytest.mark.parametrize('shape', [(1, 64, 8, 32), (2, 192, 19, 45), (1, 384, 40, 70), (2, 128, 24, 48), (3, 64, 12, 24)])
 def test_dw_fast_bf16(dev, ks, shape):
     from ofa_b200 import functional as OF, backend as B
     import ofa_b200
