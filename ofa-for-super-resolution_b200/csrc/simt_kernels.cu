@@ -370,6 +370,42 @@ __global__ void reorder_nhwc_kernel(TV x, TV y, int store, unsigned total) {
   }
 }
 
+// 16-bit dense NHWC PixelShuffle(2) as 16-byte loads and coalesced 4-byte stores: a thread takes the 8 input channels
+// 4c'+s of two neighbouring output channels c' = 2l, 2l+1 (one 16-byte vector) and writes one channel pair to each of
+// the four sub-pixels s = 2i+j; a warp's 32 words per sub-pixel are contiguous.  PixelUnshuffle(2) is the inverse:
+// four 4-byte loads (one per sub-pixel), one 16-byte store.
+__global__ void pixel_shuffle2_vec_kernel(const uint4* __restrict__ x, uint32_t* __restrict__ y, int H, int W, int q2,
+                                          unsigned total) {   // q2 = output channel pairs per pixel = C_in / 8
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned l = i % (unsigned)q2;
+    unsigned r = i / (unsigned)q2;                           // input pixel index (n, h, w)
+    const unsigned w = r % (unsigned)W; r /= (unsigned)W;
+    const unsigned h = r % (unsigned)H, n = r / (unsigned)H;
+    const uint4 v = x[i];
+    const size_t orow = ((size_t)n * 2 * H + 2 * h) * 2 * W + 2 * w;   // output pixel (2h, 2w)
+    uint32_t* o = y + orow * q2 + l;
+    o[0] = __byte_perm(v.x, v.z, 0x5410);                                 // s = 0: (c'0 s0, c'1 s0)
+    o[q2] = __byte_perm(v.x, v.z, 0x7632);                                // s = 1 -> pixel (2h, 2w + 1)
+    o[(size_t)2 * W * q2] = __byte_perm(v.y, v.w, 0x5410);                // s = 2 -> pixel (2h + 1, 2w)
+    o[(size_t)2 * W * q2 + q2] = __byte_perm(v.y, v.w, 0x7632);           // s = 3
+  }
+}
+
+__global__ void pixel_unshuffle2_vec_kernel(const uint32_t* __restrict__ x, uint4* __restrict__ y, int Ho, int Wo,
+                                            int c2, unsigned total) {   // c2 = input channel pairs per pixel
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned l = i % (unsigned)c2;
+    unsigned r = i / (unsigned)c2;                           // output pixel index (n, h', w')
+    const unsigned w = r % (unsigned)Wo; r /= (unsigned)Wo;
+    const unsigned h = r % (unsigned)Ho, n = r / (unsigned)Ho;
+    const size_t irow = ((size_t)n * 2 * Ho + 2 * h) * 2 * Wo + 2 * w;
+    const uint32_t* p = x + irow * c2 + l;
+    const uint32_t s0 = p[0], s1 = p[c2], s2 = p[(size_t)2 * Wo * c2], s3 = p[(size_t)2 * Wo * c2 + c2];
+    y[i] = make_uint4(__byte_perm(s0, s1, 0x5410), __byte_perm(s2, s3, 0x5410), __byte_perm(s0, s1, 0x7632),
+                      __byte_perm(s2, s3, 0x7632));
+  }
+}
+
 __global__ void affine_act_kernel(TV x, TV y, Epi epi, int store, int c_is_inner) {
   const long long total = (long long)x.n * x.c * x.h * x.w;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -419,8 +455,27 @@ int launch_affine_act(const TV& x, const TV& y, const Epi& epi, int store, cudaS
     affine_act_nhwc_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, y, epi, (unsigned)(total / 2), (unsigned)(x.c / 2));
     return check_launch("affine_act_nhwc_kernel");
   }
-  if (store != OFA_STORE_PLAIN && total < (1ll << 31) && tv_nhwc_dense(x) && tv_nhwc_dense(y) && !epi.res.ptr &&
-      !epi.gamma && !epi.beta && !epi.mean && !epi.var && epi.act == OFA_ACT_NONE) {
+  const bool pure_reorder = store != OFA_STORE_PLAIN && total < (1ll << 31) && tv_nhwc_dense(x) && tv_nhwc_dense(y) &&
+                            !epi.res.ptr && !epi.gamma && !epi.beta && !epi.mean && !epi.var && epi.act == OFA_ACT_NONE;
+  if (pure_reorder && x.dtype != OFA_F32 && y.dtype == x.dtype && x.c % 8 == 0 && store == OFA_STORE_PIXELSHUFFLE2 &&
+      reinterpret_cast<uintptr_t>(x.ptr) % 16 == 0 && reinterpret_cast<uintptr_t>(y.ptr) % 4 == 0) {
+    const unsigned nv = (unsigned)(total / 8);
+    long long nb = (nv + 255) / 256;
+    if (nb > (long long)sm_count() * 8) nb = (long long)sm_count() * 8;
+    pixel_shuffle2_vec_kernel<<<(unsigned)nb, 256, 0, st>>>(reinterpret_cast<const uint4*>(x.ptr),
+                                                            reinterpret_cast<uint32_t*>(y.ptr), x.h, x.w, x.c / 8, nv);
+    return check_launch("pixel_shuffle2_vec_kernel");
+  }
+  if (pure_reorder && x.dtype != OFA_F32 && y.dtype == x.dtype && x.c % 2 == 0 && store == OFA_STORE_PIXELUNSHUFFLE2 &&
+      reinterpret_cast<uintptr_t>(y.ptr) % 16 == 0 && reinterpret_cast<uintptr_t>(x.ptr) % 4 == 0) {
+    const unsigned nv = (unsigned)(total / 8);
+    long long nb = (nv + 255) / 256;
+    if (nb > (long long)sm_count() * 8) nb = (long long)sm_count() * 8;
+    pixel_unshuffle2_vec_kernel<<<(unsigned)nb, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(x.ptr),
+                                                              reinterpret_cast<uint4*>(y.ptr), y.h, y.w, x.c / 2, nv);
+    return check_launch("pixel_unshuffle2_vec_kernel");
+  }
+  if (pure_reorder) {
     reorder_nhwc_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, y, store, (unsigned)total);
     return check_launch("reorder_nhwc_kernel");
   }
@@ -1309,60 +1364,94 @@ int launch_dw_bwd_filter(const TV& x, const TV& dy, int ks, float* dw, cudaStrea
 
 // chain rule through the filter transform (dynamic_op.py:46-71), one thread per channel, atomics
 // for the shared matrices.
-__global__ void active_filter_bwd_kernel(const float* __restrict__ w7, int kmax,
-                                         const float* __restrict__ m75, const float* __restrict__ m53,
-                                         int transform_on, int ks, int C,
-                                         const float* __restrict__ dwa, float* __restrict__ dw7,
-                                         float* __restrict__ dm75, float* __restrict__ dm53) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const float* w = w7 + (size_t)c * kmax * kmax;
-  float* dw = dw7 + (size_t)c * kmax * kmax;
-  const float* g = dwa + (size_t)c * ks * ks;
-  if (!transform_on || ks == kmax) {
-    const int s = kmax / 2 - ks / 2;
-    for (int y = 0; y < ks; ++y)
-      for (int x = 0; x < ks; ++x) dw[(y + s) * kmax + (x + s)] += g[y * ks + x];
-    return;
-  }
-  // forward recompute of the intermediate 5x5 (when the 7->5 step exists)
-  float k5[25], g5[25];
-  const float* cur = w;
-  int kc = kmax;
+// no transform in play (ks == kmax, or KERNEL_TRANSFORM_MODE off): the gradient lands on the centre crop; one thread
+// per (channel, tap) so that consecutive threads touch consecutive addresses
+__global__ void active_filter_bwd_crop_kernel(int kmax, int ks, int C, const float* __restrict__ dwa,
+                                              float* __restrict__ dw7) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C * ks * ks) return;
+  const int c = i / (ks * ks), t = i - c * ks * ks;
+  const int y = t / ks, x = t - y * ks, s = kmax / 2 - ks / 2;
+  dw7[(size_t)c * kmax * kmax + (y + s) * kmax + (x + s)] += dwa[i];
+}
+
+// transform path: a block of 64 threads owns 64 channels (thread = channel).  The per-channel chain (recompute the
+// 5x5, push the gradient back through the 5->3 and 7->5 matrices) is private to the thread; the gradients of the
+// SHARED matrices are sums over channels, reduced inside the block through shared memory -- each thread sums a few
+// matrix entries over the block's 64 channels -- so a matrix entry receives one atomicAdd per block instead of one
+// per channel (240 k atomics on 625 addresses took ~20 us per layer).
+constexpr int AFB_CH = 64;
+__global__ void __launch_bounds__(AFB_CH)
+active_filter_bwd_kernel(const float* __restrict__ w7, int kmax, const float* __restrict__ m75,
+                         const float* __restrict__ m53, int ks, int C, const float* __restrict__ dwa,
+                         float* __restrict__ dw7, float* __restrict__ dm75, float* __restrict__ dm53) {
+  __shared__ float s_src[25][AFB_CH + 1];     // the values the current matrix multiplied (per channel)
+  __shared__ float s_g[25][AFB_CH + 1];       // the gradient of that matrix product's output (per channel)
+  const int c = blockIdx.x * AFB_CH + threadIdx.x;
+  const bool ok = c < C;
+  const int nch = min(AFB_CH, C - blockIdx.x * AFB_CH);
+  const float* w = w7 + (size_t)(ok ? c : 0) * kmax * kmax;
+  float* dw = dw7 + (size_t)(ok ? c : 0) * kmax * kmax;
+  const float* g = dwa + (size_t)(ok ? c : 0) * ks * ks;
   const bool step75 = (kmax == 7 && m75 != nullptr);
-  if (step75) {
+  // forward recompute of the intermediate 5x5 (when the 7->5 step exists); cur = what the ->3 step reads
+  float k5[25], gcur[25];
+  const int kc = step75 ? 5 : kmax;           // kc in {5, 7}; with kc == 7 only ks == 3 reaches this kernel (7->3)
+  if (step75 && ok) {
     for (int j = 0; j < 25; ++j) {
       float acc = 0.f;
       for (int i = 0; i < 25; ++i) acc = fmaf(w[(i / 5 + 1) * 7 + (i % 5 + 1)], m75[j * 25 + i], acc);
       k5[j] = acc;
     }
-    cur = k5;
-    kc = 5;
   }
-  // gradient w.r.t. `cur` (size kc*kc)
-  float gcur[49];
-  for (int j = 0; j < kc * kc; ++j) gcur[j] = 0.f;
-  if (ks == kc) {
-    for (int j = 0; j < kc * kc; ++j) gcur[j] = g[j];
-  } else {
+  for (int j = 0; j < 25; ++j) gcur[j] = 0.f;
+  float g7[49];                               // gradient w.r.t. the 7x7 when the ->3 step reads it directly
+  if (!step75) for (int j = 0; j < 49; ++j) g7[j] = 0.f;
+  if (ks == kc) {                             // ks == 5 through the 7->5 matrix
+    if (ok) for (int j = 0; j < 25; ++j) gcur[j] = g[j];
+  } else {                                    // ks == 3: through the ->3 matrix
     const int s = kc / 2 - 1;
-    for (int j = 0; j < 9; ++j)
-      for (int i = 0; i < 9; ++i) {
-        int src = (i / 3 + s) * kc + (i % 3 + s);
-        atomicAdd(&dm53[j * 9 + i], g[j] * cur[src]);
-        gcur[src] = fmaf(g[j], m53[j * 9 + i], gcur[src]);
-      }
+    for (int j = 0; j < 9; ++j) {
+      const int src = (j / 3 + s) * kc + (j % 3 + s);
+      s_src[j][threadIdx.x] = ok ? (step75 ? k5[src] : w[src]) : 0.f;
+      s_g[j][threadIdx.x] = ok ? g[j] : 0.f;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 81; e += AFB_CH) {        // dm53[j][i] = sum_c g[c][j] * cur[c][src(i)]
+      const int j = e / 9, i = e - j * 9;
+      float acc = 0.f;
+      for (int q = 0; q < nch; ++q) acc = fmaf(s_g[j][q], s_src[i][q], acc);
+      atomicAdd(&dm53[e], acc);
+    }
+    __syncthreads();
+    if (ok)
+      for (int j = 0; j < 9; ++j)
+        for (int i = 0; i < 9; ++i) {
+          const int src = (i / 3 + s) * kc + (i % 3 + s);
+          const float v = g[j] * m53[j * 9 + i];
+          if (step75) gcur[src] += v; else g7[src] += v;
+        }
   }
   if (step75) {
-    for (int j = 0; j < 25; ++j) g5[j] = gcur[j];
-    for (int j = 0; j < 25; ++j)
+    for (int j = 0; j < 25; ++j) {
+      s_src[j][threadIdx.x] = ok ? w[(j / 5 + 1) * 7 + (j % 5 + 1)] : 0.f;
+      s_g[j][threadIdx.x] = ok ? gcur[j] : 0.f;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 625; e += AFB_CH) {       // dm75[j][i] = sum_c g5[c][j] * w[c][crop(i)]
+      const int j = e / 25, i = e - j * 25;
+      float acc = 0.f;
+      for (int q = 0; q < nch; ++q) acc = fmaf(s_g[j][q], s_src[i][q], acc);
+      atomicAdd(&dm75[e], acc);
+    }
+    if (ok)
       for (int i = 0; i < 25; ++i) {
-        int src = (i / 5 + 1) * 7 + (i % 5 + 1);
-        atomicAdd(&dm75[j * 25 + i], g5[j] * w[src]);
-        dw[src] += g5[j] * m75[j * 25 + i];
+        float acc = 0.f;
+        for (int j = 0; j < 25; ++j) acc = fmaf(gcur[j], m75[j * 25 + i], acc);
+        dw[(i / 5 + 1) * 7 + (i % 5 + 1)] += acc;
       }
-  } else {
-    for (int j = 0; j < kc * kc; ++j) dw[j] += gcur[j];
+  } else if (ok) {
+    for (int j = 0; j < kc * kc; ++j) dw[j] += g7[j];
   }
 }
 
@@ -1370,8 +1459,13 @@ int launch_active_filter_bwd(const float* w7, int kmax, const float* m75, const 
                              int transform_on, int ks, int C, const float* dwa, float* dw7, float* dm75,
                              float* dm53, cudaStream_t st) {
   if (C == 0) return OFA_OK;
-  active_filter_bwd_kernel<<<(C + 63) / 64, 64, 0, st>>>(w7, kmax, m75, m53, transform_on, ks, C, dwa, dw7,
-                                                         dm75, dm53);
+  if (!transform_on || ks == kmax) {
+    const int total = C * ks * ks;
+    active_filter_bwd_crop_kernel<<<(total + 255) / 256, 256, 0, st>>>(kmax, ks, C, dwa, dw7);
+    return check_launch("active_filter_bwd_crop_kernel");
+  }
+  active_filter_bwd_kernel<<<(C + AFB_CH - 1) / AFB_CH, AFB_CH, 0, st>>>(w7, kmax, m75, m53, ks, C, dwa, dw7, dm75,
+                                                                       dm53);
   return check_launch("active_filter_bwd_kernel");
 }
 

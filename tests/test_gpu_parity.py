@@ -1052,3 +1052,19 @@ def test_full_size_training_step_c3_bf16_vs_exact_path(dev):
     l_cl, g_cl, _ = results['bf16_cl']
     assert abs(l_cl - l16) <= 1e-3 * l16
     assert float(g_cl @ g16) / (float(g_cl.norm()) * float(g16.norm())) > 0.999
+
+
+@pytest.mark.parametrize('dtype', [torch.bfloat16, torch.float16, torch.float32])
+@pytest.mark.parametrize('shape', [(2, 256, 5, 7), (1, 64, 12, 24), (3, 8, 3, 2), (1, 12, 4, 6)])
+def test_pixel_reorder_kernels_exact(dev, dtype, shape):
+    """(a10, a11) stand-alone PixelShuffle(2) / PixelUnshuffle(2) (the training path's reorder, incl. the 16-byte vector
+    kernels for 16-bit dense NHWC tensors): pure data movement, bit-exact against torch, and inverse of each other."""
+    from ofa_b200 import functional as OF, backend as B
+    n, c, h, w = shape
+    x = torch.randn(n, c, h, w, device=dev).to(dtype).contiguous(memory_format=torch.channels_last)
+    up = OF.ReorderFn.apply(x, B.STORE_PIXELSHUFFLE2)
+    assert torch.equal(up, torch.nn.functional.pixel_shuffle(x, 2))
+    assert torch.equal(OF.ReorderFn.apply(up, B.STORE_PIXELUNSHUFFLE2), x)
+    if h % 2 == 0 and w % 2 == 0:
+        down = OF.ReorderFn.apply(x, B.STORE_PIXELUNSHUFFLE2)
+        assert torch.equal(down, torch.nn.functional.pixel_unshuffle(x, 2))
