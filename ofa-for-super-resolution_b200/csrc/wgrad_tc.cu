@@ -191,6 +191,13 @@ int launch_wgrad_tc(const OfaTensor4* x, const OfaTensor4* dy, float* dw, long l
   WgradParams p;
   memset(&p, 0, sizeof(p));
   p.N = x->n; p.H = x->h; p.W = x->w; p.ks = ks;
+  if (ks == 1 && (p.H % WG_TH != 0 || p.W % WG_TW != 0)) {
+    // a 1x1 conv has no spatial structure and the pixels are only the reduction dimension: re-view the dense tensors
+    // as one image of P / 8 rows by 8 pixels, which the 16 x 8 pixel tiles cover exactly (24 x 24 patches: 6 tiles
+    // of which a quarter is padding -> 4.5)
+    const long long P = (long long)x->n * x->h * x->w;
+    if (P % WG_TW == 0 && P / WG_TW < (1ll << 31)) { p.N = 1; p.H = (int)(P / WG_TW); p.W = WG_TW; }
+  }
   p.f16 = x->dtype == OFA_F16 ? 1 : 0;
   p.swap = (cin == 64) ? 0 : 1;
   p.m_ch = p.swap ? cin : cout;
