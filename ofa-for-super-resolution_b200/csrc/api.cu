@@ -281,7 +281,8 @@ int ofa_mbconv_fwd(const OfaMBConvArgs* a, int32_t impl, void* stream) {
               a->mid_dtype);
 
   // ---- planar tcgen05 path: expand -> Toeplitz depthwise -> project around channel-planar intermediates
-  if (impl != OFA_IMPL_SIMT && impl != OFA_IMPL_NHWC && mbconv_planar_supported(a)) {
+  if (impl != OFA_IMPL_SIMT && impl != OFA_IMPL_NHWC && mbconv_planar_supported(a) &&
+      (impl == OFA_IMPL_FAST || mbconv_planar_preferred(a))) {
     const int f16 = (a->mid_dtype == OFA_BF16) ? 0 : 1;
     const int tf16 = a->x.dtype == OFA_F16 ? 1 : 0;
     const int HW = a->x.h * a->x.w;

@@ -59,6 +59,7 @@ int launch_wgrad_tc(const OfaTensor4* x, const OfaTensor4* dy, float* dw, long l
 
 // ---- mbconv_planar.cu : MBConv block on channel-planar 16-bit intermediates (tcgen05) ---------------
 bool mbconv_planar_supported(const OfaMBConvArgs* a);
+bool mbconv_planar_preferred(const OfaMBConvArgs* a);   // tile-fill heuristic of OFA_IMPL_AUTO
 int launch_pack_block_weights(const float* w_exp, long long e_so, long long e_si, const float* w_proj,
                               long long p_so, long long p_si, int cin, int mid, int cout, int mid_pad, int trunk_f16,
                               int f16, void* wexp_p, void* wproj_p, cudaStream_t st);

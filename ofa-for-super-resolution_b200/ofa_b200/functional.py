@@ -715,7 +715,8 @@ def mbconv_infer(x, w_exp, w_dw, m75, m53, w_proj, cin, mid, cout, ks, transform
     n, _, h, w = x.shape
     if x.numel() == 0:
         return B.new_nhwc(n, cout, h, w, x.dtype, x.device)
-    planar = planar_supported(x, cin, mid, cout) and _state['impl'] not in (B.IMPL_SIMT, B.IMPL_NHWC)
+    planar = (planar_supported(x, cin, mid, cout) and _state['impl'] not in (B.IMPL_SIMT, B.IMPL_NHWC)
+              and (_state['impl'] == B.IMPL_FAST or planar_preferred(x)))
     if _profiler is not None and planar:
         return _mbconv_planar_staged(x, w_exp, w_dw, m75, m53, w_proj, mid, ks, transform_on, act, bn_exp, bn_dw,
                                      bn_proj, add_residual)
@@ -753,6 +754,16 @@ def planar_supported(x, cin, mid, cout):
     """Shapes the planar tcgen05 MBConv path takes (mirrors mbconv_planar_supported in the library)."""
     return (x.dtype in (torch.bfloat16, torch.float16) and cin == 64 and cout == 64 and mid % 64 == 0 and 64 <= mid <= 384
             and x.shape[3] % 8 == 0)
+
+
+def planar_preferred(x):
+    """Tile-fill heuristic of IMPL_AUTO (mirrors mbconv_planar_preferred): planes that fill < 25 % of their 128 (64) x 112
+    depthwise tiles -- batches of small patches -- take the three NHWC kernels; IMPL_FAST forces the planar path."""
+    h, w = x.shape[2], x.shape[3]
+    tail = h % 128
+    rows = h // 128 * 128 + (0 if tail == 0 else 64 if tail <= 64 else 128)
+    cols = (w + 111) // 112 * 112
+    return 4 * h * w >= rows * cols
 
 
 def _mbconv_planar_staged(x, w_exp, w_dw, m75, m53, w_proj, mid, ks, transform_on, act, bn_exp, bn_dw, bn_proj,

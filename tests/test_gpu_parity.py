@@ -419,8 +419,9 @@ def test_mbconv_planar_shape_sweep_vs_oracle(dev):
     columns of tiles, H = 1, one 8-pixel row, batch > 1, sizes straddling the 128-row / 112-column / 256- and
     128-pixel tile edges — against the oracle block (fp32 CPU), fp16 storage."""
     import ofa_b200
-    from ofa_b200 import functional as OF
+    from ofa_b200 import functional as OF, backend as B
     ofa_b200.set_compute_dtype(torch.float16)
+    ofa_b200.set_impl(B.IMPL_FAST)       # force the planar path: IMPL_AUTO sends planes this small to the NHWC kernels
     layer = _block_layer(dev).eval()
     spec = O.SuperNetSpec('s4', FULL['ks_list'], FULL['expand_ratio_list'], FULL['depth_list'], [1])
     pre = 'blocks.0.mobile_inverted_conv.'
@@ -443,7 +444,8 @@ def test_mbconv_planar_shape_sweep_vs_oracle(dev):
 @pytest.mark.parametrize('dtype', [torch.bfloat16, torch.float16])
 def test_mbconv_planar_equals_nhwc_path(dev, dtype):
     """The planar path and the three NHWC kernels are two implementations of the same block
-    (ofa_mbconv_fwd picks by shape): they must agree to storage rounding, for every (ks, e)."""
+    (ofa_mbconv_fwd picks by shape: planes that fill < 25 % of the depthwise tiles go NHWC under IMPL_AUTO): they must
+    agree to storage rounding, for every (ks, e); and the AUTO choice follows the documented rule."""
     import ofa_b200
     from ofa_b200 import backend as B
     layer = _block_layer(dev).eval()
@@ -452,12 +454,16 @@ def test_mbconv_planar_equals_nhwc_path(dev, dtype):
         for e in (3, 4, 6):
             layer.active_kernel_size, layer.active_expand_ratio = ks, e
             with torch.no_grad():
-                ofa_b200.set_impl(B.IMPL_AUTO)
+                ofa_b200.set_impl(B.IMPL_FAST)        # planar even for this small plane (AUTO would pick NHWC)
                 y_planar = layer(x)
                 ofa_b200.set_impl(B.IMPL_NHWC)
                 y_nhwc = layer(x)
             ofa_b200.set_impl(B.IMPL_AUTO)
             assert y_planar.dtype == dtype and relerr(y_planar, y_nhwc) < (2 ** -6 if dtype == torch.bfloat16 else 2 ** -8)
+    from ofa_b200 import functional as OF
+    mk = lambda h, w: torch.empty(1, 64, h, w, dtype=dtype, device=dev).contiguous(memory_format=torch.channels_last)
+    assert not OF.planar_preferred(mk(24, 24)) and not OF.planar_preferred(mk(20, 24))
+    assert OF.planar_preferred(mk(48, 48)) and OF.planar_preferred(mk(96, 96)) and OF.planar_preferred(mk(540, 960))
 
 
 # =================================================================================================

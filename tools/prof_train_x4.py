@@ -1,0 +1,6 @@
+import sys, runpy, torch
+sys.argv = ['bench_train_x4.py', '--steps', '1']
+from torch.profiler import profile, ProfilerActivity
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    runpy.run_path('/root/repo/tools/bench_train_x4.py', run_name='__main__')
+print(prof.key_averages().table(sort_by='cuda_time_total', row_limit=22, max_name_column_width=60))
