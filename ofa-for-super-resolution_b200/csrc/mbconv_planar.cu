@@ -651,15 +651,19 @@ bool mbconv_planar_supported(const OfaMBConvArgs* a) {
   return true;
 }
 
-// The depthwise tiles are 128 (64 for a short tail) x 112 pixels of ONE plane: batches of small images (the 24 x 24 LR
-// patches of a training batch run through a teacher fill 8 % of a tile and took 1.07 ms per block instead of ~0.1)
-// are better served by the three NHWC kernels.  OFA_IMPL_AUTO asks this; OFA_IMPL_FAST forces the planar path.
+// OFA_IMPL_AUTO's choice between the planar path and the three NHWC kernels (OFA_IMPL_FAST forces planar).  The planar
+// depthwise works per channel PLANE: its Toeplitz filter matrices are rebuilt for every plane (~6 us, hidden behind the
+// previous plane's tiles only when a plane has several tiles) and its tiles are 128 (64 for a short tail) x 112
+// pixels.  Batches of small images therefore run far below the frame rates: 64 x 384 planes of 48 x 48 took 1.07 ms per
+// block against ~0.25 ms on the NHWC kernels, 24 x 24 planes likewise.  Rule: planes of at least 8192 pixels that fill
+// at least a quarter of their tiles.
 bool mbconv_planar_preferred(const OfaMBConvArgs* a) {
   const OfaTensor4& x = a->x;
   const int tail = x.h % DW_TH;
   const long long rows = (long long)(x.h / DW_TH) * DW_TH + (tail == 0 ? 0 : tail <= DW_TH / 2 ? DW_TH / 2 : DW_TH);
   const long long cols = (long long)((x.w + DW_TW - 1) / DW_TW) * DW_TW;
-  return 4ll * x.h * x.w >= rows * cols;
+  const long long area = (long long)x.h * x.w;
+  return area >= 8192 && 4 * area >= rows * cols;
 }
 
 static CUtensorMapDataType dt16(int f16) {

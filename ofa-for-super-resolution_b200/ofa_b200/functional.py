@@ -757,13 +757,14 @@ def planar_supported(x, cin, mid, cout):
 
 
 def planar_preferred(x):
-    """Tile-fill heuristic of IMPL_AUTO (mirrors mbconv_planar_preferred): planes that fill < 25 % of their 128 (64) x 112
-    depthwise tiles -- batches of small patches -- take the three NHWC kernels; IMPL_FAST forces the planar path."""
+    """IMPL_AUTO's choice (mirrors mbconv_planar_preferred): the planar depthwise rebuilds its filter matrices per channel
+    plane and works in 128 (64) x 112-pixel tiles, so planes under 8192 pixels or filling < 25 % of their tiles -- batches
+    of small patches -- take the three NHWC kernels; IMPL_FAST forces the planar path."""
     h, w = x.shape[2], x.shape[3]
     tail = h % 128
     rows = h // 128 * 128 + (0 if tail == 0 else 64 if tail <= 64 else 128)
     cols = (w + 111) // 112 * 112
-    return 4 * h * w >= rows * cols
+    return h * w >= 8192 and 4 * h * w >= rows * cols
 
 
 def _mbconv_planar_staged(x, w_exp, w_dw, m75, m53, w_proj, mid, ks, transform_on, act, bn_exp, bn_dw, bn_proj,

@@ -444,7 +444,7 @@ def test_mbconv_planar_shape_sweep_vs_oracle(dev):
 @pytest.mark.parametrize('dtype', [torch.bfloat16, torch.float16])
 def test_mbconv_planar_equals_nhwc_path(dev, dtype):
     """The planar path and the three NHWC kernels are two implementations of the same block
-    (ofa_mbconv_fwd picks by shape: planes that fill < 25 % of the depthwise tiles go NHWC under IMPL_AUTO): they must
+    (ofa_mbconv_fwd picks by shape: small planes go NHWC under IMPL_AUTO): they must
     agree to storage rounding, for every (ks, e); and the AUTO choice follows the documented rule."""
     import ofa_b200
     from ofa_b200 import backend as B
@@ -462,8 +462,8 @@ def test_mbconv_planar_equals_nhwc_path(dev, dtype):
             assert y_planar.dtype == dtype and relerr(y_planar, y_nhwc) < (2 ** -6 if dtype == torch.bfloat16 else 2 ** -8)
     from ofa_b200 import functional as OF
     mk = lambda h, w: torch.empty(1, 64, h, w, dtype=dtype, device=dev).contiguous(memory_format=torch.channels_last)
-    assert not OF.planar_preferred(mk(24, 24)) and not OF.planar_preferred(mk(20, 24))
-    assert OF.planar_preferred(mk(48, 48)) and OF.planar_preferred(mk(96, 96)) and OF.planar_preferred(mk(540, 960))
+    assert not OF.planar_preferred(mk(24, 24)) and not OF.planar_preferred(mk(48, 48)) and not OF.planar_preferred(mk(8, 2048))
+    assert OF.planar_preferred(mk(96, 96)) and OF.planar_preferred(mk(256, 256)) and OF.planar_preferred(mk(540, 960))
 
 
 # =================================================================================================
