@@ -24,6 +24,15 @@ from ... import backend as B
 __all__ = ['DynamicMBConvLayer', 'DynamicConvLayer', 'DynamicLinearLayer']
 
 
+def _has_hooks(*mods):
+    """True when a sub-module carries forward / backward hooks (then it is called as a module, not bypassed)."""
+    for m in mods:
+        if m is not None and (m._forward_hooks or m._forward_pre_hooks or m._backward_hooks or
+                              getattr(m, '_backward_pre_hooks', None)):
+            return True
+    return False
+
+
 class DynamicMBConvLayer(MyModule):
 
     def __init__(self, in_channel_list, out_channel_list, kernel_size_list=3, expand_ratio_list=6, stride=1,
@@ -110,6 +119,16 @@ class DynamicMBConvLayer(MyModule):
         mid = in_channel
         if self.inverted_bottleneck is not None:
             mid = self.inverted_bottleneck.conv.active_out_channel
+        if self.stride == 1 and not _has_hooks(self.inverted_bottleneck.conv if self.inverted_bottleneck is not None
+                                               else None, dwm, self.point_linear.conv):
+            # one autograd node per conv + BN + act layer (same library calls; the eager step is launch-rate-bound)
+            if self.inverted_bottleneck is not None:
+                h = OF.conv_bn_act(h, self.inverted_bottleneck.conv.conv.weight, in_channel, mid, 1, bn_ex, act)
+            h = OF.dw_bn_act(h, dwm.conv.weight, m75, m53, ks, transform_on, bn_dw, act)
+            if self.use_se:
+                h = self.depth_conv.se(h)
+            return OF.conv_bn_act(h, w_pl, mid, cout, 1, bn_pl, B.ACT_NONE, residual)
+        if self.inverted_bottleneck is not None:
             h = self.inverted_bottleneck.conv(h)
             h = DynamicBatchNorm2d.bn_forward(h, self.inverted_bottleneck.bn.bn, mid, act)
         h = dwm(h)

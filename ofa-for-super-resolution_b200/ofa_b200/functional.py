@@ -107,17 +107,44 @@ def dw_active_filter(w7, m75, m53, transform_on, ks, C):
     return out
 
 
+def _dw_fwd_impl(x, w7, m75, m53, ks, transform_on):
+    n, c, h, w = x.shape
+    y = B.new_nhwc(n, c, h, w, x.dtype, x.device)
+    p75, p53 = _transform_ptrs(m75, m53)
+    tx, ty = B.t4(x), B.t4(y)
+    B.check(B.lib().ofa_dw_fwd(byref(tx), byref(ty), B.fptr(w7), w7.shape[-1], p75, p53,
+                               int(bool(transform_on)), ks, None, _state['impl'], _stream(x)))
+    return y
+
+
+def _dw_bwd_impl(x, w7, m75, m53, ks, transform_on, dy, need_dx, need_filter):
+    """(dx, dw7, dm75, dm53) of the stride-1 elastic depthwise conv."""
+    n, c, h, w = x.shape
+    kmax = w7.shape[-1]
+    p75, p53 = _transform_ptrs(m75, m53)
+    L = B.lib()
+    st = _stream(x)
+    tdy = B.t4(dy)
+    dx = dw7 = dm75 = dm53 = None
+    if need_dx:
+        dx = B.new_nhwc(n, c, h, w, x.dtype, dy.device)
+        tdx = B.t4(dx)
+        B.check(L.ofa_dw_bwd_data(byref(tdy), byref(tdx), B.fptr(w7), kmax, p75, p53,
+                                  int(bool(transform_on)), ks, st))
+    if need_filter:
+        dwa = torch.empty((c, ks * ks), dtype=torch.float32, device=x.device)
+        tx = B.t4(x)
+        B.check(L.ofa_dw_bwd_filter(byref(tx), byref(tdy), ks, dwa.data_ptr(), st))
+        dw7, dm75, dm53 = _dw_filter_chain(dwa, w7, m75, m53, transform_on, ks, c, st)
+    return dx, dw7, dm75, dm53
+
+
 class DwConvFn(torch.autograd.Function):
     """y = depthwise_conv(x, active_filter(w7, m75, m53, ks)), stride 1, same padding."""
 
     @staticmethod
     def forward(ctx, x, w7, m75, m53, ks, transform_on):
-        n, c, h, w = x.shape
-        y = B.new_nhwc(n, c, h, w, x.dtype, x.device)
-        p75, p53 = _transform_ptrs(m75, m53)
-        tx, ty = B.t4(x), B.t4(y)
-        B.check(B.lib().ofa_dw_fwd(byref(tx), byref(ty), B.fptr(w7), w7.shape[-1], p75, p53,
-                                   int(bool(transform_on)), ks, None, _state['impl'], _stream(x)))
+        y = _dw_fwd_impl(x, w7, m75, m53, ks, transform_on)
         ctx.save_for_backward(x, w7, m75, m53)
         ctx.ks, ctx.transform_on = ks, transform_on
         return y
@@ -125,24 +152,8 @@ class DwConvFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         x, w7, m75, m53 = ctx.saved_tensors
-        ks, transform_on = ctx.ks, ctx.transform_on
-        n, c, h, w = x.shape
-        kmax = w7.shape[-1]
-        p75, p53 = _transform_ptrs(m75, m53)
-        L = B.lib()
-        st = _stream(x)
-        tdy = B.t4(dy)
-        dx = dw7 = dm75 = dm53 = None
-        if ctx.needs_input_grad[0]:
-            dx = B.new_nhwc(n, c, h, w, x.dtype, dy.device)
-            tdx = B.t4(dx)
-            B.check(L.ofa_dw_bwd_data(byref(tdy), byref(tdx), B.fptr(w7), kmax, p75, p53,
-                                      int(bool(transform_on)), ks, st))
-        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
-            dwa = torch.empty((c, ks * ks), dtype=torch.float32, device=x.device)
-            tx = B.t4(x)
-            B.check(L.ofa_dw_bwd_filter(byref(tx), byref(tdy), ks, dwa.data_ptr(), st))
-            dw7, dm75, dm53 = _dw_filter_chain(dwa, w7, m75, m53, transform_on, ks, c, st)
+        dx, dw7, dm75, dm53 = _dw_bwd_impl(x, w7, m75, m53, ctx.ks, ctx.transform_on, dy, ctx.needs_input_grad[0],
+                                           ctx.needs_input_grad[1] or ctx.needs_input_grad[2] or ctx.needs_input_grad[3])
         return dx, dw7, dm75, dm53, None, None
 
 
@@ -360,6 +371,92 @@ def _is_half_nhwc(t):
     return t.dtype in (torch.bfloat16, torch.float16) and t.is_contiguous(memory_format=torch.channels_last)
 
 
+def _conv_fwd_impl(x, w, cin, cout, ks):
+    """Forward of ConvFn (shared with the fused conv + BN + act node)."""
+    tdt = _state['train_dtype']
+    ydt = tdt if tdt != torch.float32 else x.dtype
+    if cout < 16:
+        ydt = torch.float32   # thin tensors (X4's 3-channel learned LR image) stay fp32, as in inference
+    y = _conv_out(x, cout, B.STORE_PLAIN, ydt)
+    impl, w16, cin_pad, cout_pad = B.IMPL_SIMT, None, 0, 0
+    if tdt != torch.float32:
+        if _is_half_nhwc(x) and cin % 64 == 0:
+            cache = _train_cache(w, ('f', cin, cout))
+            w16 = cache.get(w, cin, cout, ks, B.STORE_PLAIN, x.dtype)
+            cin_pad, cout_pad, impl = cache.cin_pad, cache.cout_pad, B.IMPL_AUTO
+        elif cin <= 4 and cout == 64:
+            impl = B.IMPL_AUTO        # stem kernel: fp32 image in, 16-bit NHWC out
+    a = _conv_args(x, y, w, cin, cout, ks, B.STORE_PLAIN, None, w16, cin_pad, cout_pad)
+    B.check(B.lib().ofa_conv_fwd(byref(a), impl, _stream(x)))
+    return y
+
+
+def _conv_bwd_impl(x, w, cin, cout, ks, dy, need_dx, need_dw):
+    """Backward of ConvFn: (dx, dw), either may be None."""
+    L = B.lib()
+    st = _stream(x)
+    so, si, sh, sw = w.stride()
+    if dy.dtype != torch.float32 and not dy.is_contiguous(memory_format=torch.channels_last):
+        dy = dy.contiguous(memory_format=torch.channels_last)
+    tdy = B.t4(dy)
+    dx = dw = None
+    if need_dx:
+        n, _, h, wd = x.shape
+        dx = B.new_nhwc(n, cin, h, wd, x.dtype, dy.device)     # gradients carry their activation's type
+        if _is_half_nhwc(dy) and dy.dtype == x.dtype and cout % 64 == 0 and _state['train_dtype'] != torch.float32:
+            # dX = conv(dY, W^T rotated 180 deg): pack W[o, i, ks-1-ky, ks-1-kx] as a (cout -> cin) weight
+            cache = _train_cache(w, ('b', cin, cout))
+            key = (w.data_ptr(), w._version, tuple(w.shape), cin, cout, ks, str(w.device), dy.dtype)
+            if cache._key != key:
+                cin_pad_b, cout_pad_b = cout, (cin + 15) // 16 * 16
+                buf = torch.empty((ks * ks, cout_pad_b, cin_pad_b), dtype=dy.dtype, device=w.device)
+                last = (ks - 1) * sh + (ks - 1) * sw
+                B.check(L.ofa_pack_weight_16(w.data_ptr() + 4 * last, si, so, -sh, -sw, cout, cin, ks, cin_pad_b,
+                                             cout_pad_b, B.STORE_PLAIN, B.dtype_code(dy.dtype), buf.data_ptr(), st))
+                cache._key, cache._buf, cache.cin_pad, cache.cout_pad = key, buf, cin_pad_b, cout_pad_b
+            a = _conv_args(dy, dx, None, cout, cin, ks, B.STORE_PLAIN, None, cache._buf, cache.cin_pad, cache.cout_pad)
+            B.check(L.ofa_conv_fwd(byref(a), B.IMPL_FAST, st))
+        elif (_state['train_dtype'] != torch.float32 and cout <= 4 and cin == 64 and ks in (3, 5)
+              and dx.dtype != torch.float32 and w.is_contiguous()):
+            # thin output (64 -> 3 at the SR resolution): its data gradient is a 3 -> 64 conv of dY with the rotated,
+            # transposed slice -- the stem kernel, reading the fp32 master through swapped / negative strides
+            last = (ks - 1) * sh + (ks - 1) * sw
+            a = _conv_args(dy, dx, None, cout, cin, ks, B.STORE_PLAIN)
+            a.w = w.data_ptr() + 4 * last
+            a.w_so, a.w_si, a.w_sh, a.w_sw = si, so, -sh, -sw
+            B.check(L.ofa_conv_fwd(byref(a), B.IMPL_AUTO, st))
+        else:
+            tdx = B.t4(dx)
+            B.check(L.ofa_conv_bwd_data(byref(tdy), byref(tdx), B.fptr(w), so, si, sh, sw, cin, cout, ks, st))
+    if need_dw:
+        dw = torch.zeros_like(w)
+        tdt = _state['train_dtype']
+        if tdt != torch.float32 and cin == 64 and cout < 8 and _is_half_nhwc(x):
+            # thin output (64 -> 3): pad dY to 8 channels so the tcgen05 weight-gradient kernel applies
+            dy8 = torch.empty((dy.shape[0], 8, dy.shape[2], dy.shape[3]), dtype=x.dtype, device=dy.device,
+                              memory_format=torch.channels_last).zero_()
+            dy8[:, :cout] = dy
+            dw8 = torch.zeros((8, w.shape[1], ks, ks), dtype=torch.float32, device=w.device)
+            t8 = B.t4(dy8)
+            tx = B.t4(x)
+            B.check(L.ofa_conv_bwd_weight(byref(tx), byref(t8), dw8.data_ptr(), *dw8.stride(), cin, 8, ks, st))
+            dw[:cout] = dw8[:cout]
+        elif tdt != torch.float32 and cout == 64 and cin < 8 and _is_half_nhwc(dy):
+            # thin input (the stem, 3 -> 64): pad X to 8 channels
+            x8 = torch.empty((x.shape[0], 8, x.shape[2], x.shape[3]), dtype=dy.dtype, device=dy.device,
+                             memory_format=torch.channels_last).zero_()
+            x8[:, :cin] = x
+            dw8 = torch.zeros((w.shape[0], 8, ks, ks), dtype=torch.float32, device=w.device)
+            t8 = B.t4(x8)
+            B.check(L.ofa_conv_bwd_weight(byref(t8), byref(tdy), dw8.data_ptr(), *dw8.stride(), 8, cout, ks, st))
+            dw[:, :cin] = dw8[:, :cin]
+        else:
+            tx = B.t4(x)
+            B.check(L.ofa_conv_bwd_weight(byref(tx), byref(tdy), dw.data_ptr(), so, si, sh, sw, cin, cout, ks, st))
+    
+    return dx, dw
+
+
 class ConvFn(torch.autograd.Function):
     """y = conv2d(x, w[:cout, :cin]), stride 1, same padding; the slice is addressed in place.
     fp32 activations: the exact CUDA-core kernels.  16-bit NHWC activations (set_train_dtype): forward and
@@ -369,21 +466,7 @@ class ConvFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w, cin, cout, ks):
-        tdt = _state['train_dtype']
-        ydt = tdt if tdt != torch.float32 else x.dtype
-        if cout < 16:
-            ydt = torch.float32   # thin tensors (X4's 3-channel learned LR image) stay fp32, as in inference
-        y = _conv_out(x, cout, B.STORE_PLAIN, ydt)
-        impl, w16, cin_pad, cout_pad = B.IMPL_SIMT, None, 0, 0
-        if tdt != torch.float32:
-            if _is_half_nhwc(x) and cin % 64 == 0:
-                cache = _train_cache(w, ('f', cin, cout))
-                w16 = cache.get(w, cin, cout, ks, B.STORE_PLAIN, x.dtype)
-                cin_pad, cout_pad, impl = cache.cin_pad, cache.cout_pad, B.IMPL_AUTO
-            elif cin <= 4 and cout == 64:
-                impl = B.IMPL_AUTO        # stem kernel: fp32 image in, 16-bit NHWC out
-        a = _conv_args(x, y, w, cin, cout, ks, B.STORE_PLAIN, None, w16, cin_pad, cout_pad)
-        B.check(B.lib().ofa_conv_fwd(byref(a), impl, _stream(x)))
+        y = _conv_fwd_impl(x, w, cin, cout, ks)
         ctx.save_for_backward(x, w)
         ctx.dims = (cin, cout, ks)
         return y
@@ -392,66 +475,7 @@ class ConvFn(torch.autograd.Function):
     def backward(ctx, dy):
         x, w = ctx.saved_tensors
         cin, cout, ks = ctx.dims
-        L = B.lib()
-        st = _stream(x)
-        so, si, sh, sw = w.stride()
-        if dy.dtype != torch.float32 and not dy.is_contiguous(memory_format=torch.channels_last):
-            dy = dy.contiguous(memory_format=torch.channels_last)
-        tdy = B.t4(dy)
-        dx = dw = None
-        if ctx.needs_input_grad[0]:
-            n, _, h, wd = x.shape
-            dx = B.new_nhwc(n, cin, h, wd, x.dtype, dy.device)     # gradients carry their activation's type
-            if _is_half_nhwc(dy) and dy.dtype == x.dtype and cout % 64 == 0 and _state['train_dtype'] != torch.float32:
-                # dX = conv(dY, W^T rotated 180 deg): pack W[o, i, ks-1-ky, ks-1-kx] as a (cout -> cin) weight
-                cache = _train_cache(w, ('b', cin, cout))
-                key = (w.data_ptr(), w._version, tuple(w.shape), cin, cout, ks, str(w.device), dy.dtype)
-                if cache._key != key:
-                    cin_pad_b, cout_pad_b = cout, (cin + 15) // 16 * 16
-                    buf = torch.empty((ks * ks, cout_pad_b, cin_pad_b), dtype=dy.dtype, device=w.device)
-                    last = (ks - 1) * sh + (ks - 1) * sw
-                    B.check(L.ofa_pack_weight_16(w.data_ptr() + 4 * last, si, so, -sh, -sw, cout, cin, ks, cin_pad_b,
-                                                 cout_pad_b, B.STORE_PLAIN, B.dtype_code(dy.dtype), buf.data_ptr(), st))
-                    cache._key, cache._buf, cache.cin_pad, cache.cout_pad = key, buf, cin_pad_b, cout_pad_b
-                a = _conv_args(dy, dx, None, cout, cin, ks, B.STORE_PLAIN, None, cache._buf, cache.cin_pad, cache.cout_pad)
-                B.check(L.ofa_conv_fwd(byref(a), B.IMPL_FAST, st))
-            elif (_state['train_dtype'] != torch.float32 and cout <= 4 and cin == 64 and ks in (3, 5)
-                  and dx.dtype != torch.float32 and w.is_contiguous()):
-                # thin output (64 -> 3 at the SR resolution): its data gradient is a 3 -> 64 conv of dY with the rotated,
-                # transposed slice -- the stem kernel, reading the fp32 master through swapped / negative strides
-                last = (ks - 1) * sh + (ks - 1) * sw
-                a = _conv_args(dy, dx, None, cout, cin, ks, B.STORE_PLAIN)
-                a.w = w.data_ptr() + 4 * last
-                a.w_so, a.w_si, a.w_sh, a.w_sw = si, so, -sh, -sw
-                B.check(L.ofa_conv_fwd(byref(a), B.IMPL_AUTO, st))
-            else:
-                tdx = B.t4(dx)
-                B.check(L.ofa_conv_bwd_data(byref(tdy), byref(tdx), B.fptr(w), so, si, sh, sw, cin, cout, ks, st))
-        if ctx.needs_input_grad[1]:
-            dw = torch.zeros_like(w)
-            tdt = _state['train_dtype']
-            if tdt != torch.float32 and cin == 64 and cout < 8 and _is_half_nhwc(x):
-                # thin output (64 -> 3): pad dY to 8 channels so the tcgen05 weight-gradient kernel applies
-                dy8 = torch.empty((dy.shape[0], 8, dy.shape[2], dy.shape[3]), dtype=x.dtype, device=dy.device,
-                                  memory_format=torch.channels_last).zero_()
-                dy8[:, :cout] = dy
-                dw8 = torch.zeros((8, w.shape[1], ks, ks), dtype=torch.float32, device=w.device)
-                t8 = B.t4(dy8)
-                tx = B.t4(x)
-                B.check(L.ofa_conv_bwd_weight(byref(tx), byref(t8), dw8.data_ptr(), *dw8.stride(), cin, 8, ks, st))
-                dw[:cout] = dw8[:cout]
-            elif tdt != torch.float32 and cout == 64 and cin < 8 and _is_half_nhwc(dy):
-                # thin input (the stem, 3 -> 64): pad X to 8 channels
-                x8 = torch.empty((x.shape[0], 8, x.shape[2], x.shape[3]), dtype=dy.dtype, device=dy.device,
-                                 memory_format=torch.channels_last).zero_()
-                x8[:, :cin] = x
-                dw8 = torch.zeros((w.shape[0], 8, ks, ks), dtype=torch.float32, device=w.device)
-                t8 = B.t4(x8)
-                B.check(L.ofa_conv_bwd_weight(byref(t8), byref(tdy), dw8.data_ptr(), *dw8.stride(), 8, cout, ks, st))
-                dw[:, :cin] = dw8[:, :cin]
-            else:
-                tx = B.t4(x)
-                B.check(L.ofa_conv_bwd_weight(byref(tx), byref(tdy), dw.data_ptr(), so, si, sh, sw, cin, cout, ks, st))
+        dx, dw = _conv_bwd_impl(x, w, cin, cout, ks, dy, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
         return dx, dw, None, None, None
 
 
@@ -463,6 +487,60 @@ def conv2d(x, w, cin, cout, ks):
 # BatchNorm (+ activation, + residual) on the active channel prefix (a5, a6, a8, a14)
 # =================================================================================================
 
+def _bn_fwd_impl(x, gamma, beta, running_mean, running_var, residual, training, momentum, eps, act, bump):
+    """Forward of BnActFn (shared with the fused nodes): returns (y, mean, var) -- the statistics used to normalise."""
+    n, c, h, w = x.shape
+    L = B.lib()
+    st = _stream(x)
+    tx = B.t4(x)
+    if training:
+        stats = torch.empty((2, c), dtype=torch.float32, device=x.device)
+        mean, var = stats[0], stats[1]
+        B.check(L.ofa_bn_stats(byref(tx), mean.data_ptr(), var.data_ptr(), st))
+        if running_mean is not None and momentum is not None and momentum != 0.0:
+            B.check(L.ofa_bn_update_running(mean.data_ptr(), var.data_ptr(), n * h * w,
+                                            B.fptr(running_mean), B.fptr(running_var), float(momentum), c,
+                                            bump.data_ptr() if bump is not None else None, st))
+            bump = None
+        if bump is not None:
+            bump += 1
+    else:
+        mean, var = running_mean, running_var
+    y = B.new_nhwc(n, c, h, w, x.dtype, x.device)
+    ty = B.t4(y)
+    e, keep = B.epilogue(gamma, beta, mean, var, eps, act, residual)
+    B.check(L.ofa_affine_act(byref(tx), byref(ty), byref(e), B.STORE_PLAIN, st))
+    return y, mean, var
+
+
+def _bn_bwd_impl(x, gamma, beta, mean, var, training, eps, act, dy, need_dx, need_dgamma, need_dbeta):
+    """Backward of BnActFn: (dx, dgamma, dbeta)."""
+    n, c, h, w = x.shape
+    L = B.lib()
+    st = _stream(x)
+    tx, tdy = B.t4(x), B.t4(dy)
+    # the two per-channel sums ARE d(beta) and d(gamma) on the active prefix: they are reduced straight into one
+    # zero-filled [2, C_full] buffer whose rows are returned as the full-width gradients (1 fill instead of 2 fills
+    # + 2 slice copies per BatchNorm)
+    c_full = max(c, gamma.shape[0] if gamma is not None else c, beta.shape[0] if beta is not None else c)
+    sums = torch.zeros((2, c_full), dtype=torch.float32, device=x.device)
+    s0, s1 = sums[0], sums[1]
+    B.check(L.ofa_bn_bwd_reduce(byref(tx), byref(tdy), _null_or(gamma), _null_or(beta), B.fptr(mean),
+                                B.fptr(var), eps, act, s0.data_ptr(), s1.data_ptr(), st))
+    dx = dgamma = dbeta = None
+    if need_dx:
+        dx = B.new_nhwc(n, c, h, w, x.dtype, dy.device)
+        tdx = B.t4(dx)
+        B.check(L.ofa_bn_bwd_apply(byref(tx), byref(tdy), byref(tdx), _null_or(gamma), _null_or(beta),
+                                   B.fptr(mean), B.fptr(var), eps, act, int(training), s0.data_ptr(),
+                                   s1.data_ptr(), st))
+    if gamma is not None and need_dgamma:
+        dgamma = s1[:gamma.shape[0]]
+    if beta is not None and need_dbeta:
+        dbeta = s0[:beta.shape[0]]
+    return dx, dgamma, dbeta
+
+
 class BnActFn(torch.autograd.Function):
     """y = act(BN(x)) [+ residual].  Training: batch statistics (biased var for normalisation,
     unbiased for the running update, momentum update of the [:C] slice in place).  Eval: running
@@ -470,27 +548,8 @@ class BnActFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, gamma, beta, running_mean, running_var, residual, training, momentum, eps, act, bump=None):
-        n, c, h, w = x.shape
-        L = B.lib()
-        st = _stream(x)
-        tx = B.t4(x)
-        if training:
-            stats = torch.empty((2, c), dtype=torch.float32, device=x.device)
-            mean, var = stats[0], stats[1]
-            B.check(L.ofa_bn_stats(byref(tx), mean.data_ptr(), var.data_ptr(), st))
-            if running_mean is not None and momentum is not None and momentum != 0.0:
-                B.check(L.ofa_bn_update_running(mean.data_ptr(), var.data_ptr(), n * h * w,
-                                                B.fptr(running_mean), B.fptr(running_var), float(momentum), c,
-                                                bump.data_ptr() if bump is not None else None, st))
-                bump = None
-            if bump is not None:
-                bump += 1
-        else:
-            mean, var = running_mean, running_var
-        y = B.new_nhwc(n, c, h, w, x.dtype, x.device)
-        ty = B.t4(y)
-        e, keep = B.epilogue(gamma, beta, mean, var, eps, act, residual)
-        B.check(L.ofa_affine_act(byref(tx), byref(ty), byref(e), B.STORE_PLAIN, st))
+        y, mean, var = _bn_fwd_impl(x, gamma, beta, running_mean, running_var, residual, training, momentum, eps, act,
+                                    bump)
         ctx.save_for_backward(x, gamma, beta, mean, var)
         ctx.cfg = (training, eps, act, residual is not None)
         return y
@@ -499,31 +558,64 @@ class BnActFn(torch.autograd.Function):
     def backward(ctx, dy):
         x, gamma, beta, mean, var = ctx.saved_tensors
         training, eps, act, has_res = ctx.cfg
-        n, c, h, w = x.shape
-        L = B.lib()
-        st = _stream(x)
-        tx, tdy = B.t4(x), B.t4(dy)
-        # the two per-channel sums ARE d(beta) and d(gamma) on the active prefix: they are reduced straight into one
-        # zero-filled [2, C_full] buffer whose rows are returned as the full-width gradients (1 fill instead of 2 fills
-        # + 2 slice copies per BatchNorm)
-        c_full = max(c, gamma.shape[0] if gamma is not None else c, beta.shape[0] if beta is not None else c)
-        sums = torch.zeros((2, c_full), dtype=torch.float32, device=x.device)
-        s0, s1 = sums[0], sums[1]
-        B.check(L.ofa_bn_bwd_reduce(byref(tx), byref(tdy), _null_or(gamma), _null_or(beta), B.fptr(mean),
-                                    B.fptr(var), eps, act, s0.data_ptr(), s1.data_ptr(), st))
-        dx = dgamma = dbeta = None
-        if ctx.needs_input_grad[0]:
-            dx = B.new_nhwc(n, c, h, w, x.dtype, dy.device)
-            tdx = B.t4(dx)
-            B.check(L.ofa_bn_bwd_apply(byref(tx), byref(tdy), byref(tdx), _null_or(gamma), _null_or(beta),
-                                       B.fptr(mean), B.fptr(var), eps, act, int(training), s0.data_ptr(),
-                                       s1.data_ptr(), st))
-        if gamma is not None and ctx.needs_input_grad[1]:
-            dgamma = s1[:gamma.shape[0]]
-        if beta is not None and ctx.needs_input_grad[2]:
-            dbeta = s0[:beta.shape[0]]
+        dx, dgamma, dbeta = _bn_bwd_impl(x, gamma, beta, mean, var, training, eps, act, dy, ctx.needs_input_grad[0],
+                                         ctx.needs_input_grad[1], ctx.needs_input_grad[2])
         dres = dy if (has_res and ctx.needs_input_grad[5]) else None
         return dx, dgamma, dbeta, None, None, dres, None, None, None, None, None
+
+
+class ConvBnActFn(torch.autograd.Function):
+    """y = act(BN(conv2d(x, w[:cout, :cin]))) [+ residual] as ONE autograd node: the same library calls as ConvFn followed
+    by BnActFn, but one Python-side node per layer instead of two (the eager training step is bounded by the host's
+    launch rate; a node costs ~15 us each way)."""
+
+    @staticmethod
+    def forward(ctx, x, w, cin, cout, ks, gamma, beta, running_mean, running_var, residual, training, momentum, eps,
+                act, bump):
+        z = _conv_fwd_impl(x, w, cin, cout, ks)
+        y, mean, var = _bn_fwd_impl(z, gamma, beta, running_mean, running_var, residual, training, momentum, eps, act,
+                                    bump)
+        ctx.save_for_backward(x, w, z, gamma, beta, mean, var)
+        ctx.cfg = (cin, cout, ks, training, eps, act, residual is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, z, gamma, beta, mean, var = ctx.saved_tensors
+        cin, cout, ks, training, eps, act, has_res = ctx.cfg
+        ng = ctx.needs_input_grad
+        dz, dgamma, dbeta = _bn_bwd_impl(z, gamma, beta, mean, var, training, eps, act, dy, ng[0] or ng[1], ng[5], ng[6])
+        dx = dw = None
+        if dz is not None:
+            dx, dw = _conv_bwd_impl(x, w, cin, cout, ks, dz, ng[0], ng[1])
+        dres = dy if (has_res and ng[9]) else None
+        return dx, dw, None, None, None, dgamma, dbeta, None, None, dres, None, None, None, None, None
+
+
+class DwBnActFn(torch.autograd.Function):
+    """y = act(BN(depthwise_conv(x, active_filter(w7, m75, m53, ks)))) as one autograd node (stride 1)."""
+
+    @staticmethod
+    def forward(ctx, x, w7, m75, m53, ks, transform_on, gamma, beta, running_mean, running_var, training, momentum, eps,
+                act, bump):
+        z = _dw_fwd_impl(x, w7, m75, m53, ks, transform_on)
+        y, mean, var = _bn_fwd_impl(z, gamma, beta, running_mean, running_var, None, training, momentum, eps, act, bump)
+        ctx.save_for_backward(x, w7, m75, m53, z, gamma, beta, mean, var)
+        ctx.cfg = (ks, transform_on, training, eps, act)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w7, m75, m53, z, gamma, beta, mean, var = ctx.saved_tensors
+        ks, transform_on, training, eps, act = ctx.cfg
+        ng = ctx.needs_input_grad
+        need_filter = ng[1] or ng[2] or ng[3]
+        dz, dgamma, dbeta = _bn_bwd_impl(z, gamma, beta, mean, var, training, eps, act, dy, ng[0] or need_filter,
+                                         ng[6], ng[7])
+        dx = dw7 = dm75 = dm53 = None
+        if dz is not None:
+            dx, dw7, dm75, dm53 = _dw_bwd_impl(x, w7, m75, m53, ks, transform_on, dz, ng[0], need_filter)
+        return dx, dw7, dm75, dm53, None, None, dgamma, dbeta, None, None, None, None, None, None, None
 
 
 def bn_hooked(*bns):
@@ -573,6 +665,13 @@ def bn_act(x, bn, C, act=B.ACT_NONE, residual=None, full_width=False):
         # a per-instance `forward` override = the hook set_running_statistics installs on every BatchNorm2d of a
         # deep copy (reference elastic_nn/utils.py:29-52): honour it, then apply the rest of the fused epilogue
         return act_residual(bn(x), act, residual)
+    training, momentum, bump = _bn_mode(bn)
+    return BnActFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, residual, training,
+                         momentum, bn.eps, act, bump)
+
+
+def _bn_mode(bn):
+    """(training, momentum, bump) of nn.BatchNorm2d.forward / DynamicBatchNorm2d.bn_forward (dynamic_op.py:148-167)."""
     training = bn.training or not bn.track_running_stats
     momentum = 0.0
     bump = None
@@ -586,8 +685,25 @@ def bn_act(x, bn, C, act=B.ACT_NONE, residual=None, full_width=False):
             if not (bump.is_cuda and bump.dtype == torch.int64):
                 bn.num_batches_tracked += 1
                 bump = None
-    return BnActFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, residual, training,
-                         momentum, bn.eps, act, bump)
+    return training, momentum, bump
+
+
+def conv_bn_act(x, w, cin, cout, ks, bn, act=B.ACT_NONE, residual=None):
+    """conv2d -> bn_act as one autograd node (two when the BatchNorm carries a set_running_statistics override)."""
+    if 'forward' in bn.__dict__:
+        return bn_act(conv2d(x, w, cin, cout, ks), bn, cout, act, residual)
+    training, momentum, bump = _bn_mode(bn)
+    return ConvBnActFn.apply(x, w, cin, cout, ks, bn.weight, bn.bias, bn.running_mean, bn.running_var, residual,
+                             training, momentum, bn.eps, act, bump)
+
+
+def dw_bn_act(x, w7, m75, m53, ks, transform_on, bn, act=B.ACT_NONE, stride=1):
+    """depthwise conv -> bn_act as one autograd node (stride 1, no override on the BatchNorm), else two."""
+    if stride != 1 or 'forward' in bn.__dict__:
+        return bn_act(dw_conv(x, w7, m75, m53, ks, transform_on, stride), bn, x.shape[1], act)
+    training, momentum, bump = _bn_mode(bn)
+    return DwBnActFn.apply(x, w7, m75, m53, ks, transform_on, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                           training, momentum, bn.eps, act, bump)
 
 
 # =================================================================================================

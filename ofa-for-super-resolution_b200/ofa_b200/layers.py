@@ -101,17 +101,20 @@ class ConvLayer(MyModule):
             return OF.conv_bn_act_infer(x, w, self.in_channels, self.out_channels, self.kernel_size, bn,
                                         self._act_code, self._store, residual, self._packed,
                                         out_dtype, self.out_nchw)
-        y = OF.conv2d(x, w, self.in_channels, self.out_channels, self.kernel_size)
         if self._store == B.STORE_PLAIN:
-            if bn is not None:
-                y = OF.bn_act(y, bn, self.out_channels, self._act_code, residual)
+            if bn is not None:      # conv -> BN -> act (+ residual) as one autograd node
+                y = OF.conv_bn_act(x, w, self.in_channels, self.out_channels, self.kernel_size, bn, self._act_code,
+                                   residual)
             else:
                 assert self._act_code == B.ACT_NONE and residual is None
+                y = OF.conv2d(x, w, self.in_channels, self.out_channels, self.kernel_size)
             if self.out_dtype is not None and y.dtype != self.out_dtype:
                 y = y.to(self.out_dtype)      # mixed-precision training: the caller's loss sees fp32
             return y
         if bn is not None:
-            y = OF.bn_act(y, bn, self.out_channels, B.ACT_NONE, None)
+            y = OF.conv_bn_act(x, w, self.in_channels, self.out_channels, self.kernel_size, bn, B.ACT_NONE, None)
+        else:
+            y = OF.conv2d(x, w, self.in_channels, self.out_channels, self.kernel_size)
         y = OF.pixel_shuffle2(y) if self._store == B.STORE_PIXELSHUFFLE2 else OF.pixel_unshuffle2(y)
         if residual is not None:
             y = y + residual

