@@ -16,7 +16,8 @@ from ofa_b200.elastic_nn.networks import OFAMobileNetS4
 
 ap = argparse.ArgumentParser()
 ap.add_argument('--batch', type=int, default=64)
-ap.add_argument('--steps', type=int, default=5)
+ap.add_argument('--steps', type=int, default=30)
+ap.add_argument('--warmup', type=int, default=8, help='untimed steps: sampled sub-networks change the tensor sizes every step, so the allocator needs a few steps to settle')
 ap.add_argument('--max-subnet', dest='max', action='store_true', help='max subnet instead of sampled ones')
 ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
 ap.add_argument('--verbose', action='store_true')
@@ -70,7 +71,7 @@ def step(i):
     return loss
 
 
-for i in range(2):
+for i in range(a.warmup):
     step(i)
 torch.cuda.synchronize()
 if a.graph:
@@ -100,7 +101,7 @@ t0 = time.perf_counter()
 per_step = []
 for i in range(a.steps):
     ts = time.perf_counter()
-    step(10 + i)
+    step(100 + i)
     if a.verbose:
         torch.cuda.synchronize()
         per_step.append((time.perf_counter() - ts) * 1e3)

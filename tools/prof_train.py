@@ -1,5 +1,5 @@
 import sys, runpy, torch
-sys.argv = ['bench_train.py', '--steps', '1', '--max-subnet']
+sys.argv = ['bench_train.py', '--steps', '1', '--max-subnet'] + sys.argv[1:]
 from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     runpy.run_path('/root/repo/tools/bench_train.py', run_name='__main__')
