@@ -112,6 +112,23 @@ def test_module_api_surface():
     DynamicSeparableConv2d.KERNEL_TRANSFORM_MODE = 1
     assert DynamicBatchNorm2d.SET_RUNNING_STATISTICS is False
     assert DynamicConvLayer([3], [16], 3).module_str == 'DyConv(O16, K3, S1)'
+    # the MobileNetV3 flavour: same class names, children and state_dict keys as the reference
+    from ofa_b200.elastic_nn.modules import DynamicSE, DynamicLinear, DynamicLinearLayer
+    from ofa_b200.layers import LinearLayer, MBInvertedConvLayer, set_layer_from_config
+    from ofa_b200.utils import SEModule, make_divisible
+    se = DynamicSE(96)
+    assert isinstance(se, SEModule) and se.reduction == 4
+    assert set(se.state_dict()) == {'fc.reduce.weight', 'fc.reduce.bias', 'fc.expand.weight', 'fc.expand.bias'}
+    assert tuple(se.fc.reduce.weight.shape) == (make_divisible(96 // 4, 8), 96, 1, 1)
+    v3 = DynamicMBConvLayer([24], [40], [3, 5, 7], [3, 4, 6], stride=2, act_func='h_swish', use_se=True)
+    assert isinstance(v3.depth_conv.se, DynamicSE) and v3.depth_conv.conv.stride == 2
+    assert list(v3.depth_conv._modules) == ['conv', 'bn', 'act', 'se']
+    lin = DynamicLinearLayer([48, 96], 10, bias=True, dropout_rate=0.1)
+    assert isinstance(lin.linear, DynamicLinear) and lin.linear.active_out_features == 10 and lin.dropout is not None
+    static = MBInvertedConvLayer(16, 24, 5, stride=2, expand_ratio=4, act_func='h_swish', use_se=True)
+    assert static.module_str == 'SE_5x5_MBConv4_H_SWISH_O24'
+    cfg = LinearLayer(32, 10).config
+    assert isinstance(set_layer_from_config(cfg), LinearLayer)
 
 
 def test_load_weights_from_net_key_mapping():
