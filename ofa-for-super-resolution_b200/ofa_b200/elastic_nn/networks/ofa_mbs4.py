@@ -16,6 +16,9 @@ import torch.nn as nn
 from ...layers import ConvLayer, IdentityLayer, MobileInvertedResidualBlock
 from ...utils import make_divisible, int2list
 from ..modules.dynamic_layers import DynamicMBConvLayer
+from ..modules.dynamic_op import DynamicBatchNorm2d
+from ... import functional as OF
+from ... import backend as B
 from .supernet_base import ElasticSRSuperNet
 
 __all__ = ['OFAMobileNetS4']
@@ -91,7 +94,42 @@ class OFAMobileNetS4(ElasticSRSuperNet):
     def name():
         return 'OFAMobileNetS4'
 
+    # The planar tensor-core path needs image rows of a multiple of 8 pixels (16-byte TMA row pitch); a frame of any
+    # other width would run ~2x slower on the NHWC kernels (16.5 vs 7.9 ms at 956 x 540).  In inference such a frame is
+    # computed as TWO column tiles whose widths ARE multiples of 8, overlapping by the receptive field (64 LR pixels):
+    # eval-mode BatchNorm is a per-channel affine, so each tile's core columns equal the whole-frame result.
+    _SPLIT_HALO = 64
+    _SPLIT_MIN_W = 256
+
+    def _column_split(self, x):
+        """None, or (core split c, left window end a, right window start b) for a frame that should be computed as two
+        column tiles."""
+        if not (x.dim() == 4 and x.is_cuda and x.shape[3] % 8 != 0 and x.shape[3] >= self._SPLIT_MIN_W
+                and x.shape[2] * x.shape[3] >= 16384 and OF.inference_mode_active(self)
+                and OF.get_compute_dtype() != torch.float32 and OF._state['impl'] in (B.IMPL_AUTO, B.IMPL_FAST)
+                and not DynamicBatchNorm2d.SET_RUNNING_STATISTICS):
+            return None
+        w = x.shape[3]
+        c = (w // 2) // 8 * 8
+        a = (c + self._SPLIT_HALO + 7) // 8 * 8
+        b = c - self._SPLIT_HALO
+        b -= (8 - (w - b) % 8) % 8               # the right window [b, w) gets a width that is a multiple of 8
+        if a > w or b < 0:
+            return None
+        return c, a, b
+
     def forward(self, x):
+        split = self._column_split(x)
+        if split is not None:
+            c, a, b = split
+            left = self.forward(x[:, :, :, :a])
+            right = self.forward(x[:, :, :, b:])
+            s = left.shape[3] // a                # 2 ** (number of PixelShuffle stages that ran)
+            out = torch.empty((x.shape[0], left.shape[1], left.shape[2], s * x.shape[3]), dtype=left.dtype,
+                              device=left.device)
+            out[:, :, :, :s * c] = left[:, :, :, :s * c]
+            out[:, :, :, s * c:] = right[:, :, :, s * (c - b):]
+            return out
         x = self.dec_first_conv_block(x)
         dec_big_skip = x
         x = self._run_groups(x, 0, 4)

@@ -1077,3 +1077,31 @@ def test_pixel_reorder_kernels_exact(dev, dtype, shape):
     if h % 2 == 0 and w % 2 == 0:
         down = OF.ReorderFn.apply(x, B.STORE_PIXELUNSHUFFLE2)
         assert torch.equal(down, torch.nn.functional.pixel_unshuffle(x, 2))
+
+
+def test_frame_width_not_multiple_of_8_is_split_into_column_tiles(dev):
+    """A frame whose width is not a multiple of 8 cannot take the planar kernels (16-byte TMA row pitch); in inference
+    OFAMobileNetS4 computes it as two column tiles of legal widths that overlap by the receptive field.  The result must
+    equal the whole frame computed on the NHWC kernels, and the oracle."""
+    import ofa_b200
+    from ofa_b200 import backend as B
+    ofa_b200.set_compute_dtype(torch.float16)
+    net = _build_net('s4', [1, 2], 67, dev)
+    spec = O.SuperNetSpec('s4', FULL['ks_list'], FULL['expand_ratio_list'], FULL['depth_list'], [1, 2])
+    sd = O.synth_state_dict(spec.param_shapes(), 67)
+    x = torch.from_numpy(np.random.RandomState(4).rand(1, 3, 72, 300).astype(np.float32))
+    assert net._column_split(x.to(dev)) is None            # grad mode on: the autograd path is never split
+    for sub in (dict(ks=7, e=6, d=4, pixel_d=2), dict(ks=3, e=4, d=2, pixel_d=1)):
+        net.set_active_subnet(**sub)
+        spec.set_active_subnet(**sub)
+        with torch.no_grad():
+            c, a, b = net._column_split(x.to(dev))
+            assert a % 8 == 0 and (300 - b) % 8 == 0 and a - c >= 64 and c - b >= 64
+            y = net(x.to(dev))
+            ofa_b200.set_impl(B.IMPL_NHWC)                  # whole frame on the NHWC kernels: no split
+            assert net._column_split(x.to(dev)) is None
+            y_whole = net(x.to(dev))
+            ofa_b200.set_impl(B.IMPL_AUTO)
+            ref = O.supernet_forward(x, sd, spec)
+        assert y.shape == y_whole.shape == ref.shape
+        assert relerr(y, y_whole) < 2e-3 and relerr(y, ref) < 1e-2
