@@ -84,33 +84,59 @@ def ncu_traffic(tag):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: through NVML (nvidia_ml_py, ~10 ms period, so a
+    100 ms timed region yields ~10 samples) when it is importable, else by spawning nvidia-smi (~0.2 s period)."""
     Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    NAMES = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self._halt = index, [], threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            uuid = torch.cuda.get_device_properties(index).uuid           # CUDA order may differ from NVML order
+            try:
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(('GPU-' + str(uuid)).encode())
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+        mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+        bits = [n.nvmlClocksEventReasonHwSlowdown, n.nvmlClocksEventReasonHwThermalSlowdown,
+                n.nvmlClocksEventReasonSwThermalSlowdown, n.nvmlClocksEventReasonSwPowerCap]
+        self.rows.append([str(mhz), str(self.max_mhz)] + ['Active' if mask & b else 'Not Active' for b in bits])
 
     def run(self):
         while not self._halt.is_set():
             try:
-                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([c.strip() for c in out.strip().split(',')])
+                if self.nvml is not None:
+                    self._sample_nvml()
+                else:
+                    out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits'], capture_output=True, text=True,
+                                         timeout=5).stdout
+                    self.rows.append([c.strip() for c in out.strip().split(',')])
             except Exception:
                 pass
-            self._halt.wait(0.2)
+            self._halt.wait(0.01 if self.nvml is not None else 0.2)
 
     def finish(self):
         self._halt.set()
         self.join(timeout=6)
         sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace('.', '').isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace('.', '').isdigit()]
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower() == 'active'})
+        reasons = sorted({self.NAMES[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower() == 'active'})
         return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': reasons, 'samples': len(sm)}
+                'reasons': reasons, 'samples': len(sm), 'source': 'nvml' if self.nvml is not None else 'nvidia-smi'}
 
 
 # =====================================================================================================
