@@ -24,6 +24,16 @@ from ... import backend as B
 __all__ = ['DynamicMBConvLayer', 'DynamicConvLayer', 'DynamicLinearLayer']
 
 
+def _fill_from_slice(dst, src, *extent):
+    """dst <- src[:extent[0], :extent[1], ...] (the active prefix of a full-size parameter)."""
+    dst.data.copy_(src.data[tuple(slice(0, e) for e in extent)])
+
+
+def _permute(param, dim, order):
+    """Reorder a parameter along `dim` in place (the tensor object is replaced, the Parameter stays)."""
+    param.data = torch.index_select(param.data, dim, order)
+
+
 def _has_hooks(*mods):
     """True when a sub-module carries forward / backward hooks (then it is called as a module, not bypassed)."""
     for m in mods:
@@ -165,22 +175,22 @@ class DynamicMBConvLayer(MyModule):
         ).to(get_net_device(self))
         if not preserve_weight:
             return sub_layer
+        mid, cout = middle_channel, self.active_out_channel
         if sub_layer.inverted_bottleneck is not None:
-            sub_layer.inverted_bottleneck.conv.weight.data.copy_(
-                self.inverted_bottleneck.conv.conv.weight.data[:middle_channel, :in_channel, :, :])
+            _fill_from_slice(sub_layer.inverted_bottleneck.conv.weight, self.inverted_bottleneck.conv.conv.weight,
+                             mid, in_channel)
             copy_bn(sub_layer.inverted_bottleneck.bn, self.inverted_bottleneck.bn.bn)
-        sub_layer.depth_conv.conv.weight.data.copy_(
-            self.depth_conv.conv.get_active_filter(middle_channel, self.active_kernel_size).data)
+        # the depthwise filter of the sub-layer is the TRANSFORMED active filter, not a slice
+        sub_layer.depth_conv.conv.weight.data.copy_(self.depth_conv.conv.get_active_filter(mid, self.active_kernel_size).data)
         copy_bn(sub_layer.depth_conv.bn, self.depth_conv.bn.bn)
         if self.use_se:
-            se_mid = make_divisible(middle_channel // SEModule.REDUCTION, divisor=8)
-            src, dst = self.depth_conv.se.fc, sub_layer.depth_conv.se.fc
-            dst.reduce.weight.data.copy_(src.reduce.weight.data[:se_mid, :middle_channel, :, :])
-            dst.reduce.bias.data.copy_(src.reduce.bias.data[:se_mid])
-            dst.expand.weight.data.copy_(src.expand.weight.data[:middle_channel, :se_mid, :, :])
-            dst.expand.bias.data.copy_(src.expand.bias.data[:middle_channel])
-        sub_layer.point_linear.conv.weight.data.copy_(
-            self.point_linear.conv.conv.weight.data[:self.active_out_channel, :middle_channel, :, :])
+            se_mid = make_divisible(mid // SEModule.REDUCTION, divisor=8)
+            full, part = self.depth_conv.se.fc, sub_layer.depth_conv.se.fc
+            _fill_from_slice(part.reduce.weight, full.reduce.weight, se_mid, mid)
+            _fill_from_slice(part.reduce.bias, full.reduce.bias, se_mid)
+            _fill_from_slice(part.expand.weight, full.expand.weight, mid, se_mid)
+            _fill_from_slice(part.expand.bias, full.expand.bias, mid)
+        _fill_from_slice(sub_layer.point_linear.conv.weight, self.point_linear.conv.conv.weight, cout, mid)
         copy_bn(sub_layer.point_linear.bn, self.point_linear.bn.bn)
         return sub_layer
 
@@ -193,29 +203,25 @@ class DynamicMBConvLayer(MyModule):
             target_width = round(max(self.in_channel_list) * sorted_expand_list[expand_ratio_stage])
             importance[target_width:] = torch.arange(0, target_width - importance.size(0), -1)
         _, sorted_idx = torch.sort(importance, dim=0, descending=True)
-        pl = self.point_linear.conv.conv
-        pl.weight.data = torch.index_select(pl.weight.data, 1, sorted_idx)
+        # every tensor indexed by the middle channel follows the new order
+        _permute(self.point_linear.conv.conv.weight, 1, sorted_idx)
         adjust_bn_according_to_idx(self.depth_conv.bn.bn, sorted_idx)
-        dw = self.depth_conv.conv.conv
-        dw.weight.data = torch.index_select(dw.weight.data, 0, sorted_idx)
+        _permute(self.depth_conv.conv.conv.weight, 0, sorted_idx)
         if self.use_se:
-            # expand: output dim follows the middle channels; reduce: input dim; then the SE middle channels are
-            # sorted by their own importance (dynamic_layers.py:175-189)
-            se_expand, se_reduce = self.depth_conv.se.fc.expand, self.depth_conv.se.fc.reduce
-            se_expand.weight.data = torch.index_select(se_expand.weight.data, 0, sorted_idx)
-            se_expand.bias.data = torch.index_select(se_expand.bias.data, 0, sorted_idx)
-            se_reduce.weight.data = torch.index_select(se_reduce.weight.data, 1, sorted_idx)
-            se_importance = torch.sum(torch.abs(se_expand.weight.data), dim=(0, 2, 3))
-            _, se_idx = torch.sort(se_importance, dim=0, descending=True)
-            se_expand.weight.data = torch.index_select(se_expand.weight.data, 1, se_idx)
-            se_reduce.weight.data = torch.index_select(se_reduce.weight.data, 0, se_idx)
-            se_reduce.bias.data = torch.index_select(se_reduce.bias.data, 0, se_idx)
-        if self.inverted_bottleneck is not None:
-            adjust_bn_according_to_idx(self.inverted_bottleneck.bn.bn, sorted_idx)
-            ib = self.inverted_bottleneck.conv.conv
-            ib.weight.data = torch.index_select(ib.weight.data, 0, sorted_idx)
-            return None
-        return sorted_idx
+            fc = self.depth_conv.se.fc
+            _permute(fc.expand.weight, 0, sorted_idx)
+            _permute(fc.expand.bias, 0, sorted_idx)
+            _permute(fc.reduce.weight, 1, sorted_idx)
+            # ... and the squeeze channels are ranked by their own importance (dynamic_layers.py:175-189)
+            se_rank = torch.sort(torch.sum(torch.abs(fc.expand.weight.data), dim=(0, 2, 3)), dim=0, descending=True)[1]
+            _permute(fc.expand.weight, 1, se_rank)
+            _permute(fc.reduce.weight, 0, se_rank)
+            _permute(fc.reduce.bias, 0, se_rank)
+        if self.inverted_bottleneck is None:
+            return sorted_idx
+        adjust_bn_according_to_idx(self.inverted_bottleneck.bn.bn, sorted_idx)
+        _permute(self.inverted_bottleneck.conv.conv.weight, 0, sorted_idx)
+        return None
 
 
 class DynamicConvLayer(MyModule):
@@ -283,50 +289,4 @@ class DynamicConvLayer(MyModule):
         return sub_layer
 
 
-class DynamicLinearLayer(MyModule):
-    """dynamic_layers.py:270-322: [dropout ->] DynamicLinear over the active input width."""
-
-    def __init__(self, in_features_list, out_features, bias=True, dropout_rate=0):
-        super().__init__()
-        self.in_features_list = in_features_list
-        self.out_features = out_features
-        self.bias = bias
-        self.dropout_rate = dropout_rate
-        if self.dropout_rate > 0:
-            self.dropout = nn.Dropout(self.dropout_rate, inplace=True)
-        else:
-            self.dropout = None
-        self.linear = DynamicLinear(max_in_features=max(self.in_features_list), max_out_features=self.out_features,
-                                    bias=self.bias)
-
-    def forward(self, x):
-        if self.dropout is not None:
-            x = self.dropout(x)
-        return self.linear(x)
-
-    @property
-    def module_str(self):
-        return 'DyLinear(%d)' % self.out_features
-
-    @property
-    def config(self):
-        return {
-            'name': DynamicLinear.__name__,      # (sic) the reference stores the op's class name here
-            'in_features_list': self.in_features_list,
-            'out_features': self.out_features,
-            'bias': self.bias,
-        }
-
-    @staticmethod
-    def build_from_config(config):
-        return DynamicLinearLayer(**config)
-
-    def get_active_subnet(self, in_features, preserve_weight=True):
-        sub_layer = LinearLayer(in_features, self.out_features, self.bias, dropout_rate=self.dropout_rate)
-        sub_layer = sub_layer.to(get_net_device(self))
-        if not preserve_weight:
-            return sub_layer
-        sub_layer.linear.weight.data.copy_(self.linear.linear.weight.data[:self.out_features, :in_features])
-        if self.bias:
-            sub_layer.linear.bias.data.copy_(self.linear.linear.bias.data[:self.out_features])
-        return sub_layer
+from .dynamic_linear import DynamicLinearLayer  # noqa: E402,F401  (re-exported: the reference defines it in this module)
