@@ -73,13 +73,14 @@ class FusedAdam:
 
     def step(self):
         assert [p.data_ptr() for p in self.params] == self._ptrs, 'parameters were re-allocated: rebuild FusedAdam'
-        ptrs = []
+        ptrs, touched = [], []
         for p in self.params:
             if p.grad is None:
                 ptrs.append(0)
             else:
                 assert p.grad.dtype == torch.float32 and p.grad.is_contiguous()
                 ptrs.append(p.grad.data_ptr())
+                touched.append(p)
         if torch.cuda.is_current_stream_capturing():
             # CUDA-graph capture of a whole training step: the gradient buffers live in the graph's private pool, so
             # their addresses are the same on every replay; the table is uploaded from a pinned buffer that is not
@@ -94,6 +95,10 @@ class FusedAdam:
                                       self._chunks.shape[0], self._grad_dev.data_ptr(), self._steps.data_ptr(),
                                       float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps),
                                       B.stream_ptr(dev)))
+        # the kernel writes the parameters through raw pointers: tell autograd / the modules' derived 16-bit weight
+        # caches (keyed on Tensor._version) that these tensors changed, as an in-place torch op would have
+        if touched:
+            torch.autograd.graph.increment_version(touched)
 
     def set_lr(self, lr):
         """adjust_learning_rate / warmup_adjust_learning_rate write param_group['lr'] (sr_run_manager.py:78-90)."""
