@@ -409,7 +409,10 @@ def _conv_bwd_impl(x, w, cin, cout, ks, dy, need_dx, need_dw):
             key = (w.data_ptr(), w._version, tuple(w.shape), cin, cout, ks, str(w.device), dy.dtype)
             if cache._key != key:
                 cin_pad_b, cout_pad_b = cout, (cin + 15) // 16 * 16
-                buf = torch.empty((ks * ks, cout_pad_b, cin_pad_b), dtype=dy.dtype, device=w.device)
+                buf = cache._buf
+                if (buf is None or tuple(buf.shape) != (ks * ks, cout_pad_b, cin_pad_b) or buf.dtype != dy.dtype
+                        or buf.device != w.device):
+                    buf = torch.empty((ks * ks, cout_pad_b, cin_pad_b), dtype=dy.dtype, device=w.device)
                 last = (ks - 1) * sh + (ks - 1) * sw
                 B.check(L.ofa_pack_weight_16(w.data_ptr() + 4 * last, si, so, -sh, -sw, cout, cin, ks, cin_pad_b,
                                              cout_pad_b, B.STORE_PLAIN, B.dtype_code(dy.dtype), buf.data_ptr(), st))
@@ -756,7 +759,10 @@ class PackedWeightCache:
         if key != self._key:
             cin_pad = (cin + 63) // 64 * 64
             cout_pad = (cout + 15) // 16 * 16
-            buf = torch.empty((ks * ks, cout_pad, cin_pad), dtype=dtype, device=w.device)
+            shape = (ks * ks, cout_pad, cin_pad)
+            buf = self._buf
+            if buf is None or tuple(buf.shape) != shape or buf.dtype != dtype or buf.device != w.device:
+                buf = torch.empty(shape, dtype=dtype, device=w.device)   # else: repack in place (stream-ordered)
             so, si, sh, sw = w.stride()
             B.check(B.lib().ofa_pack_weight_16(B.fptr(w), so, si, sh, sw, cin, cout, ks, cin_pad, cout_pad,
                                                store, B.dtype_code(dtype), buf.data_ptr(), _stream(w)))
