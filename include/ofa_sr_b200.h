@@ -216,6 +216,12 @@ typedef struct OfaMBConvArgs {
 
 int64_t ofa_mbconv_workspace_bytes(int32_t n, int32_t h, int32_t w, int32_t cin, int32_t mid,
                                    int32_t cout);
+/* impl: OFA_IMPL_AUTO runs the planar tcgen05 path (expand -> Toeplitz depthwise -> project on channel-planar 16-bit
+ * intermediates) when cin = cout = 64, mid % 64 == 0, W % 8 == 0 AND the planes are frame-sized (H * W >= 8192 pixels
+ * filling >= 25 % of the 128 (64) x 112-pixel depthwise tiles): the depthwise rebuilds its filter matrices per channel
+ * plane, so batches of small patches run faster on the three NHWC kernels, which AUTO picks otherwise.
+ * OFA_IMPL_FAST forces the planar path whenever it is supported, OFA_IMPL_NHWC the NHWC kernels, OFA_IMPL_SIMT the
+ * exact CUDA-core kernels. */
 int ofa_mbconv_fwd(const OfaMBConvArgs* a, int32_t impl, void* stream);
 
 /* The three stages of ofa_mbconv_fwd's planar tcgen05 path (cin = cout = 64, mid % 64 == 0, W % 8 == 0),
