@@ -212,6 +212,8 @@ typedef struct OfaMBConvArgs {
   int32_t mid_dtype; /* storage of the two expanded intermediates on the planar tensor-core path:
                         0 = default (OFA_F16: they are ReLU6-clamped, fp16 keeps 3 more mantissa bits),
                         OFA_BF16 or OFA_F16 */
+  const void* w_exp_packed;  /* optional (both or neither): the block's weights already packed for the planar path by */
+  const void* w_proj_packed; /* ofa_mbconv_pack_weights with the same trunk / mid formats; NULL = pack per call       */
 } OfaMBConvArgs;
 
 int64_t ofa_mbconv_workspace_bytes(int32_t n, int32_t h, int32_t w, int32_t cin, int32_t mid,

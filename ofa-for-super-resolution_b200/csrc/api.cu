@@ -287,8 +287,13 @@ int ofa_mbconv_fwd(const OfaMBConvArgs* a, int32_t impl, void* stream) {
     const int tf16 = a->x.dtype == OFA_F16 ? 1 : 0;
     const int HW = a->x.h * a->x.w;
     const int mid_pad = (a->mid + 127) / 128 * 128;
-    if ((rc = launch_pack_block_weights(a->w_exp, a->w_exp_so, a->w_exp_si, a->w_proj, a->w_proj_so, a->w_proj_si,
-                                        a->cin, a->mid, a->cout, mid_pad, tf16, f16, wexp_p, wproj_p, st))) return rc;
+    if (a->w_exp_packed && a->w_proj_packed) {            // the caller keeps a packed copy (valid until its weights change)
+      wexp_p = const_cast<void*>(a->w_exp_packed);
+      wproj_p = const_cast<void*>(a->w_proj_packed);
+    } else if ((rc = launch_pack_block_weights(a->w_exp, a->w_exp_so, a->w_exp_si, a->w_proj, a->w_proj_so, a->w_proj_si,
+                                               a->cin, a->mid, a->cout, mid_pad, tf16, f16, wexp_p, wproj_p, st))) {
+      return rc;
+    }
     if ((rc = launch_expand_planar(a->x.ptr, t1, wexp_p, a->x.n, HW, a->mid, tf16, f16, &a->bn_exp, a->act, st)))
       return rc;
     if ((rc = launch_dw_planar(t1, t2, a->x.n, a->mid, a->x.h, a->x.w, a->w_dw, a->kmax, a->m75, a->m53,

@@ -53,7 +53,8 @@ class OfaMBConvArgs(Structure):
                 ('w_proj', c_void_p), ('w_proj_so', c_int64), ('w_proj_si', c_int64),
                 ('cin', c_int32), ('mid', c_int32), ('cout', c_int32), ('ks', c_int32), ('act', c_int32),
                 ('bn_exp', OfaBn), ('bn_dw', OfaBn), ('bn_proj', OfaBn),
-                ('add_residual', c_int32), ('ws', c_void_p), ('ws_bytes', c_int64), ('mid_dtype', c_int32)]
+                ('add_residual', c_int32), ('ws', c_void_p), ('ws_bytes', c_int64), ('mid_dtype', c_int32),
+                ('w_exp_packed', c_void_p), ('w_proj_packed', c_void_p)]
 
 
 # every symbol include/ofa_sr_b200.h declares: name -> (restype, argtypes)

@@ -116,7 +116,8 @@ class DynamicMBConvLayer(MyModule):
                             and (residual is None or residual is x) and OF._state['impl'] != B.IMPL_SIMT)
                 if fused_ok:
                     return OF.mbconv_infer(x, exp.conv.weight, dwm.conv.weight, m75, m53, w_pl, in_channel, mid,
-                                           cout, ks, transform_on, act, bn_exp, bn_dw, bn_pl, residual is not None)
+                                           cout, ks, transform_on, act, bn_exp, bn_dw, bn_pl, residual is not None,
+                                           pack_cache=self.__dict__.setdefault('_planar_pack', {}))
                 h = OF.conv_bn_act_infer(x, exp.conv.weight, in_channel, mid, 1, bn_exp, act, cache=exp._packed)
             else:
                 mid, h = in_channel, x

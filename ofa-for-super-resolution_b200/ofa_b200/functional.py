@@ -831,7 +831,7 @@ def _bn_struct(bn):
 
 
 def mbconv_infer(x, w_exp, w_dw, m75, m53, w_proj, cin, mid, cout, ks, transform_on, act, bn_exp, bn_dw,
-                 bn_proj, add_residual):
+                 bn_proj, add_residual, pack_cache=None):
     """Whole inference MBConv block (expand -> dw -> project [+x]) through ofa_mbconv_fwd; needs
     NHWC-dense bf16 x.  Returns NHWC bf16."""
     n, _, h, w = x.shape
@@ -868,8 +868,35 @@ def mbconv_infer(x, w_exp, w_dw, m75, m53, w_proj, cin, mid, cout, ks, transform
     a.add_residual = int(bool(add_residual))
     a.ws, a.ws_bytes = ws.data_ptr(), ws_bytes
     a.mid_dtype = _state['mid_dtype']
+    if planar and pack_cache is not None:
+        we, wp = _planar_packed_weights(pack_cache, w_exp, w_proj, mid, x.dtype)
+        a.w_exp_packed, a.w_proj_packed = we.data_ptr(), wp.data_ptr()
     B.check(L.ofa_mbconv_fwd(byref(a), _state['impl'], _stream(x)))
     return y
+
+
+def _planar_packed_weights(cache, w_exp, w_proj, mid, trunk_dtype):
+    """Planar-format 16-bit copies of a block's (expand, project) weight slices.  `cache` is a dict OWNED BY THE MODULE
+    (one entry per active width and format pair), rebuilt when either fp32 master changes: Tensor._version moves on
+    optimizer steps (FusedAdam bumps it), load_state_dict and re_organize_middle_weights; data_ptr on .to(device).
+    A frame used to re-pack all 14 blocks' weights on every forward."""
+    mdt = _state['mid_dtype']
+    key = (mid, trunk_dtype, mdt)
+    ver = (w_exp.data_ptr(), w_proj.data_ptr(), w_exp._version, w_proj._version, str(w_exp.device))
+    hit = cache.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1], hit[2]
+    tdt = torch.float16 if mdt in (0, B.OFA_F16) else torch.bfloat16
+    if hit is not None and hit[1].device == w_exp.device:
+        we, wp = hit[1], hit[2]                      # same shapes: repack in place (stream-ordered)
+    else:
+        we = torch.empty(((mid + 127) // 128 * 128, 64), dtype=trunk_dtype, device=w_exp.device)
+        wp = torch.empty((64, mid), dtype=tdt, device=w_exp.device)
+    B.check(B.lib().ofa_mbconv_pack_weights(B.fptr(w_exp), w_exp.stride(0), w_exp.stride(1), B.fptr(w_proj),
+                                            w_proj.stride(0), w_proj.stride(1), mid, B.dtype_code(trunk_dtype),
+                                            B.dtype_code(tdt), we.data_ptr(), wp.data_ptr(), _stream(w_exp)))
+    cache[key] = (ver, we, wp)
+    return we, wp
 
 
 def planar_supported(x, cin, mid, cout):
