@@ -25,7 +25,7 @@ for h, w, seed in cases:
     img = synth(h, w, seed)
     pil = Image.fromarray(img, 'RGB')
     out['img_%dx%d' % (h, w)] = img
-    for opt in (2, 4):
+    for opt in (2, 4, 8):        # get_transform_L accepts 2, 4 and 8 (div2k_setxx.py:382); the data sets use 2 and 4
         lo = get_transform_L(opt=opt)(pil)
         out['down%d_%dx%d' % (opt, h, w)] = np.asarray(lo)
         out['down%d_tensor_%dx%d' % (opt, h, w)] = T.ToTensor()(lo).numpy()

@@ -22,7 +22,7 @@ def prep():
 @pytest.mark.parametrize('hw', CASES)
 def test_oracle_bicubic_matches_pillow(prep, hw):
     img = prep['img_' + hw]
-    for opt in (2, 4):
+    for opt in (2, 4, 8):
         got = P.scale_down(img, opt)
         assert np.array_equal(got, prep['down%d_%s' % (opt, hw)])
         assert np.array_equal(P.to_tensor(got), prep['down%d_tensor_%s' % (opt, hw)])
@@ -92,7 +92,7 @@ def dev():
 def test_gpu_bicubic_matches_pillow(dev, prep, hw):
     from ofa_b200 import data as D
     img = torch.from_numpy(prep['img_' + hw]).to(dev)[None].contiguous()
-    for opt in (2, 4):
+    for opt in (2, 4, 8):
         ref = prep['down%d_%s' % (opt, hw)]
         got, got_u8 = D.bicubic_resize(img, ref.shape[0], ref.shape[1], want_u8=True)
         assert np.array_equal(got_u8[0].cpu().numpy(), ref)
