@@ -356,14 +356,16 @@ def _conv_out(x, cout, store, dtype, nchw=False):
     return torch.empty(shape, dtype=dtype, device=x.device, memory_format=torch.channels_last)
 
 
-_train_caches = {}
-
-
 def _train_cache(w, kind):
-    key = (w.data_ptr(), kind)
-    c = _train_caches.get(key)
+    """The packed 16-bit copies of a weight for the training path live ON the parameter object (one PackedWeightCache
+    per layout `kind`), so their lifetime is the parameter's: a global table keyed by data_ptr would hand a new
+    network the previous network's weights whenever the allocator reuses an address."""
+    packs = w.__dict__.get('_ofa_packs')
+    if packs is None:
+        packs = w.__dict__['_ofa_packs'] = {}
+    c = packs.get(kind)
     if c is None:
-        c = _train_caches[key] = PackedWeightCache()
+        c = packs[kind] = PackedWeightCache()
     return c
 
 
@@ -823,7 +825,6 @@ def dw_bn_act_infer(x, w7, m75, m53, ks, transform_on, bn, act):
     return y
 
 
-_prof_caches = {}
 
 
 def _bn_struct(bn):
@@ -844,8 +845,8 @@ def mbconv_infer(x, w_exp, w_dw, m75, m53, w_proj, cin, mid, cout, ks, transform
                                      bn_proj, add_residual)
     if _profiler is not None:
         # same kernels, issued one by one so each gets its own event pair
-        c1 = _prof_caches.setdefault((w_exp.data_ptr(), 0), PackedWeightCache())
-        c2 = _prof_caches.setdefault((w_proj.data_ptr(), 1), PackedWeightCache())
+        c1 = _train_cache(w_exp, ('prof', 0))
+        c2 = _train_cache(w_proj, ('prof', 1))
         t = conv_bn_act_infer(x, w_exp, cin, mid, 1, bn_exp, act, cache=c1)
         t = dw_bn_act_infer(t, w_dw, m75, m53, ks, transform_on, bn_dw, act)
         return conv_bn_act_infer(t, w_proj, mid, cout, 1, bn_proj, B.ACT_NONE, residual=x if add_residual else None,
