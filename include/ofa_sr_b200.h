@@ -157,6 +157,19 @@ int ofa_pack_weight_16(const float* w, int64_t w_so, int64_t w_si, int64_t w_sh,
                        int32_t cin, int32_t cout, int32_t ks, int32_t cin_pad, int32_t cout_pad,
                        int32_t store, int32_t dtype, void* out, void* stream);
 
+/* Many packs in ONE launch: `jobs_device` is a DEVICE array of `njobs` OfaPackJob records (each is the argument
+ * list of ofa_pack_weight_16).  The drop-in modules re-derive every 16-bit weight copy a forward pass uses from
+ * the fp32 masters at the start of that pass with one such launch, so a copy can never be stale -- whatever
+ * wrote the master (optimizer step, load_state_dict, `w.data.copy_()`, ofa/utils.py:134-155 init_model,
+ * elastic_nn/utils.py:76-82 adjust_bn_according_to_idx / dynamic_layers.py:156-199 re-sorting). */
+typedef struct OfaPackJob {
+  const float* w;
+  int64_t w_so, w_si, w_sh, w_sw;
+  int32_t cin, cout, ks, cin_pad, cout_pad, store, dtype, reserved;
+  void* out;
+} OfaPackJob;
+int ofa_pack_weights_multi(const OfaPackJob* jobs_device, int32_t njobs, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * (a5) DynamicBatchNorm2d.bn_forward in TRAINING mode — dynamic_op.py:148-167
  *   stats : per-channel batch mean and BIASED variance over N*H*W (what F.batch_norm normalises with)

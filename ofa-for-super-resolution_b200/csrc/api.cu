@@ -214,6 +214,14 @@ int ofa_pack_weight_16(const float* w, int64_t w_so, int64_t w_si, int64_t w_sh,
                             dtype == OFA_F16 ? 1 : 0, out, (cudaStream_t)stream);
 }
 
+int ofa_pack_weights_multi(const OfaPackJob* jobs_device, int32_t njobs, void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  OFA_REQUIRE(njobs >= 0 && njobs <= 65535, "ofa_pack_weights_multi: njobs out of range");
+  OFA_REQUIRE(njobs == 0 || jobs_device, "ofa_pack_weights_multi: null job table");
+  return launch_pack_weights_multi(jobs_device, njobs, (cudaStream_t)stream);
+}
+
 int ofa_bn_stats(const OfaTensor4* x, float* mean, float* var, void* stream) {
   int rc = require_device();
   if (rc) return rc;

@@ -368,7 +368,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
           if (two) ptx::tmem_ld16(t_addr + (uint32_t)(j + 16), v + 16);
           ptx::tmem_ld_wait();
           const int op0 = col0 + j;
-          if (p.vec_store && j + 32 <= p.BN && op0 + 32 <= p.cout) {
+          // (a 32-channel block must stay inside ONE PixelShuffle sub-pixel group of cout / 4 channels: cout = 64 or 192
+          // have groups of 16 / 48 channels and take the 16-channel emit16 path)
+          if (p.vec_store && j + 32 <= p.BN && op0 + 32 <= p.cout &&
+              (p.store != OFA_STORE_PIXELSHUFFLE2 || ((p.cout >> 2) & 31) == 0)) {
             // ---- coalesced path: thread = pixel row computes, then the warp re-reads the 32 x 64-byte
             // block through a swizzled staging tile so each store instruction writes 8 x 64 contiguous bytes
             int sub = 0, oc0 = op0;

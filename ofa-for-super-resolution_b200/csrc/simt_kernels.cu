@@ -269,6 +269,37 @@ int launch_pack_weight(const float* w, long long w_so, long long w_si, long long
   return check_launch("pack_weight_kernel");
 }
 
+// the same pack for a device-resident list of jobs (blockIdx.y = job): one launch refreshes every 16-bit weight copy a
+// forward pass is going to use
+__global__ void pack_weights_multi_kernel(const OfaPackJob* __restrict__ jobs) {
+  const OfaPackJob j = jobs[blockIdx.y];
+  const int ks = j.ks, cin_pad = j.cin_pad, cout_pad = j.cout_pad;
+  const int f16 = j.dtype == OFA_F16 ? 1 : 0;
+  const float* __restrict__ w = j.w;
+  uint16_t* __restrict__ out = reinterpret_cast<uint16_t*>(j.out);
+  const int total = ks * ks * cout_pad * cin_pad;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int ci = i % cin_pad;
+    const int r = i / cin_pad;
+    const int o = r % cout_pad;
+    const int tap = r / cout_pad;
+    const int ky = tap / ks, kx = tap - ky * ks;
+    float v = 0.f;
+    if (ci < j.cin && o < j.cout) {
+      int oo = o;
+      if (j.store == OFA_STORE_PIXELSHUFFLE2) { const int q = j.cout >> 2; oo = 4 * (o % q) + o / q; }
+      v = w[oo * j.w_so + ci * j.w_si + ky * j.w_sh + kx * j.w_sw];
+    }
+    out[i] = cvt16(v, f16);
+  }
+}
+
+int launch_pack_weights_multi(const OfaPackJob* jobs_device, int njobs, cudaStream_t st) {
+  if (njobs <= 0) return OFA_OK;
+  pack_weights_multi_kernel<<<dim3(24, (unsigned)njobs), 256, 0, st>>>(jobs_device);
+  return check_launch("pack_weights_multi_kernel");
+}
+
 // =================================================================================================
 // elementwise: y = store(act(affine(x))) + residual
 // =================================================================================================

@@ -57,6 +57,12 @@ class OfaMBConvArgs(Structure):
                 ('w_exp_packed', c_void_p), ('w_proj_packed', c_void_p)]
 
 
+class OfaPackJob(Structure):
+    _fields_ = [('w', c_void_p), ('w_so', c_int64), ('w_si', c_int64), ('w_sh', c_int64), ('w_sw', c_int64),
+                ('cin', c_int32), ('cout', c_int32), ('ks', c_int32), ('cin_pad', c_int32), ('cout_pad', c_int32),
+                ('store', c_int32), ('dtype', c_int32), ('reserved', c_int32), ('out', c_void_p)]
+
+
 # every symbol include/ofa_sr_b200.h declares: name -> (restype, argtypes)
 _T4 = POINTER(OfaTensor4)
 _EP = POINTER(OfaEpilogue)
@@ -77,6 +83,7 @@ SYMBOLS = {
                                        c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     'ofa_pack_weight_16': (c_int32, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int32, c_int32,
                                      c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    'ofa_pack_weights_multi': (c_int32, [c_void_p, c_int32, c_void_p]),
     'ofa_bn_stats': (c_int32, [_T4, c_void_p, c_void_p, c_void_p]),
     'ofa_bn_update_running': (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_float, c_int32,
                                         c_void_p, c_void_p]),
@@ -196,17 +203,28 @@ def fptr(t):
 _raw_stream = getattr(torch._C, '_cuda_getCurrentRawStream', None)
 
 
+_raw_device = getattr(torch._C, '_cuda_getDevice', None)
+
+
 def stream_ptr(device=None):
     """cudaStream_t of torch's current stream on `device` (the stream every library call launches on).  The raw
     lookup costs ~0.3 us; torch.cuda.current_stream(device).cuda_stream builds a Stream object (~7 us), which at
-    ~250 library calls per training step was 13 % of the eager step."""
-    if _raw_stream is not None:
-        if device is None:
+    ~250 library calls per training step was 13 % of the eager step.
+
+    The library launches on the CURRENT device (kernels, cudaMallocAsync scratch, SM count), so when the tensor lives
+    on another device -- `net.to('cuda:1')` while cuda:0 is current; stock torch modules guard against this themselves
+    -- the current device is switched to the tensor's before the call (every library call fetches its stream here
+    first)."""
+    if device is None:
+        idx = torch.cuda.current_device()
+    else:
+        idx = device.index if isinstance(device, torch.device) else int(device)
+        if idx is None:
             idx = torch.cuda.current_device()
-        else:
-            idx = device.index if isinstance(device, torch.device) else int(device)
-            if idx is None:
-                idx = torch.cuda.current_device()
+    cur = _raw_device() if _raw_device is not None else torch.cuda.current_device()
+    if idx != cur:
+        torch.cuda.set_device(idx)
+    if _raw_stream is not None:
         return _raw_stream(idx)
     return torch.cuda.current_stream(device).cuda_stream
 

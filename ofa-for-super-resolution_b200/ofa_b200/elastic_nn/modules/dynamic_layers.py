@@ -85,6 +85,7 @@ class DynamicMBConvLayer(MyModule):
         self._act_code, _ = _split_act(self.act_func)
 
     # ---------------------------------------------------------------------------------------------
+    @OF.scoped_forward()
     def forward(self, x, residual=None):
         in_channel = x.size(1)
         if self.inverted_bottleneck is not None:
@@ -198,6 +199,7 @@ class DynamicMBConvLayer(MyModule):
     def re_organize_middle_weights(self, expand_ratio_stage=0):
         """Sort the middle channels by the L1 norm of the project weights, descending
         (dynamic_layers.py:156-199) so every narrower expand ratio keeps the most important ones."""
+        OF.invalidate_packed_weights()
         importance = torch.sum(torch.abs(self.point_linear.conv.conv.weight.data), dim=(0, 2, 3))
         if expand_ratio_stage > 0:
             sorted_expand_list = sorted(copy.deepcopy(self.expand_ratio_list), reverse=True)
@@ -249,6 +251,7 @@ class DynamicConvLayer(MyModule):
         self.active_out_channel = max(self.out_channel_list)
         self._act_code, _ = _split_act(self.act_func)
 
+    @OF.scoped_forward()
     def forward(self, x):
         self.conv.active_out_channel = self.active_out_channel
         cin, cout = x.size(1), self.active_out_channel

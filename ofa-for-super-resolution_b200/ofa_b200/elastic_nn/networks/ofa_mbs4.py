@@ -118,6 +118,7 @@ class OFAMobileNetS4(ElasticSRSuperNet):
             return None
         return c, a, b
 
+    @OF.scoped_forward(OF.pack_plan_signature)
     def forward(self, x):
         split = self._column_split(x)
         if split is not None:

@@ -13,6 +13,7 @@ import torch.nn as nn
 from ...layers import ConvLayer, IdentityLayer, MobileInvertedResidualBlock
 from ...utils import make_divisible, int2list
 from ..modules.dynamic_layers import DynamicMBConvLayer
+from ... import functional as OF
 from .supernet_base import ElasticSRSuperNet
 
 __all__ = ['OFAMobileNetX4']
@@ -99,6 +100,7 @@ class OFAMobileNetX4(ElasticSRSuperNet):
     def name():
         return 'OFAMobileNetX4'
 
+    @OF.scoped_forward(OF.pack_plan_signature)
     def forward(self, x):
         # encoder
         x = self._run_groups(x, 0, 1)

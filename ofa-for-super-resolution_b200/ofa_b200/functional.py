@@ -408,18 +408,8 @@ def _conv_bwd_impl(x, w, cin, cout, ks, dy, need_dx, need_dw):
         if _is_half_nhwc(dy) and dy.dtype == x.dtype and cout % 64 == 0 and _state['train_dtype'] != torch.float32:
             # dX = conv(dY, W^T rotated 180 deg): pack W[o, i, ks-1-ky, ks-1-kx] as a (cout -> cin) weight
             cache = _train_cache(w, ('b', cin, cout))
-            key = (w.data_ptr(), w._version, tuple(w.shape), cin, cout, ks, str(w.device), dy.dtype)
-            if cache._key != key:
-                cin_pad_b, cout_pad_b = cout, (cin + 15) // 16 * 16
-                buf = cache._buf
-                if (buf is None or tuple(buf.shape) != (ks * ks, cout_pad_b, cin_pad_b) or buf.dtype != dy.dtype
-                        or buf.device != w.device):
-                    buf = torch.empty((ks * ks, cout_pad_b, cin_pad_b), dtype=dy.dtype, device=w.device)
-                last = (ks - 1) * sh + (ks - 1) * sw
-                B.check(L.ofa_pack_weight_16(w.data_ptr() + 4 * last, si, so, -sh, -sw, cout, cin, ks, cin_pad_b,
-                                             cout_pad_b, B.STORE_PLAIN, B.dtype_code(dy.dtype), buf.data_ptr(), st))
-                cache._key, cache._buf, cache.cin_pad, cache.cout_pad = key, buf, cin_pad_b, cout_pad_b
-            a = _conv_args(dy, dx, None, cout, cin, ks, B.STORE_PLAIN, None, cache._buf, cache.cin_pad, cache.cout_pad)
+            w16 = cache.get(w, cin, cout, ks, B.STORE_PLAIN, dy.dtype, rotated=True, backward=True)
+            a = _conv_args(dy, dx, None, cout, cin, ks, B.STORE_PLAIN, None, w16, cache.cin_pad, cache.cout_pad)
             B.check(L.ofa_conv_fwd(byref(a), B.IMPL_FAST, st))
         elif (_state['train_dtype'] != torch.float32 and cout <= 4 and cin == 64 and ks in (3, 5)
               and dx.dtype != torch.float32 and w.is_contiguous()):
@@ -747,29 +737,190 @@ def pixel_unshuffle2(x):
 # fused inference calls
 # =================================================================================================
 
+# ---- derived 16-bit weight copies ---------------------------------------------------------------------------------
+# The tensor-core kernels read packed 16-bit copies of the active fp32 weight slices.  A copy is NEVER trusted across
+# forward passes: `Tensor._version` (what round 1 keyed on) does not move for `w.data.copy_()` / `w.data.normal_()`
+# (ofa/utils.py:134-155 init_model, elastic_nn/utils.py:76-82), raw-pointer writers or NCCL broadcasts, so any cache
+# keyed on it can serve stale weights.  Instead every top-level forward pass (`forward_scope`) starts a new EPOCH on
+# its device and a copy is fresh only if it was written in the current epoch:
+#   * the first pass with a given (sub-network, shape, dtype) signature packs each copy on first use and records the
+#     jobs as a PLAN; every later pass with that signature re-derives ALL of its copies from the fp32 masters with ONE
+#     multi-job launch (ofa_pack_weights_multi: ~16 MB of traffic, a few microseconds) before the first layer runs --
+#     inside a captured CUDA graph too, so graph replays follow weight updates;
+#   * passes without a plan (training with a freshly sampled sub-network, stand-alone modules) pack on first use per
+#     epoch, one small launch per copy -- what an optimizer step forced anyway;
+#   * the backward pass belongs to the epoch of the last forward on that device.
+# Slots are per device, so nn.DataParallel replicas (shallow module copies sharing this object, one thread per GPU,
+# sr_run_manager.py:197-198) never hand each other buffers.
+import threading
+
+_tls = threading.local()
+_epochs = {}                 # device index -> epoch counter
+_generation = [0]            # bumped by invalidate_packed_weights()
+_tables_keepalive = []       # device job tables are never freed: a captured CUDA graph may still replay them
+_MAX_PLANS = 64
+
+
+def invalidate_packed_weights():
+    """Explicitly drop every derived 16-bit weight copy (they are re-derived on next use).  Not needed for correctness
+    -- every forward pass re-derives its copies -- kept as the explicit hook init_model / load_state_dict /
+    re_organize_middle_weights / broadcast_parameters call."""
+    _generation[0] += 1
+
+
+def _token(di):
+    return (_generation[0], _epochs.get(di, 0))
+
+
+def _new_epoch(di):
+    _epochs[di] = _epochs.get(di, 0) + 1
+
+
+class _Plan:
+    __slots__ = ('jobs', 'table', 'n')
+
+    def __init__(self, jobs, device):
+        self.jobs = jobs                                        # [(cache, slot_key, w, wptr, buf, cin_pad, cout_pad)]
+        arr = (B.OfaPackJob * len(jobs))()
+        for k, (cache, key, w, job, buf, cp, op) in enumerate(jobs):
+            arr[k] = job
+        raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        self.table = raw.to(device)
+        _tables_keepalive.append(self.table)
+        self.n = len(jobs)
+
+    def replay(self, di, stream):
+        """Re-derive every copy of the plan (one launch); False when a master moved (plan must be re-recorded)."""
+        for cache, key, w, job, buf, cp, op in self.jobs:
+            if w.data_ptr() != key[0]:
+                return False
+        B.check(B.lib().ofa_pack_weights_multi(self.table.data_ptr(), self.n, stream))
+        tok = _token(di)
+        for cache, key, w, job, buf, cp, op in self.jobs:
+            cache._slots[di] = [key, buf, cp, op, tok]
+        return True
+
+
+class forward_scope:
+    """`with forward_scope(module, x[, signature]):` around a module's forward.  The OUTERMOST scope of a thread starts
+    a new weight epoch on x's device; with a hashable `signature` (networks pass their active sub-network + input
+    shape + dtypes) it replays / records the pack plan described above."""
+
+    def __init__(self, owner, x, signature=None):
+        self.owner, self.x, self.signature = owner, x, signature
+        self.top = False
+        self.rec = None
+
+    def __enter__(self):
+        depth = getattr(_tls, 'depth', 0)
+        _tls.depth = depth + 1
+        x = self.x
+        if depth != 0 or not (torch.is_tensor(x) and x.is_cuda):
+            return self
+        self.top = True
+        di = x.device.index
+        _new_epoch(di)
+        if self.signature is None:
+            return self
+        plans = self.owner.__dict__.setdefault('_ofa_pack_plans', {})
+        pkey = (di, self.signature)
+        plan = plans.get(pkey)
+        if plan is not None:
+            if plan.replay(di, _stream(x)):
+                return self
+            del plans[pkey]
+        if len(plans) < _MAX_PLANS and not torch.cuda.is_current_stream_capturing():
+            self.rec = _tls.rec = []
+        return self
+
+    def __exit__(self, et, ev, tb):
+        _tls.depth -= 1
+        if self.top and self.rec is not None:
+            _tls.rec = None
+            if et is None and self.rec:
+                plans = self.owner.__dict__.setdefault('_ofa_pack_plans', {})
+                plans[(self.x.device.index, self.signature)] = _Plan(self.rec, self.x.device)
+        return False
+
+
+def scoped_forward(signature=None):
+    """Decorator for a module's `forward(self, x, ...)`: runs it inside a forward_scope (nested calls pay one
+    attribute lookup).  `signature(self, x)` -> hashable plan key, or None for no plan."""
+    def wrap(fwd):
+        def forward(self, x, *args, **kwargs):
+            if getattr(_tls, 'depth', 0):
+                return fwd(self, x, *args, **kwargs)
+            sig = signature(self, x) if signature is not None else None
+            with forward_scope(self, x, sig):
+                return fwd(self, x, *args, **kwargs)
+        forward.__doc__ = fwd.__doc__
+        forward.__wrapped__ = fwd
+        return forward
+    return wrap
+
+
+def pack_plan_signature(net, x):
+    """Everything that decides WHICH weight copies a network forward uses: the active sub-network, the input shape and
+    the dtype / dispatch state (a wrong guess only costs speed: copies outside the plan are packed on first use)."""
+    if not (torch.is_tensor(x) and x.is_cuda) or net.training or torch.is_grad_enabled():
+        return None
+    blocks = []
+    for blk in net.blocks:
+        mb = getattr(blk, 'mobile_inverted_conv', None)
+        if mb is not None:
+            blocks.append((getattr(mb, 'active_kernel_size', 0), getattr(mb, 'active_expand_ratio', 0)))
+    return (tuple(x.shape), x.dtype, _state['compute_dtype'], _state['mid_dtype'], _state['impl'], _profiler is None,
+            tuple(net.runtime_depth), tuple(blocks))
+
+
 class PackedWeightCache:
-    """16-bit [tap][cout_pad][cin_pad] copy (in the activation's format) of an active weight slice — a derived cache owned by the
-    module, rebuilt whenever the fp32 master changes (optimizer step / load_state_dict / re-sort)."""
+    """16-bit [tap][cout_pad][cin_pad] copy (in the activation's format) of an active weight slice, owned by the module (or,
+    for the training path, by the parameter).  See the epoch rules above: `get` re-derives the copy unless it was
+    already written during the current forward pass."""
 
     def __init__(self):
-        self._key = None
-        self._buf = None
+        self._slots = {}            # device index -> [key, buf, cin_pad, cout_pad, token]
         self.cin_pad = self.cout_pad = 0
 
-    def get(self, w, cin, cout, ks, store, dtype=torch.bfloat16):
-        key = (w.data_ptr(), w._version, tuple(w.shape), cin, cout, ks, store, str(w.device), dtype)
-        if key != self._key:
+    def get(self, w, cin, cout, ks, store, dtype=torch.bfloat16, cout_pad=None, rotated=False, backward=False):
+        """rotated=True packs the data-gradient weight: W[o, i, ks-1-ky, ks-1-kx] as a (cout -> cin) conv weight, read
+        from the fp32 master through swapped / negative strides.  backward=True marks a call from an autograd backward
+        (it belongs to the epoch of the forward pass that preceded it)."""
+        di = w.device.index
+        if getattr(_tls, 'depth', 0) == 0 and not backward:
+            _new_epoch(di)          # a bare functional call is its own forward pass
+        key = (w.data_ptr(), tuple(w.shape), w.stride(), cin, cout, ks, store, dtype, cout_pad, rotated)
+        slot = self._slots.get(di)
+        tok = _token(di)
+        if slot is not None and slot[0] == key and slot[4] == tok:
+            self.cin_pad, self.cout_pad = slot[2], slot[3]
+            return slot[1]
+        so, si, sh, sw = w.stride()
+        if rotated:
+            p_cin, p_cout = cout, cin
+            cin_pad, c_pad = cout, (cin + 15) // 16 * 16
+            wptr = w.data_ptr() + 4 * ((ks - 1) * sh + (ks - 1) * sw)
+            strides = (si, so, -sh, -sw)
+        else:
+            p_cin, p_cout = cin, cout
             cin_pad = (cin + 63) // 64 * 64
-            cout_pad = (cout + 15) // 16 * 16
-            shape = (ks * ks, cout_pad, cin_pad)
-            buf = self._buf
-            if buf is None or tuple(buf.shape) != shape or buf.dtype != dtype or buf.device != w.device:
-                buf = torch.empty(shape, dtype=dtype, device=w.device)   # else: repack in place (stream-ordered)
-            so, si, sh, sw = w.stride()
-            B.check(B.lib().ofa_pack_weight_16(B.fptr(w), so, si, sh, sw, cin, cout, ks, cin_pad, cout_pad,
-                                               store, B.dtype_code(dtype), buf.data_ptr(), _stream(w)))
-            self._key, self._buf, self.cin_pad, self.cout_pad = key, buf, cin_pad, cout_pad
-        return self._buf
+            c_pad = cout_pad if cout_pad is not None else (cout + 15) // 16 * 16
+            wptr = B.fptr(w)
+            strides = (so, si, sh, sw)
+        shape = (ks * ks, c_pad, cin_pad)
+        buf = slot[1] if slot is not None else None
+        if buf is None or tuple(buf.shape) != shape or buf.dtype != dtype:
+            buf = torch.empty(shape, dtype=dtype, device=w.device)   # else: repack in place (stream-ordered)
+        job = B.OfaPackJob(wptr, strides[0], strides[1], strides[2], strides[3], p_cin, p_cout, ks, cin_pad, c_pad,
+                           store, B.dtype_code(dtype), 0, buf.data_ptr())
+        B.check(B.lib().ofa_pack_weight_16(job.w, job.w_so, job.w_si, job.w_sh, job.w_sw, p_cin, p_cout, ks, cin_pad,
+                                           c_pad, store, job.dtype, job.out, _stream(w)))
+        self._slots[di] = [key, buf, cin_pad, c_pad, tok]
+        self.cin_pad, self.cout_pad = cin_pad, c_pad
+        rec = getattr(_tls, 'rec', None)
+        if rec is not None and not backward:
+            rec.append((self, key, w, job, buf, cin_pad, c_pad))
+        return buf
 
 
 def _bn_epilogue(bn, act, residual):
@@ -877,26 +1028,20 @@ def mbconv_infer(x, w_exp, w_dw, m75, m53, w_proj, cin, mid, cout, ks, transform
 
 
 def _planar_packed_weights(cache, w_exp, w_proj, mid, trunk_dtype):
-    """Planar-format 16-bit copies of a block's (expand, project) weight slices.  `cache` is a dict OWNED BY THE MODULE
-    (one entry per active width and format pair), rebuilt when either fp32 master changes: Tensor._version moves on
-    optimizer steps (FusedAdam bumps it), load_state_dict and re_organize_middle_weights; data_ptr on .to(device).
-    A frame used to re-pack all 14 blocks' weights on every forward."""
+    """Planar-format 16-bit copies of a block's (expand, project) weight slices: expand = [ceil128(mid)][64] in the trunk's
+    format (the UMMA A operand, zero rows above `mid`), project = [64][mid] in the intermediates' format.  Both are plain
+    ks = 1 packs, so they live in PackedWeightCache slots (`cache` is a dict owned by the module) and follow the same
+    epoch / plan rules as every other derived weight copy."""
     mdt = _state['mid_dtype']
-    key = (mid, trunk_dtype, mdt)
-    ver = (w_exp.data_ptr(), w_proj.data_ptr(), w_exp._version, w_proj._version, str(w_exp.device))
-    hit = cache.get(key)
-    if hit is not None and hit[0] == ver:
-        return hit[1], hit[2]
     tdt = torch.float16 if mdt in (0, B.OFA_F16) else torch.bfloat16
-    if hit is not None and hit[1].device == w_exp.device:
-        we, wp = hit[1], hit[2]                      # same shapes: repack in place (stream-ordered)
-    else:
-        we = torch.empty(((mid + 127) // 128 * 128, 64), dtype=trunk_dtype, device=w_exp.device)
-        wp = torch.empty((64, mid), dtype=tdt, device=w_exp.device)
-    B.check(B.lib().ofa_mbconv_pack_weights(B.fptr(w_exp), w_exp.stride(0), w_exp.stride(1), B.fptr(w_proj),
-                                            w_proj.stride(0), w_proj.stride(1), mid, B.dtype_code(trunk_dtype),
-                                            B.dtype_code(tdt), we.data_ptr(), wp.data_ptr(), _stream(w_exp)))
-    cache[key] = (ver, we, wp)
+    ce = cache.get('exp')
+    if ce is None:
+        ce = cache.setdefault('exp', PackedWeightCache())
+    cp = cache.get('proj')
+    if cp is None:
+        cp = cache.setdefault('proj', PackedWeightCache())
+    we = ce.get(w_exp, 64, mid, 1, B.STORE_PLAIN, trunk_dtype, cout_pad=(mid + 127) // 128 * 128)
+    wp = cp.get(w_proj, mid, 64, 1, B.STORE_PLAIN, tdt, cout_pad=64)
     return we, wp
 
 

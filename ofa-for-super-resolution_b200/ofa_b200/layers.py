@@ -87,6 +87,7 @@ class ConvLayer(MyModule):
         self.out_dtype = None
         self.out_nchw = False
 
+    @OF.scoped_forward()
     def forward(self, x, residual=None):
         """`residual` (optional) is added after BN/act/shuffle — the networks use it to fuse their
         in-place long-skip adds (`x += dec_big_skip`, ofa_mbs4.py:159)."""
@@ -280,6 +281,7 @@ class MBInvertedConvLayer(MyModule):
         self._packed_exp = OF.PackedWeightCache()
         self._packed_proj = OF.PackedWeightCache()
 
+    @OF.scoped_forward()
     def forward(self, x, residual=None):
         act, mid = self._act_code, self._feature_dim
         infer = OF.inference_mode_active(self) and not OF.bn_hooked(
@@ -343,6 +345,7 @@ class MobileInvertedResidualBlock(MyModule):
         self.mobile_inverted_conv = mobile_inverted_conv
         self.shortcut = shortcut
 
+    @OF.scoped_forward()
     def forward(self, x):
         if self.mobile_inverted_conv is None or isinstance(self.mobile_inverted_conv, ZeroLayer):
             return x

@@ -173,3 +173,5 @@ def broadcast_parameters(module, src=0, process_group=None):
     import torch.distributed as dist
     for t in list(module.parameters()) + list(module.buffers()):
         dist.broadcast(t.data, src=src, group=process_group)
+    from . import functional as OF
+    OF.invalidate_packed_weights()          # .data writes do not move Tensor._version

@@ -149,6 +149,13 @@ def build_activation(act_func, inplace=True, upscale_factor=2):
     return table[act_func]()
 
 
+def _invalidate_packed_weights():
+    """`.data` writes do not move Tensor._version: tell the operator layer its derived 16-bit weight copies are void
+    (they are re-derived per forward pass anyway; this is the explicit hook)."""
+    from . import functional as OF
+    OF.invalidate_packed_weights()
+
+
 class MyModule(nn.Module):
     def forward(self, x):
         raise NotImplementedError
@@ -171,6 +178,11 @@ class MyNetwork(MyModule):
 
     def zero_last_gamma(self):
         raise NotImplementedError
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        _invalidate_packed_weights()
+        return out
 
     def _bn_modules(self):
         return [m for m in self.modules() if isinstance(m, (nn.BatchNorm2d, nn.BatchNorm1d))]
@@ -205,6 +217,7 @@ class MyNetwork(MyModule):
                 m.weight.data.uniform_(-bound, bound)
                 if m.bias is not None:
                     m.bias.data.zero_()
+        _invalidate_packed_weights()
 
     def get_parameters(self, keys=None, mode='include', exclude_set=None):
         skip = exclude_set or {}
