@@ -56,6 +56,8 @@ extern "C" {
 #define OFA_IMPL_SIMT 1 /* CUDA-core kernels: any layout, fp32 / bf16 / fp16 I/O                */
 #define OFA_IMPL_FAST 2 /* TMA halo tiles (depthwise) / tcgen05+TMEM implicit GEMM (dense conv)  */
 #define OFA_IMPL_NHWC 3 /* ofa_mbconv_fwd only: the three NHWC kernels instead of the planar path */
+#define OFA_IMPL_BAND 4 /* ofa_mbconv_fwd only: force the single-launch band-scheduled block (L2-resident ring)   */
+#define OFA_IMPL_PLANAR3 5 /* ofa_mbconv_fwd only: force the three stand-alone planar kernels (HBM intermediates) */
 
 /* A 4-D activation view: element (n, c, h, w) lives at ptr + n*sn + c*sc + h*sh + w*sw (elements). */
 typedef struct OfaTensor4 {
@@ -231,7 +233,12 @@ typedef struct OfaMBConvArgs {
 
 int64_t ofa_mbconv_workspace_bytes(int32_t n, int32_t h, int32_t w, int32_t cin, int32_t mid,
                                    int32_t cout);
-/* impl: OFA_IMPL_AUTO runs the planar tcgen05 path (expand -> Toeplitz depthwise -> project on channel-planar 16-bit
+/* Frame-sized inputs (>= 128 x 448 pixels) run the planar path as ONE launch (mbconv_band.cu): expand, depthwise and
+ * project execute concurrently as role-specialised persistent CTAs, handing 128 x 112-pixel regions to each other
+ * through ring buffers small enough to stay in the 126 MB L2, so the two expanded intermediates never reach HBM
+ * (dynamic_layers.py:70-84: the reference materialises both, at full size).  OFA_IMPL_BAND forces it on any supported
+ * shape, OFA_IMPL_PLANAR3 forces the three stand-alone kernels.
+ * impl: OFA_IMPL_AUTO runs the planar tcgen05 path (expand -> Toeplitz depthwise -> project on channel-planar 16-bit
  * intermediates) when cin = cout = 64, mid % 64 == 0, W % 8 == 0 AND the planes are frame-sized (H * W >= 8192 pixels
  * filling >= 25 % of the 128 (64) x 112-pixel depthwise tiles): the depthwise rebuilds its filter matrices per channel
  * plane, so batches of small patches run faster on the three NHWC kernels, which AUTO picks otherwise.

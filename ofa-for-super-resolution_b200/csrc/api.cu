@@ -253,12 +253,21 @@ int ofa_affine_act(const OfaTensor4* x, const OfaTensor4* y, const OfaEpilogue* 
   return launch_affine_act(make_tv(x), make_tv(y), make_epi(epi), store, (cudaStream_t)stream);
 }
 
+static int64_t mbconv_act_bytes(int32_t n, int32_t h, int32_t w, int32_t mid) {
+  const int64_t P = (int64_t)n * h * w;
+  const int64_t full = 2 * P * mid * 2;
+  const int64_t nreg = (int64_t)n * ((h + 127) / 128) * ((w + 111) / 112);
+  const int64_t band = mbconv_band_workspace_bytes(w, mid, (int)(nreg < (1 << 24) ? nreg : (1 << 24)));
+  return (full > band ? full : band) + 256;
+}
+
 int64_t ofa_mbconv_workspace_bytes(int32_t n, int32_t h, int32_t w, int32_t cin, int32_t mid, int32_t cout) {
   (void)cin; (void)cout;
   int64_t P = (int64_t)n * h * w;
   int64_t mid_pad = (mid + 63) / 64 * 64;
-  // two bf16 [P, mid] intermediates + three packed bf16 weights (<= 384*64 each, padded) + slack
-  return 2 * P * mid_pad * 2 + 2 * (int64_t)(384 + 64) * 384 * 2 + 4096;
+  // two bf16 [P, mid] intermediates (or the band kernel's ring + counters, whichever is larger) + three packed bf16
+  // weights (<= 384*64 each, padded) + slack
+  return mbconv_act_bytes(n, h, w, (int32_t)mid_pad) + 2 * (int64_t)(384 + 64) * 384 * 2 + 4096;
 }
 
 int ofa_mbconv_fwd(const OfaMBConvArgs* a, int32_t impl, void* stream) {
@@ -283,14 +292,16 @@ int ofa_mbconv_fwd(const OfaMBConvArgs* a, int32_t impl, void* stream) {
   char* ws = reinterpret_cast<char*>(a->ws);
   void* t1 = ws;
   void* t2 = ws + P * a->mid * 2;
-  void* wexp_p = ws + 2 * P * a->mid * 2;
+  const int64_t act_bytes = mbconv_act_bytes(a->x.n, a->x.h, a->x.w, (a->mid + 63) / 64 * 64);
+  void* wexp_p = ws + act_bytes;
   void* wproj_p = reinterpret_cast<char*>(wexp_p) + (int64_t)384 * 384 * 2;
   OFA_REQUIRE(a->mid_dtype == 0 || a->mid_dtype == OFA_BF16 || a->mid_dtype == OFA_F16, "bad mid_dtype %d",
               a->mid_dtype);
 
   // ---- planar tcgen05 path: expand -> Toeplitz depthwise -> project around channel-planar intermediates
+  const bool force_planar = impl == OFA_IMPL_FAST || impl == OFA_IMPL_BAND || impl == OFA_IMPL_PLANAR3;
   if (impl != OFA_IMPL_SIMT && impl != OFA_IMPL_NHWC && mbconv_planar_supported(a) &&
-      (impl == OFA_IMPL_FAST || mbconv_planar_preferred(a))) {
+      (force_planar || mbconv_planar_preferred(a))) {
     const int f16 = (a->mid_dtype == OFA_BF16) ? 0 : 1;
     const int tf16 = a->x.dtype == OFA_F16 ? 1 : 0;
     const int HW = a->x.h * a->x.w;
@@ -302,6 +313,8 @@ int ofa_mbconv_fwd(const OfaMBConvArgs* a, int32_t impl, void* stream) {
                                                a->cin, a->mid, a->cout, mid_pad, tf16, f16, wexp_p, wproj_p, st))) {
       return rc;
     }
+    if (impl != OFA_IMPL_PLANAR3 && mbconv_band_supported(a) && (impl == OFA_IMPL_BAND || mbconv_band_preferred(a)))
+      return launch_mbconv_band(a, wexp_p, wproj_p, f16, ws, act_bytes, st);
     if ((rc = launch_expand_planar(a->x.ptr, t1, wexp_p, a->x.n, HW, a->mid, tf16, f16, &a->bn_exp, a->act, st)))
       return rc;
     if ((rc = launch_dw_planar(t1, t2, a->x.n, a->mid, a->x.h, a->x.w, a->w_dw, a->kmax, a->m75, a->m53,
@@ -309,7 +322,7 @@ int ofa_mbconv_fwd(const OfaMBConvArgs* a, int32_t impl, void* stream) {
     return launch_project_planar(t2, a->add_residual ? a->x.ptr : nullptr, a->y.ptr, wproj_p, a->x.n, HW, a->mid, tf16,
                                  f16, &a->bn_proj, st);
   }
-  if (impl == OFA_IMPL_NHWC) impl = OFA_IMPL_AUTO;
+  if (impl == OFA_IMPL_NHWC || force_planar) impl = impl == OFA_IMPL_FAST ? OFA_IMPL_FAST : OFA_IMPL_AUTO;
   // pack the active weight slices (tiny) — the slice W[:mid,:cin] is read in place from the full parameter
   const int xf16 = a->x.dtype == OFA_F16 ? 1 : 0;
   if ((rc = launch_pack_weight(a->w_exp, a->w_exp_so, a->w_exp_si, 0, 0, a->cin, a->mid, 1, a->cin, a->mid, OFA_STORE_PLAIN, xf16, wexp_p, st))) return rc;

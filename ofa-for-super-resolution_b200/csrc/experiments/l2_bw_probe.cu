@@ -111,5 +111,21 @@ int main() {
       printf("%s working set %5zu MB : %8.1f GB/s (%d passes, %.3f ms)\n", names[mode], mb, moved / ms / 1e6, passes, ms);
     }
   }
+  // is the L2 write (read) rate a per-SM or a chip-wide limit?  32 MB working set, fewer CTAs
+  for (int mode = 0; mode < 2; ++mode) {
+    for (int ctas : {8, 16, 32, 64, 100, sms}) {
+      const size_t bytes = (size_t)32 << 20;
+      const int passes = 64;
+      probe<<<ctas, 128, STAGES * CHUNK>>>(buf, bytes, 2, mode);
+      cudaEventRecord(e0);
+      probe<<<ctas, 128, STAGES * CHUNK>>>(buf, bytes, passes, mode);
+      cudaEventRecord(e1);
+      cudaDeviceSynchronize();
+      float ms; cudaEventElapsedTime(&ms, e0, e1);
+      const double moved = (double)bytes * passes;
+      printf("%s 32 MB, %3d CTAs : %8.1f GB/s total, %6.1f GB/s per SM\n", names[mode], ctas, moved / ms / 1e6,
+             moved / ms / 1e6 / ctas);
+    }
+  }
   return 0;
 }

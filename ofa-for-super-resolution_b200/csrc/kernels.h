@@ -71,6 +71,13 @@ int launch_dw_planar(const void* x, void* y, int N, int C, int H, int W, const f
 int launch_project_planar(const void* x, const void* res, void* y, const void* wproj_p, int N, int HW, int mid,
                           int trunk_f16, int f16, const OfaBn* bn, cudaStream_t st);
 
+// ---- mbconv_band.cu : the same three stages as ONE launch around an L2-resident region ring ---------------
+bool mbconv_band_supported(const OfaMBConvArgs* a);
+bool mbconv_band_preferred(const OfaMBConvArgs* a);
+long long mbconv_band_workspace_bytes(int W, int mid, int n_regions_max);
+int launch_mbconv_band(const OfaMBConvArgs* a, const void* wexp_p, const void* wproj_p, int f16, void* ws,
+                       long long ws_bytes, cudaStream_t st);
+
 // ---- data_prep.cu : SR data preparation (Pillow-exact bicubic resampling, crop / flip / rotate, ToTensor) ----
 int resample_ksize(int in_size, int out_size);
 int resample_build_table(int in_size, int out_size, int32_t* bounds_host, int32_t* kk_host);

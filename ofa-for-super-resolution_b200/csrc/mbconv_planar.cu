@@ -24,19 +24,12 @@
 #include "ofa_common.cuh"
 #include "kernels.h"
 #include "sm100_ptx.cuh"
+#include "mbconv_planar.cuh"
 
 #include <string.h>
 
 namespace ofa {
 namespace {
-
-__device__ __forceinline__ void bn_fold(const float* gamma, const float* beta, const float* mean, const float* var,
-                                        float eps, int c, float& scale, float& shift) {
-  const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
-  const float m = mean ? mean[c] : 0.f, rstd = var ? rsqrtf(var[c] + eps) : 1.f;
-  scale = g * rstd;
-  shift = b - m * scale;
-}
 
 // ==================================================================================================
 // weight packing for the block: expand -> bf16 [mt*128][64] (A operand), project -> 16-bit [64][mid]
@@ -61,15 +54,6 @@ __global__ void pack_block_weights_kernel(const float* __restrict__ w_exp, long 
 // ==================================================================================================
 // (1) expand: NHWC bf16 trunk -> planar 16-bit, folded BN + activation
 // ==================================================================================================
-constexpr int EX_NPIX = 256;                 // pixels per tile = UMMA N
-constexpr int EX_X_STAGES = 3;
-constexpr int EX_SBUFS = 2;                  // store staging buffers per epilogue warp (TMA stores in flight)
-constexpr int EX_X_BYTES = EX_NPIX * 128;    // 32 KiB
-constexpr int EX_EPI_WARPS = 8;
-constexpr int EX_THREADS = 64 + 32 * EX_EPI_WARPS;
-constexpr int EX_SBUF_BYTES = 32 * 128;      // per-warp store staging: 32 channels x 64 pixels
-constexpr int EX_MAX_MT = 3;
-
 struct ExpandParams {
   int N, HW, mid, mt, f16, xf16, act;
   const float* gamma; const float* beta; const float* mean; const float* var; float eps;
@@ -225,20 +209,9 @@ expand_planar_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
 //     B_dy[k][n] = f[dy][k - n + 8 + R]   (zero outside the band), the same matrix for every chunk.
 // The very first MMA of a tile (dy = 0, chunk 0) uses the same matrix zero-extended to all 144 accumulator
 // columns with accumulate = 0: it initialises the accumulator, every later MMA accumulates.
-constexpr int DW_TW = 112;                    // valid output columns per tile (224 bytes: TMA-storable)
-constexpr int DW_TH = 128;                    // output rows per tile = UMMA M
-constexpr int DW_XPAD = 8;
-constexpr int DW_CHUNKS = 8;                  // 16-column K chunks per tile row
-constexpr int DW_ACC_COLS = 16 * (DW_CHUNKS - 1) + 32;   // 144
-constexpr int DW_ACC_STAGES = 3;
-constexpr int DW_A_STAGES = 4;
-constexpr int DW_ATOM_STRIDE = 17408;         // (128 + 6) * 128 rounded up to 1024
-constexpr int DW_A_STRIDE = 2 * DW_ATOM_STRIDE;
-constexpr int DW_BFIRST_BYTES = (DW_ACC_COLS / 8) * 256;   // 4608: N = 144 zero-extended matrix
-constexpr int DW_B_BYTES = DW_BFIRST_BYTES + 7 * 1024;
-constexpr int DW_OUT_BYTES = DW_TH * DW_TW * 2;            // 28672
-constexpr int DW_EPI_WARPS = 8;               // 4 lane quarters x 2 column halves
-constexpr int DW_THREADS = (3 + DW_EPI_WARPS) * 32;   // TMA, MMA, filter builder, epilogue warps
+// (Tried: 5 input stages with a single output staging tile -- 0.192 ms instead of 0.179 at C2: the epilogue then waits
+// for the TMA engine to get to the previous store behind the queued prefetch loads.)
+constexpr int DWP_A_STAGES = 4;
 
 struct DwPlanarParams {
   int NC, C, H, W, ks, kmax, transform_on, f16, act;
@@ -259,10 +232,6 @@ __device__ __forceinline__ bool dw_decode(const DwPlanarParams& p, int t, int& p
   x0 = (int)tx * DW_TW;
   return p.short_last && (int)ty == p.tiles_y - 1;
 }
-// offset of element (n = accumulator column, k = input column within the chunk) in a K-major, unswizzled
-// B tile: 8 x 16-byte core matrices, K-halves 128 bytes apart, 8-column groups 256 bytes apart
-__device__ __forceinline__ int dw_b_off(int n, int k) { return (n >> 3) * 256 + (k >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2; }
-
 // KS: kernel size; F16: fp16 (1) or bf16 (0) storage; RELU6: the activation is ReLU6 (else p.act at run time)
 template <int KS, int F16, int RELU6>
 __global__ void __launch_bounds__(DW_THREADS, 1)
@@ -271,12 +240,12 @@ dw_planar_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
   uint8_t* sA = smem;
-  uint8_t* sO = sA + DW_A_STAGES * DW_A_STRIDE;                    // 2 output staging tiles (1024-aligned)
+  uint8_t* sO = sA + DWP_A_STAGES * DW_A_STRIDE;                   // 2 output staging tiles (1024-aligned)
   uint8_t* sB = sO + 2 * DW_OUT_BYTES;                             // 2 filter buffers
   float* s_filt = reinterpret_cast<float*>(sB + 2 * DW_B_BYTES);   // 49 active taps + 32 scratch
   uint64_t* a_full = reinterpret_cast<uint64_t*>(s_filt + 96);
-  uint64_t* a_empty = a_full + DW_A_STAGES;
-  uint64_t* tfull = a_empty + DW_A_STAGES;
+  uint64_t* a_empty = a_full + DWP_A_STAGES;
+  uint64_t* tfull = a_empty + DWP_A_STAGES;
   uint64_t* tempty = tfull + DW_ACC_STAGES;
   uint64_t* b_full = tempty + DW_ACC_STAGES;
   uint64_t* b_empty = b_full + 2;
@@ -286,9 +255,10 @@ dw_planar_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   const int lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&tm_x); ptx::prefetch_tmap(&tm_xs); ptx::prefetch_tmap(&tm_y); }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < DW_A_STAGES; ++s) { ptx::mbar_init(&a_full[s], 1); ptx::mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < DWP_A_STAGES; ++s) { ptx::mbar_init(&a_full[s], 1); ptx::mbar_init(&a_empty[s], 1); }
     for (int a = 0; a < DW_ACC_STAGES; ++a) { ptx::mbar_init(&tfull[a], 1); ptx::mbar_init(&tempty[a], DW_EPI_WARPS); }
-    for (int b = 0; b < 2; ++b) { ptx::mbar_init(&b_full[b], 1); ptx::mbar_init(&b_empty[b], 1); }
+    // both MMA issuer warps release a filter buffer (each commits at every plane switch)
+    for (int b = 0; b < 2; ++b) { ptx::mbar_init(&b_full[b], 1); ptx::mbar_init(&b_empty[b], 2); }
     ptx::fence_barrier_init();
   }
   if (warp == 2) { ptx::tmem_alloc(tmem_ptr, 512); ptx::tmem_relinquish(); }
@@ -315,11 +285,18 @@ dw_planar_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         ptx::mbar_arrive_expect_tx(&a_full[s], 2 * (shrt ? atom_bytes_short : atom_bytes));
         ptx::tma_load_3d(sA + s * DW_A_STRIDE, tm, &a_full[s], x0 - DW_XPAD, y0 - R, pc);
         ptx::tma_load_3d(sA + s * DW_A_STRIDE + DW_ATOM_STRIDE, tm, &a_full[s], x0 - DW_XPAD + 64, y0 - R, pc);
-        if (++s == DW_A_STAGES) { s = 0; ph ^= 1; }
+        if (++s == DWP_A_STAGES) { s = 0; ph ^= 1; }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1 || warp == DW_ISSUER1_WARP) {
+    // ===================== MMA issuers =====================
+    // ONE warp can issue a tcgen05.mma only every ~51 clocks (measured, csrc/experiments/umma_rate_probe.cu), but an
+    // M128 x N32 x K16 MMA occupies the tensor pipe for 40 (its 5 KB of shared-memory operands at 128 B/clk): with a
+    // single issuer the kernel ran at ~65 clocks per MMA.  Two issuer warps take ALTERNATE tiles -- every tile's MMAs still
+    // come from one thread, in order, into that tile's own accumulator stage -- and their streams interleave in the pipe.
+    // Both walk the whole tile list (stage / phase bookkeeping stays in step) and both arrive on b_empty at every plane
+    // switch; a commit with no MMAs of its own outstanding arrives at once.
+    const int issuer = warp == 1 ? 0 : 1;
     constexpr int fmt = F16 ? 0 : 1;
     constexpr uint32_t idesc32_tall = ptx::umma_idesc_f16(128, 32, fmt, fmt, 0, 0);
     constexpr uint32_t idesc_first_tall = ptx::umma_idesc_f16(128, DW_ACC_COLS, fmt, fmt, 0, 0);
@@ -342,6 +319,11 @@ dw_planar_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         }
         ptx::mbar_wait(&b_full[bi], bph);
         cur_pc = pc;
+      }
+      if (((t - t_begin) & 1) != issuer) {          // the other issuer's tile
+        if (++s == DWP_A_STAGES) { s = 0; ph ^= 1; }
+        if (++acc == DW_ACC_STAGES) { acc = 0; accph ^= 1; }
+        continue;
       }
       ptx::mbar_wait(&a_full[s], ph);
       ptx::mbar_wait(&tempty[acc], accph ^ 1);
@@ -369,7 +351,7 @@ dw_planar_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       }
       ptx::umma_commit_elect(&a_empty[s]);
       ptx::umma_commit_elect(&tfull[acc]);
-      if (++s == DW_A_STAGES) { s = 0; ph ^= 1; }
+      if (++s == DWP_A_STAGES) { s = 0; ph ^= 1; }
       if (++acc == DW_ACC_STAGES) { acc = 0; accph ^= 1; }
     }
   } else if (warp == 2) {
@@ -468,14 +450,6 @@ dw_planar_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
 // ==================================================================================================
 // (3) project: planar 16-bit -> NHWC bf16 trunk, folded BN + residual
 // ==================================================================================================
-constexpr int PJ_MPIX = 128;                  // pixels per tile = UMMA M
-constexpr int PJ_A_STAGES = 8;
-constexpr int PJ_A_BYTES = 16384;             // 2 boxes of 64 pixels x 64 channels
-constexpr int PJ_MAX_KC = 6;
-constexpr int PJ_ACC_STAGES = 4;
-constexpr int PJ_R_BYTES = PJ_MPIX * 128;     // residual / output staging tile
-constexpr int PJ_THREADS = 6 * 32;            // TMA, MMA, 4 epilogue warps
-
 struct ProjectParams {
   int N, HW, mid, kcs, f16, yf16, has_res;
   const float* gamma; const float* beta; const float* mean; const float* var; float eps;
@@ -761,7 +735,7 @@ int launch_dw_planar(const void* x, void* y, int N, int C, int H, int W, const f
     uint32_t box[3] = {DW_TW, DW_TH, 1};
     if ((rc = encode_tmap(&ty, dt16(f16), 3, y, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
   }
-  const size_t smem = 1024 + DW_A_STAGES * DW_A_STRIDE + 2 * DW_OUT_BYTES + 2 * DW_B_BYTES + 96 * 4 + 256;
+  const size_t smem = 1024 + DWP_A_STAGES * DW_A_STRIDE + 2 * DW_OUT_BYTES + 2 * DW_B_BYTES + 96 * 4 + 256;
   long long grid = sm_count();
   if (grid > p.total_tiles) grid = p.total_tiles;
   const int relu6 = act == OFA_ACT_RELU6 ? 1 : 0;

@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_LIB_DIR, 'libofa_sr_b200.so')
 OFA_F32, OFA_BF16, OFA_F16 = 0, 1, 2
 ACT_NONE, ACT_RELU6, ACT_HSWISH, ACT_RELU, ACT_HSIGMOID = 0, 1, 2, 3, 4
 STORE_PLAIN, STORE_PIXELSHUFFLE2, STORE_PIXELUNSHUFFLE2 = 0, 1, 2
-IMPL_AUTO, IMPL_SIMT, IMPL_FAST, IMPL_NHWC = 0, 1, 2, 3
+IMPL_AUTO, IMPL_SIMT, IMPL_FAST, IMPL_NHWC, IMPL_BAND, IMPL_PLANAR3 = 0, 1, 2, 3, 4, 5
 
 ACT_CODES = {None: ACT_NONE, 'relu6': ACT_RELU6, 'h_swish': ACT_HSWISH, 'relu': ACT_RELU}
 

@@ -990,11 +990,13 @@ def mbconv_infer(x, w_exp, w_dw, m75, m53, w_proj, cin, mid, cout, ks, transform
     if x.numel() == 0:
         return B.new_nhwc(n, cout, h, w, x.dtype, x.device)
     planar = (planar_supported(x, cin, mid, cout) and _state['impl'] not in (B.IMPL_SIMT, B.IMPL_NHWC)
-              and (_state['impl'] == B.IMPL_FAST or planar_preferred(x)))
-    if _profiler is not None and planar:
+              and (_state['impl'] in (B.IMPL_FAST, B.IMPL_BAND, B.IMPL_PLANAR3) or planar_preferred(x)))
+    band = planar and act == B.ACT_RELU6 and _state['impl'] != B.IMPL_PLANAR3 and (
+        _state['impl'] == B.IMPL_BAND or band_preferred(x))
+    if _profiler is not None and planar and not band:
         return _mbconv_planar_staged(x, w_exp, w_dw, m75, m53, w_proj, mid, ks, transform_on, act, bn_exp, bn_dw,
                                      bn_proj, add_residual)
-    if _profiler is not None:
+    if _profiler is not None and not planar:
         # same kernels, issued one by one so each gets its own event pair
         c1 = _train_cache(w_exp, ('prof', 0))
         c2 = _train_cache(w_proj, ('prof', 1))
@@ -1023,6 +1025,12 @@ def mbconv_infer(x, w_exp, w_dw, m75, m53, w_proj, cin, mid, cout, ks, transform
     if planar and pack_cache is not None:
         we, wp = _planar_packed_weights(pack_cache, w_exp, w_proj, mid, x.dtype)
         a.w_exp_packed, a.w_proj_packed = we.data_ptr(), wp.data_ptr()
+    if band:
+        # one launch for the whole block: algorithmic traffic = trunk in + out (SURVEY 8d "fused MBConv block")
+        P = n * h * w
+        _call('mbconv band ks%d M%d' % (ks, mid), 2.0 * P * mid * (128 + ks * ks), 2 * P * 64 * x.element_size(),
+              lambda: B.check(L.ofa_mbconv_fwd(byref(a), _state['impl'], _stream(x))))
+        return y
     B.check(L.ofa_mbconv_fwd(byref(a), _state['impl'], _stream(x)))
     return y
 
@@ -1060,6 +1068,15 @@ def planar_preferred(x):
     rows = h // 128 * 128 + (0 if tail == 0 else 64 if tail <= 64 else 128)
     cols = (w + 111) // 112 * 112
     return h * w >= 8192 and 4 * h * w >= rows * cols
+
+
+def band_preferred(x):
+    """Mirrors mbconv_band_preferred: the single-launch, L2-resident block is opt-in (OFA_BAND_ENABLE=1 or IMPL_BAND): at
+    the bench shape it measured slower than the three stand-alone kernels."""
+    import os
+    h, w = x.shape[2], x.shape[3]
+    return (int(os.environ.get('OFA_BAND_ENABLE', '0') or 0) and planar_preferred(x) and h * w >= 128 * 448 and w >= 224
+            and h >= 96 and not int(os.environ.get('OFA_BAND_DISABLE', '0') or 0))
 
 
 def _mbconv_planar_staged(x, w_exp, w_dw, m75, m53, w_proj, mid, ks, transform_on, act, bn_exp, bn_dw, bn_proj,

@@ -191,4 +191,63 @@ if 'time' in which:
     timeit('dw5 C384', run_dw(B.OFA_F16, 5, 1, 384, H, W, timing=True), 2 * P * 384 * 2)
     timeit('dw3 C192', run_dw(B.OFA_F16, 3, 1, 192, H, W, timing=True), 2 * P * 192 * 2)
     timeit('project 384->64 +res', run_project(B.OFA_F16, 384, 1, P, timing=True), P * (384 + 128) * 2)
+def run_block(impl, mid, ks, N, H, W, res=True, dtype=None, seed=0, timing=False, trunk=None):
+    """Whole block through ofa_mbconv_fwd with the given impl (IMPL_BAND: one launch; IMPL_PLANAR3: three kernels)."""
+    from ofa_b200 import functional as OF
+    dtype = dtype or B.OFA_F16
+    trunk = trunk or B.OFA_F16
+    g = torch.Generator(device='cuda').manual_seed(seed)
+    x = torch.randn(N, 64, H, W, device=dev, generator=g).to(tdt(trunk)).contiguous(memory_format=torch.channels_last)
+    w_exp = torch.randn(384, 64, 1, 1, device=dev, generator=g) * 0.2
+    w_dw = torch.randn(384, 1, 7, 7, device=dev, generator=g) * 0.15
+    w_proj = torch.randn(64, 384, 1, 1, device=dev, generator=g) * 0.1
+    m75 = torch.eye(25, device=dev) + 0.05 * torch.randn(25, 25, device=dev, generator=g)
+    m53 = torch.eye(9, device=dev) + 0.05 * torch.randn(9, 9, device=dev, generator=g)
+    torch.manual_seed(seed + 1)
+    b1, b2, b3 = BN(384), BN(384), BN(64)
+
+    class _B:
+        pass
+    bns = []
+    for b in (b1, b2, b3):
+        o = _B(); o.weight, o.bias, o.running_mean, o.running_var, o.eps = b.weight, b.bias, b.running_mean, b.running_var, b.eps
+        bns.append(o)
+    OF.set_impl(impl)
+    OF.set_mid_dtype(tdt(dtype))
+
+    def call():
+        return OF.mbconv_infer(x, w_exp, w_dw, m75, m53, w_proj, 64, mid, 64, ks, True, B.ACT_RELU6, bns[0], bns[1], bns[2],
+                               res, pack_cache={})
+    y = call()
+    torch.cuda.synchronize()
+    OF.set_impl(B.IMPL_AUTO)
+    if timing:
+        def again():
+            OF.set_impl(impl)
+            r = call()
+            OF.set_impl(B.IMPL_AUTO)
+            return r
+        return again
+    return y
+
+
+if 'band' in which:
+    shapes = [(384, 7, 1, 200, 120), (384, 7, 1, 130, 232), (192, 3, 1, 96, 120), (256, 5, 2, 140, 344),
+              (384, 5, 1, 64, 448), (384, 7, 1, 300, 960), (384, 7, 1, 540, 960), (192, 3, 1, 540, 960)]
+    for mid, ks, N, H, W in shapes:
+        for res in (True, False):
+            ref = run_block(B.IMPL_PLANAR3, mid, ks, N, H, W, res)
+            got = run_block(B.IMPL_BAND, mid, ks, N, H, W, res)
+            bad = int((got.float() != ref.float()).sum())
+            err = float((got.float() - ref.float()).abs().max())
+            fin = bool(torch.isfinite(got.float()).all())
+            print('band vs 3-kernel  mid %d ks %d N%d %dx%d res %d : %d differing elements, max|diff| %.3e, finite %s  %s'
+                  % (mid, ks, N, H, W, res, bad, err, fin, 'OK' if bad == 0 and fin else 'MISMATCH'), flush=True)
+            ok &= (bad == 0 and fin)
+if 'bandtime' in which:
+    H, W = 540, 960
+    P = H * W
+    for mid, ks in ((384, 7), (384, 5), (256, 5), (192, 3)):
+        timeit('3-kernel block M%d ks%d' % (mid, ks), run_block(B.IMPL_PLANAR3, mid, ks, 1, H, W, timing=True), 2 * P * 64 * 2)
+        timeit('band block     M%d ks%d' % (mid, ks), run_block(B.IMPL_BAND, mid, ks, 1, H, W, timing=True), 2 * P * 64 * 2)
 print('ALL OK' if ok else 'SOME MISMATCH')
