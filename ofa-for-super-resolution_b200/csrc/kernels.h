@@ -15,6 +15,7 @@ int launch_conv_simt(const TV& x, const TV& y, const float* w, long long w_so, l
 int launch_pack_weight(const float* w, long long w_so, long long w_si, long long w_sh, long long w_sw,
                        int cin, int cout, int ks, int cin_pad, int cout_pad, int store, int f16, void* out,
                        cudaStream_t st);
+void keep_async_pool_resident();   // raise the default mempool's release threshold once per device (cudaMallocAsync scratch)
 int launch_pack_weights_multi(const OfaPackJob* jobs_device, int njobs, cudaStream_t st);
 int launch_affine_act(const TV& x, const TV& y, const Epi& epi, int store, cudaStream_t st);
 int launch_bn_stats(const TV& x, float* mean, float* var, cudaStream_t st);

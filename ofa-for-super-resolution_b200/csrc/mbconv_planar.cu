@@ -215,7 +215,7 @@ constexpr int DWP_A_STAGES = 4;
 
 struct DwPlanarParams {
   int NC, C, H, W, ks, kmax, transform_on, f16, act;
-  const float* w7; const float* m75; const float* m53;
+  const float* filt;   // [C][ks * ks] active filters (fp32), derived once per launch by active_filter_kernel
   const float* gamma; const float* beta; const float* mean; const float* var; float eps;
   int tiles_x, tiles_y;
   int total_tiles;
@@ -242,8 +242,8 @@ dw_planar_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   uint8_t* sA = smem;
   uint8_t* sO = sA + DWP_A_STAGES * DW_A_STRIDE;                   // 2 output staging tiles (1024-aligned)
   uint8_t* sB = sO + 2 * DW_OUT_BYTES;                             // 2 filter buffers
-  float* s_filt = reinterpret_cast<float*>(sB + 2 * DW_B_BYTES);   // 49 active taps + 32 scratch
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(s_filt + 96);
+  uint16_t* s_rows = reinterpret_cast<uint16_t*>(sB + 2 * DW_B_BYTES);   // [KS][64] zero-padded 16-bit filter rows
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(s_rows + 512);
   uint64_t* a_empty = a_full + DWP_A_STAGES;
   uint64_t* tfull = a_empty + DWP_A_STAGES;
   uint64_t* tempty = tfull + DW_ACC_STAGES;
@@ -356,32 +356,54 @@ dw_planar_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     }
   } else if (warp == 2) {
     // ===================== filter builder: active filter -> Toeplitz B tiles =====================
+    // Element (n, k) of a tile is f[dy][k - n + dx0]: only rows n_lo..n_hi can be non-zero, everything else is zeroed
+    // ONCE; a row's two 16-byte K-halves are 8 consecutive entries of the zero-padded 16-bit filter row s_rows[dy].
+    // The whole warp builds (round 1: lane 0 derived the filter with the 25 x 25 / 9 x 9 mat-vecs per plane, ~6 us, which
+    // is why planes of fewer than ~45 tiles ran slowly); the transformed filters now come from one tiny launch.
     int bi = 0, cur_pc = -1; uint32_t bph = 0;
     constexpr int dx0 = DW_XPAD + R;
+    constexpr int PADL = 16, ROWLEN = 64;
+    constexpr int n_lo = dx0 - KS + 1, n_hi = dx0 + 15, NR = n_hi - n_lo + 1;
+    for (int i = lane; i < (2 * DW_B_BYTES) / 16; i += 32)
+      *reinterpret_cast<uint4*>(sB + 16 * i) = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = lane; i < KS * ROWLEN; i += 32) s_rows[i] = (uint16_t)0;
+    // a lane owns up to two (row n, K-half) vectors of EVERY tile: source / destination offsets are loop invariants
+    int src_off[2], dst_off[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int q = lane + 32 * h;
+      const int n = n_lo + (q >> 1), kh = q & 1;
+      src_off[h] = q < NR * 2 ? kh * 8 - n + dx0 + PADL : -1;
+      dst_off[h] = dw_b_off(n, kh * 8);
+    }
+    __syncwarp();
     for (int t = t_begin; t < t_end; ++t) {
       int pc, y0, x0;
       dw_decode(p, t, pc, y0, x0);
       if (pc == cur_pc) continue;
       cur_pc = pc;
-      const int c = pc % p.C;
+      const float* f = p.filt + (size_t)(pc % p.C) * KS * KS;
+      const float t0 = lane < KS * KS ? f[lane] : 0.f;                 // issued before the wait: latency overlaps it
+      const float t1 = lane + 32 < KS * KS ? f[lane + 32] : 0.f;
       ptx::mbar_wait(&b_empty[bi], bph ^ 1);
-      if (lane == 0)
-        active_filter_channel(p.w7 + (size_t)c * p.kmax * p.kmax, p.kmax, p.m75, p.m53, p.transform_on, KS, s_filt,
-                              s_filt + 64);
+      if (lane < KS * KS) s_rows[(lane / KS) * ROWLEN + PADL + lane % KS] = cvt16(t0, F16);
+      if (lane + 32 < KS * KS) s_rows[((lane + 32) / KS) * ROWLEN + PADL + (lane + 32) % KS] = cvt16(t1, F16);
       __syncwarp();
       uint8_t* b0 = sB + bi * DW_B_BYTES;
-      // first tile (dy = 0, N = 144): columns >= 32 come out zero by the band condition
-      for (int i = lane; i < 16 * DW_ACC_COLS; i += 32) {
-        const int n = i >> 4, k = i & 15, dx = k - n + dx0;
-        const float v = (dx >= 0 && dx < KS) ? s_filt[dx] : 0.f;
-        *reinterpret_cast<uint16_t*>(b0 + dw_b_off(n, k)) = cvt16(v, F16);
-      }
-      for (int dy = 0; dy < KS; ++dy) {
-        uint8_t* bd = b0 + DW_BFIRST_BYTES + dy * 1024;
-        for (int i = lane; i < 16 * 32; i += 32) {
-          const int n = i >> 4, k = i & 15, dx = k - n + dx0;
-          const float v = (dx >= 0 && dx < KS) ? s_filt[dy * KS + dx] : 0.f;
-          *reinterpret_cast<uint16_t*>(bd + dw_b_off(n, k)) = cvt16(v, F16);
+      // tile 0: the N = 144 first matrix (dy = 0); tiles 1..KS: the N = 32 matrices of dy = 0..KS-1
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (src_off[h] >= 0) {
+#pragma unroll
+          for (int tt = 0; tt <= KS; ++tt) {
+            const int dy = tt == 0 ? 0 : tt - 1;
+            const uint16_t* src = s_rows + dy * ROWLEN + src_off[h];
+            uint32_t w[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) w[q] = (uint32_t)src[2 * q] | ((uint32_t)src[2 * q + 1] << 16);
+            uint8_t* dst = (tt == 0 ? b0 : b0 + DW_BFIRST_BYTES + dy * 1024) + dst_off[h];
+            *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
         }
       }
       ptx::fence_proxy_async();
@@ -710,7 +732,15 @@ int launch_dw_planar(const void* x, void* y, int N, int C, int H, int W, const f
   memset(&p, 0, sizeof(p));
   p.NC = N * C; p.C = C; p.H = H; p.W = W; p.ks = ks; p.kmax = kmax; p.transform_on = transform_on; p.f16 = f16;
   p.act = act;
-  p.w7 = w7; p.m75 = m75; p.m53 = m53;
+  // the transformed filters (centre crop + learned 7->5->3 matrices, dynamic_op.py:46-71) once per launch
+  float* filt = nullptr;
+  keep_async_pool_resident();
+  OFA_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&filt), (size_t)C * ks * ks * sizeof(float), st));
+  {
+    const int rc0 = launch_active_filter(w7, kmax, m75, m53, transform_on, ks, C, filt, st);
+    if (rc0) { cudaFreeAsync(filt, st); return rc0; }
+  }
+  p.filt = filt;
   if (bn) { p.gamma = bn->gamma; p.beta = bn->beta; p.mean = bn->mean; p.var = bn->var; p.eps = bn->eps; }
   p.tiles_x = (W + DW_TW - 1) / DW_TW;
   p.tiles_y = (H + DW_TH - 1) / DW_TH;
@@ -735,7 +765,7 @@ int launch_dw_planar(const void* x, void* y, int N, int C, int H, int W, const f
     uint32_t box[3] = {DW_TW, DW_TH, 1};
     if ((rc = encode_tmap(&ty, dt16(f16), 3, y, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
   }
-  const size_t smem = 1024 + DWP_A_STAGES * DW_A_STRIDE + 2 * DW_OUT_BYTES + 2 * DW_B_BYTES + 96 * 4 + 256;
+  const size_t smem = 1024 + DWP_A_STAGES * DW_A_STRIDE + 2 * DW_OUT_BYTES + 2 * DW_B_BYTES + 1024 + 256;
   long long grid = sm_count();
   if (grid > p.total_tiles) grid = p.total_tiles;
   const int relu6 = act == OFA_ACT_RELU6 ? 1 : 0;
@@ -757,7 +787,9 @@ int launch_dw_planar(const void* x, void* y, int N, int C, int H, int W, const f
   else OFA_DW_LAUNCH_KS(7);
 #undef OFA_DW_LAUNCH_KS
 #undef OFA_DW_LAUNCH
-  return check_launch("dw_planar_kernel");
+  const int rc_launch = check_launch("dw_planar_kernel");
+  cudaFreeAsync(filt, st);
+  return rc_launch;
 }
 
 // x: planar [N][mid][H*W] 16-bit; res / y: NHWC bf16 [N,H*W,64]

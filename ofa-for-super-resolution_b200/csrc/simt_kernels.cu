@@ -746,7 +746,7 @@ bn_stats_final_kernel(const float* __restrict__ part, int splits, int C, float* 
 // Stream-ordered scratch (cudaMallocAsync) for the split reductions.  The default memory pool releases its memory
 // back to the OS at every synchronisation (release threshold 0); re-creating ~100 small allocations per training
 // step then costs hundreds of milliseconds.  Once per device the threshold is raised so the pool keeps its pages.
-static void keep_async_pool_resident() {
+void keep_async_pool_resident() {
   static bool done[64] = {false};
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;

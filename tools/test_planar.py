@@ -250,4 +250,15 @@ if 'bandtime' in which:
     for mid, ks in ((384, 7), (384, 5), (256, 5), (192, 3)):
         timeit('3-kernel block M%d ks%d' % (mid, ks), run_block(B.IMPL_PLANAR3, mid, ks, 1, H, W, timing=True), 2 * P * 64 * 2)
         timeit('band block     M%d ks%d' % (mid, ks), run_block(B.IMPL_BAND, mid, ks, 1, H, W, timing=True), 2 * P * 64 * 2)
+if 'small' in which:
+    # batches of small planes (the X4 teacher / training shapes): planar tcgen05 path against the three NHWC kernels
+    for (N, H, W) in ((64, 48, 48), (64, 24, 24), (16, 96, 96), (8, 64, 64), (1, 96, 120)):
+        for mid, ks in ((384, 7), (384, 3), (192, 5)):
+            P = N * H * W
+            ref = run_block(B.IMPL_NHWC, mid, ks, N, H, W, True)
+            got = run_block(B.IMPL_PLANAR3, mid, ks, N, H, W, True)
+            err = float((got.float() - ref.float()).abs().max() / ref.float().abs().max())
+            print('N%d %dx%d M%d ks%d  planar vs NHWC max-rel-diff %.2e' % (N, H, W, mid, ks, err), flush=True)
+            timeit('  planar3 N%d %dx%d M%d ks%d' % (N, H, W, mid, ks), run_block(B.IMPL_PLANAR3, mid, ks, N, H, W, timing=True), 2 * P * 64 * 2)
+            timeit('  nhwc    N%d %dx%d M%d ks%d' % (N, H, W, mid, ks), run_block(B.IMPL_NHWC, mid, ks, N, H, W, timing=True), 2 * P * 64 * 2)
 print('ALL OK' if ok else 'SOME MISMATCH')
