@@ -46,6 +46,8 @@ def parse():
     ap.add_argument('--lr-w', type=int, default=960)
     ap.add_argument('--cpu-tile', type=int, default=256, help='LR tile edge of the bounded CPU-baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-train', action='store_true', help='skip the training-step measurements (the `train` object)')
+    ap.add_argument('--train-steps', type=int, default=20)
     ap.add_argument('--dtype', default='f16', choices=['f16', 'bf16', 'fp32'],
                     help='activation storage of our arm: f16 (default; meets the 0.01 dB PSNR criterion), bf16 (same speed) or fp32 (exact CUDA-core path)')
     return ap.parse_args()
@@ -221,6 +223,152 @@ def build_net(dev):
     return net.to(dev).eval()
 
 
+def pin_rank_to_cores(local_rank, local_world):
+    """Several ranks share the box's host cores: give each rank its own slice so that eight Python launch loops (and the
+    NCCL proxy threads they spawn) do not migrate over each other.  No-op when it cannot be done."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = max(1, len(cores) // max(1, local_world))
+        mine = cores[local_rank * per:(local_rank + 1) * per]
+        if mine:
+            os.sched_setaffinity(0, mine)
+    except Exception:
+        pass
+
+
+def run_train(dev, dist, rank, world, which, steps, warmup):
+    """BASELINE.json configs[2] (C3) / configs[3] (C4) as one progressive-shrinking optimizer step per timed step, on
+    every rank count the driver runs: batch 64 of 96x96 HR patches PER GPU (weak scaling), bf16 compute with fp32 master
+    weights, `dynamic_batch_size` 2 (two sampled sub-networks accumulate gradients, progressive_shrinking.py:158-203;
+    seed rule :164), fused Adam (sr_run_manager.py:115-133) and -- with several ranks -- ONE flat NCCL all-reduce of the
+    gradients per step, its tail segment overlapped with backward (distributed_run_manager.py:72-75).
+      c3: OFAMobileNetS4, inputs = the 2x / 4x bicubic-downscaled patches the sampled pixel_d selects
+      c4: OFAMobileNetX4 (HR in, HR out), one 2x and one 4x student per step, frozen max-sub-network teacher at both
+          scales under no_grad, loss = MSE(out, HR) + 0.5 MSE(out, teacher_out)"""
+    import copy
+    import random
+    import ofa_b200
+    from ofa_b200 import backend as B, optim, parallel as P
+    from ofa_b200.elastic_nn.modules.dynamic_op import DynamicSeparableConv2d
+    from ofa_b200.elastic_nn.networks import OFAMobileNetS4, OFAMobileNetX4
+    from ofa_b200.elastic_nn.training import train_step, subnet_seed
+    ofa_b200.set_train_dtype(torch.bfloat16)
+    DynamicSeparableConv2d.KERNEL_TRANSFORM_MODE = 1
+    Net = OFAMobileNetS4 if which == 'c3' else OFAMobileNetX4
+    cfg = {k: list(v) for k, v in NET_CFG.items()}
+    if which == 'c3':
+        # S4 runs runtime_depth[0] PixelShuffle stages whatever pixel_d says (SURVEY 3.4 Q1: always 4x), so the
+        # reference's S4 training is the 4x task: pixel_d = 2 -> the 4x-downscaled input (progressive_shrinking.py:178-180)
+        cfg['pixelshuffle_depth_list'] = [2]
+    net = Net(**cfg)
+    synth_weights(net, WEIGHT_SEED + 1)
+    net = net.to(dev).train()
+    per_gpu = 64
+    g = torch.Generator(device='cpu').manual_seed(100 + rank)
+    hr = torch.rand(per_gpu, 3, 96, 96, generator=g).to(dev)
+    batch = {'image': hr,
+             '2x_down_image': torch.nn.functional.interpolate(hr, scale_factor=0.5, mode='bilinear', align_corners=False),
+             '4x_down_image': torch.nn.functional.interpolate(hr, scale_factor=0.25, mode='bilinear', align_corners=False)}
+    teacher = copy.deepcopy(net).eval() if which == 'c4' else None
+    decay, no_decay = optim.split_no_decay(net.named_parameters())
+    opt = optim.FusedAdam(decay, no_decay, lr=1e-4, weight_decay=3e-5)
+    reducer, boundary = None, None
+    if world > 1:
+        P.broadcast_parameters(net, src=0)
+        if which == 'c3':
+            tail, boundary = P.s4_tail_parameters(net)
+            reducer = P.FlatGradAllReduce(net.parameters(), n_buckets=2, tail_params=tail)
+        else:
+            reducer = P.FlatGradAllReduce(net.parameters(), n_buckets=2)
+    n_batch = 1000
+    ar_events = []
+
+    def step(i, time_allreduce=False):
+        lr = optim.cosine_lr(1e-4, 120, 0, i, n_batch)
+        if which == 'c3':
+            if time_allreduce and reducer is not None:
+                inner = reducer.reduce
+
+                def timed_reduce():
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    inner()
+                    e1.record()
+                    ar_events.append((e0, e1))
+                reducer.reduce = timed_reduce
+            try:
+                train_step(net, opt, batch, 0, i, n_batch, dynamic_batch_size=2, reducer=reducer, lr=lr,
+                           boundary_module=boundary)
+            finally:
+                if time_allreduce and reducer is not None:
+                    reducer.reduce = inner
+            return
+        # c4: teacher at both scales, then one 2x and one 4x student (tools/bench_train_x4.py)
+        opt.set_lr(lr)
+        opt.zero_grad(set_to_none=True)
+        soft = {}
+        with torch.no_grad():
+            for pd in (1, 2):
+                teacher.set_active_subnet(ks=7, e=6, d=4, pixel_d=pd)
+                soft[pd] = teacher(hr)
+        for k, pd in enumerate((1, 2)):
+            random.seed(subnet_seed(0, n_batch, i, k))
+            net.sample_active_subnet()
+            net.set_active_subnet(pixel_d=pd)
+            out = net(hr)
+            loss = torch.nn.functional.mse_loss(out, hr) + 0.5 * torch.nn.functional.mse_loss(out, soft[pd])
+            loss.backward()
+        if reducer is not None:
+            if time_allreduce:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                reducer.reduce()
+                e1.record()
+                ar_events.append((e0, e1))
+            else:
+                reducer.reduce()
+        opt.step()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(warmup):
+        step(i)
+    barrier()
+    B.launch_count_reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step(warmup + i)
+    e1.record()
+    barrier()
+    launches = B.launch_count() // steps
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / steps
+    ar_ms = None
+    if reducer is not None:
+        for i in range(4):
+            step(warmup + steps + i, time_allreduce=True)
+        torch.cuda.synchronize()
+        ar_ms = float(np.mean([a.elapsed_time(b) for a, b in ar_events]))
+    barrier()
+    del net, teacher, opt, reducer
+    torch.cuda.empty_cache()
+    return {'config': ('C3: OFAMobileNetS4 progressive-shrinking step' if which == 'c3' else
+                       'C4: OFAMobileNetX4 joint 2x/4x step with teacher distillation (kd 0.5)') +
+                      ', batch 64 x 96x96 HR patches per GPU, dynamic_batch_size 2, bf16 + fp32 masters, fused Adam' +
+                      (', flat NCCL all-reduce (tail overlapped with backward)' if world > 1 else ''),
+            'ms_per_step': ms_per_step, 'patches_per_s': world * per_gpu / (ms_per_step / 1e3),
+            'hr_mpix_per_s': world * per_gpu * 96 * 96 / 1e6 / (ms_per_step / 1e3),
+            'library_launches_per_step': int(launches), 'allreduce_ms': ar_ms, 'graphed': False,
+            'steps': steps, 'warmup': warmup, 'scaling': 'weak', 'timing': 'CUDA events around the timed steps, max over ranks'}
+
+
 def run_ours(args):
     import ofa_b200
     from ofa_b200 import backend as B, functional as OF
@@ -228,6 +376,8 @@ def run_ours(args):
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     assert torch.cuda.is_available(), 'bench.py (our arm) needs a CUDA device: there is no CPU path'
+    if world > 1:
+        pin_rank_to_cores(local_rank, int(os.environ.get('LOCAL_WORLD_SIZE', world)))
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     dist = None
@@ -372,6 +522,14 @@ def run_ours(args):
         roof.update({'kernel': tag, 'share_of_step': top['share'], 'peak_source': pk['source'],
                      'algorithmic_bytes': nbytes, 'kernels': table[:8]})
 
+    # ---- the workload WITH a collective: progressive-shrinking training steps (C3 on S4, C4 on X4) -------------
+    train = None
+    if not args.no_train:
+        del net
+        torch.cuda.empty_cache()
+        train = {'c3': run_train(dev, dist, rank, world, 'c3', args.train_steps, 8),
+                 'c4': run_train(dev, dist, rank, world, 'c4', max(4, args.train_steps // 2), 4)}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         pix, times = cpu_forward_sample(args.cpu_tile, 6, 1)
@@ -391,6 +549,7 @@ def run_ours(args):
             'e2e': {'value': e2e_val, 'unit': UNIT, 'h2d_bytes_per_step': x_host.numel() * 4,
                     'd2h_bytes_per_step': y_host.numel() * 4},
             'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu,
+            'train': train,
         }
         print(json.dumps(line))
     if dist is not None:

@@ -1,0 +1,1 @@
+from .progressive_shrinking import *  # noqa: F401,F403

@@ -44,7 +44,15 @@ class FusedAdam:
                  [(p, 0.0) for p in no_decay_params if p.requires_grad]
         assert groups, 'no parameters'
         self.params = [p for p, _ in groups]
-        self.lr, self.betas, self.eps = lr, betas, eps
+        self.betas, self.eps = betas, eps
+        # torch.optim-style view: the run manager writes param_group['lr'] (sr_run_manager.py:78-90) and checkpoints
+        # optimizer.state_dict() (sr_run_manager.py:301,539; progressive_shrinking.py:252)
+        self.param_groups = [
+            {'params': [p for p in decay_params if p.requires_grad], 'lr': lr, 'betas': betas, 'eps': eps,
+             'weight_decay': float(weight_decay)},
+            {'params': [p for p in no_decay_params if p.requires_grad], 'lr': lr, 'betas': betas, 'eps': eps,
+             'weight_decay': 0.0},
+        ]
         dev = self.params[0].device
         assert all(p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() for p in self.params), \
             'FusedAdam updates contiguous fp32 CUDA parameters in place'
@@ -63,6 +71,31 @@ class FusedAdam:
         self._steps = torch.zeros(len(groups), dtype=torch.int32, device=dev)
         self._grad_dev = torch.zeros(len(groups), dtype=torch.int64, device=dev)
         self._ptrs = [p.data_ptr() for p in self.params]
+
+    @property
+    def lr(self):
+        return self.param_groups[0]['lr']
+
+    @lr.setter
+    def lr(self, value):
+        for g in self.param_groups:
+            g['lr'] = value
+
+    def state_dict(self):
+        """Moments, per-tensor step counters and hyper-parameters (a resumed run continues Adam's bias correction)."""
+        return {'state': {'exp_avg': self.exp_avg.clone(), 'exp_avg_sq': self.exp_avg_sq.clone(),
+                          'steps': self._steps.clone()},
+                'param_groups': [{k: v for k, v in g.items() if k != 'params'} for g in self.param_groups]}
+
+    def load_state_dict(self, sd):
+        st = sd['state']
+        assert st['exp_avg'].numel() == self.exp_avg.numel(), 'optimizer state belongs to another parameter set'
+        self.exp_avg.copy_(st['exp_avg'])
+        self.exp_avg_sq.copy_(st['exp_avg_sq'])
+        self._steps.copy_(st['steps'])
+        for g, saved in zip(self.param_groups, sd['param_groups']):
+            g.update({k: v for k, v in saved.items() if k != 'weight_decay'})
+        self.betas, self.eps = tuple(self.param_groups[0]['betas']), self.param_groups[0]['eps']
 
     def zero_grad(self, set_to_none=True):
         for p in self.params:
