@@ -8,6 +8,6 @@ All activation math runs in libofa_sr_b200.so (include/ofa_sr_b200.h); there is 
 """
 from . import backend, functional  # noqa: F401
 from .functional import (set_compute_dtype, get_compute_dtype, set_impl, set_train_dtype, get_train_dtype,  # noqa: F401
-                         set_mid_dtype)
+                         set_mid_dtype, check_finite, set_overflow_policy, invalidate_packed_weights)
 
 __version__ = '0.1.0'

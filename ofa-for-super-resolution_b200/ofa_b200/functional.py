@@ -16,7 +16,22 @@ import torch
 
 from . import backend as B
 
-_state = {'compute_dtype': torch.float16, 'impl': B.IMPL_AUTO, 'mid_dtype': B.OFA_F16, 'train_dtype': torch.float32}
+_state = {'compute_dtype': torch.float16, 'impl': B.IMPL_AUTO, 'mid_dtype': B.OFA_F16, 'train_dtype': torch.float32,
+          'overflow': 'none'}
+
+
+def check_finite(t):
+    """True when every element of `t` is finite (one device reduction + one 1-byte read)."""
+    return bool(torch.isfinite(t).all().item())
+
+
+def set_overflow_policy(policy):
+    """fp16 activation storage (the default 16-bit format: it meets the 0.01 dB criterion) has a range of
+    65504; the 64-channel trunk is an UNCLAMPED residual stream, so a checkpoint with very large BatchNorm gammas can
+    leave it.  'none' (default): no check.  'fallback_bf16': a network-level inference forward whose fp16 result
+    contains inf / NaN is recomputed with bf16 storage (fp32 range); costs one device -> host flag read per forward."""
+    assert policy in ('none', 'fallback_bf16')
+    _state['overflow'] = policy
 
 
 def set_compute_dtype(dtype):
@@ -852,7 +867,18 @@ def scoped_forward(signature=None):
                 return fwd(self, x, *args, **kwargs)
             sig = signature(self, x) if signature is not None else None
             with forward_scope(self, x, sig):
-                return fwd(self, x, *args, **kwargs)
+                y = fwd(self, x, *args, **kwargs)
+            if (signature is not None and _state['overflow'] == 'fallback_bf16' and _state['compute_dtype'] == torch.float16
+                    and torch.is_tensor(y) and y.is_cuda and not torch.is_grad_enabled() and not self.training
+                    and not torch.cuda.is_current_stream_capturing() and not check_finite(y)):
+                _state['compute_dtype'] = torch.bfloat16
+                try:
+                    sig = signature(self, x)
+                    with forward_scope(self, x, sig):
+                        y = fwd(self, x, *args, **kwargs)
+                finally:
+                    _state['compute_dtype'] = torch.float16
+            return y
         forward.__doc__ = fwd.__doc__
         forward.__wrapped__ = fwd
         return forward
