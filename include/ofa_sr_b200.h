@@ -38,6 +38,9 @@ extern "C" {
 #define OFA_F32 0
 #define OFA_BF16 1
 #define OFA_F16 2 /* IEEE half: 16-bit activation storage with 3 more mantissa bits than bf16 */
+#define OFA_U8 3  /* OUTPUT tensors of ofa_conv_fwd only (thin-output kernel / CUDA-core kernel): the image as the
+                   * reference's consumer makes it, uint8 = round_half_even(clamp(y, 0, 1) * 255) -- tensor2img_np,
+                   * sr_run_manager.py:567-597 -- so a 4K frame leaves the device as 25 MB instead of 100 MB */
 
 /* activation codes (ofa/utils.py:242-314 build_activation) */
 #define OFA_ACT_NONE 0

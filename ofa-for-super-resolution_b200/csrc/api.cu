@@ -171,14 +171,22 @@ int ofa_conv_fwd(const OfaConvArgs* a, int32_t impl, void* stream) {
   if (rc) return rc;
   OFA_REQUIRE(a != nullptr, "ofa_conv_fwd: null args");
   if ((rc = check_tensor(&a->x, "x"))) return rc;
-  if ((rc = check_tensor(&a->y, "y"))) return rc;
+  if ((rc = check_tensor(&a->y, "y", /*allow_u8=*/true))) return rc;
   OFA_REQUIRE(a->ks >= 1 && (a->ks & 1), "conv kernel size must be odd (got %d)", a->ks);
   OFA_REQUIRE(a->cin >= 1 && a->cout >= 1, "conv: cin/cout must be positive");
   OFA_REQUIRE(a->x.c == a->cin, "conv: x has %d channels, cin = %d", a->x.c, a->cin);
   if ((rc = store_shape_ok(a))) return rc;
   if ((rc = check_epi(&a->epi, &a->y))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  OFA_REQUIRE(a->x.dtype != OFA_U8, "conv: uint8 is an OUTPUT format only");
+  OFA_REQUIRE(a->y.dtype != OFA_U8 || (a->store == OFA_STORE_PLAIN && !a->epi.residual),
+              "conv: uint8 output needs a plain store and no residual");
   if (impl != OFA_IMPL_SIMT && conv_out_rows_supported(a)) return launch_conv_out_rows(a, st);
+  if (a->y.dtype == OFA_U8) {           // only the thin-output kernel and the CUDA-core kernel write the uint8 image
+    OFA_REQUIRE(a->w != nullptr, "conv: null fp32 weight");
+    return launch_conv_simt(make_tv(&a->x), make_tv(&a->y), a->w, a->w_so, a->w_si, a->w_sh, a->w_sw, a->cin,
+                            a->cout, a->ks, a->flip, a->store, make_epi(&a->epi), st);
+  }
   if (impl != OFA_IMPL_SIMT && conv_stem_supported(a)) return launch_conv_stem(a, st);
   bool tc_ok = conv_tc_supported(a);
   if (impl == OFA_IMPL_FAST && !tc_ok)

@@ -116,6 +116,9 @@ conv_out_rows_kernel(const __grid_constant__ CUtensorMap tm_x, const ConvOutPara
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    // (Tried: two issuer warps on alternate output rows, as in the depthwise kernel -- one warp issues a tcgen05.mma only
+    // every ~51 clocks, an M128 x N16 x K16 one occupies the pipe for ~36.  Slower here, 0.278 -> 0.330 ms at C2: the
+    // four epilogue warps are the co-limiter and the extra spinning warp takes issue slots from them.)
     const int fmt = p.f16 ? 0 : 1;
     const uint32_t idesc = ptx::umma_idesc_f16(128, 16, fmt, fmt, 0, 0);
     const uint32_t sA_addr = ptx::smem_u32(sA), sB_addr = ptx::smem_u32(sB);

@@ -47,6 +47,7 @@ struct TV {
   __device__ __forceinline__ float ld(long long o) const {
     if (dtype == OFA_F32) return reinterpret_cast<const float*>(ptr)[o];
     if (dtype == OFA_F16) return __half2float(reinterpret_cast<const __half*>(ptr)[o]);
+    if (dtype == OFA_U8) return (float)reinterpret_cast<const uint8_t*>(ptr)[o] * (1.f / 255.f);
     return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(ptr)[o]);
   }
   __device__ __forceinline__ void st(long long o, float v) const {
@@ -54,6 +55,8 @@ struct TV {
       reinterpret_cast<float*>(ptr)[o] = v;
     else if (dtype == OFA_F16)
       reinterpret_cast<__half*>(ptr)[o] = __float2half_rn(v);
+    else if (dtype == OFA_U8)      // tensor2img_np: clamp_(0, 1) -> * 255.0 -> numpy round (half to even) -> uint8
+      reinterpret_cast<uint8_t*>(ptr)[o] = (uint8_t)rintf(fminf(fmaxf(v, 0.f), 1.f) * 255.f);
     else
       reinterpret_cast<__nv_bfloat16*>(ptr)[o] = __float2bfloat16_rn(v);
   }
@@ -77,10 +80,10 @@ inline bool is_nhwc_dense(const OfaTensor4* t) {
          t->sn == (int64_t)t->h * t->w * t->c;
 }
 inline bool c_inner(const OfaTensor4* t) { return t->sc == 1; }
-inline int check_tensor(const OfaTensor4* t, const char* name) {
+inline int check_tensor(const OfaTensor4* t, const char* name, bool allow_u8 = false) {
   if (!t) return fail(OFA_ERR_ARG, "%s: null tensor", name);
   if (!t->ptr) return fail(OFA_ERR_ARG, "%s: null data pointer", name);
-  if (t->dtype != OFA_F32 && t->dtype != OFA_BF16 && t->dtype != OFA_F16)
+  if (t->dtype != OFA_F32 && t->dtype != OFA_BF16 && t->dtype != OFA_F16 && !(allow_u8 && t->dtype == OFA_U8))
     return fail(OFA_ERR_ARG, "%s: bad dtype %d", name, t->dtype);
   if (t->n < 0 || t->c < 0 || t->h < 0 || t->w < 0) return fail(OFA_ERR_ARG, "%s: negative extent", name);
   return OFA_OK;

@@ -14,7 +14,7 @@ import torch
 _LIB_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'lib')
 LIB_PATH = os.path.join(_LIB_DIR, 'libofa_sr_b200.so')
 
-OFA_F32, OFA_BF16, OFA_F16 = 0, 1, 2
+OFA_F32, OFA_BF16, OFA_F16, OFA_U8 = 0, 1, 2, 3
 ACT_NONE, ACT_RELU6, ACT_HSWISH, ACT_RELU, ACT_HSIGMOID = 0, 1, 2, 3, 4
 STORE_PLAIN, STORE_PIXELSHUFFLE2, STORE_PIXELUNSHUFFLE2 = 0, 1, 2
 IMPL_AUTO, IMPL_SIMT, IMPL_FAST, IMPL_NHWC, IMPL_BAND, IMPL_PLANAR3 = 0, 1, 2, 3, 4, 5
@@ -171,7 +171,7 @@ def _dtype_code(t):
     raise RuntimeError('libofa_sr_b200 supports float32, bfloat16 and float16 activations, got %s' % t.dtype)
 
 
-_DTYPE_CODES = {torch.float32: OFA_F32, torch.bfloat16: OFA_BF16, torch.float16: OFA_F16}
+_DTYPE_CODES = {torch.float32: OFA_F32, torch.bfloat16: OFA_BF16, torch.float16: OFA_F16, torch.uint8: OFA_U8}
 
 
 def dtype_code(dtype):

@@ -11,6 +11,8 @@ References: ofa/elastic_nn/networks/ofa_mbs4.py:263-370, ofa_mbx4.py:345-453.
 """
 import random
 
+import torch
+
 from ...utils import MyNetwork, int2list
 
 _CONSTRAINT_KEYS = {
@@ -60,6 +62,14 @@ class ElasticSRSuperNet(MyNetwork):
         for i, dd in enumerate(depth):
             if dd is not None:
                 self.runtime_depth[i] = min(len(self.block_group_info[i]), dd)
+
+    def set_output_dtype(self, dtype):
+        """Format of the SR image the INFERENCE path returns (the reference API returns fp32; default).  torch.float16
+        halves, torch.uint8 quarters the device -> host traffic of a frame: uint8 is exactly what the reference's consumer
+        computes from the fp32 tensor, `tensor2img_np` = round(clamp(y, 0, 1) * 255) (sr_run_manager.py:567-597), written
+        by the last conv's epilogue.  Training / grad-enabled forwards always return fp32."""
+        assert dtype in (torch.float32, torch.float16, torch.uint8)
+        self.dec_final_output_conv_block.out_dtype = dtype
 
     def set_constraint(self, include_list, constraint_type='depth'):
         if constraint_type not in _CONSTRAINT_KEYS:

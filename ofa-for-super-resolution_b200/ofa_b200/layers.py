@@ -109,8 +109,9 @@ class ConvLayer(MyModule):
             else:
                 assert self._act_code == B.ACT_NONE and residual is None
                 y = OF.conv2d(x, w, self.in_channels, self.out_channels, self.kernel_size)
-            if self.out_dtype is not None and y.dtype != self.out_dtype:
-                y = y.to(self.out_dtype)      # mixed-precision training: the caller's loss sees fp32
+            if self.out_dtype is not None and y.dtype != torch.float32:
+                y = y.to(torch.float32)       # mixed-precision training: the caller's loss sees fp32 (whatever image
+                                              # format set_output_dtype chose for inference)
             return y
         if bn is not None:
             y = OF.conv_bn_act(x, w, self.in_channels, self.out_channels, self.kernel_size, bn, B.ACT_NONE, None)

@@ -465,3 +465,40 @@ def test_fused_adam_state_dict_round_trip(dev):
     run(t, ref, 3, 10)
     for p, r in zip(ps, ref):
         assert relerr(p, r) < 1e-5
+
+
+# =================================================================================================
+# image output formats of the inference path
+# =================================================================================================
+@pytest.mark.parametrize('kind,shape', [('s4', (2, 3, 40, 56)), ('s4', (1, 3, 96, 120)), ('x4', (1, 3, 64, 96))])
+def test_uint8_and_fp16_image_outputs(dev, kind, shape):
+    """set_output_dtype(torch.uint8): the last conv's epilogue writes round_half_even(clamp(y, 0, 1) * 255) -- exactly
+    the reference's tensor2img_np (sr_run_manager.py:567-597) applied to the fp32 output of the same forward, bit for bit;
+    torch.float16: the fp32 values rounded once."""
+    net, spec, sd = build(kind, [1, 2], 47, dev)
+    sub = dict(ks=5, e=4, d=3, pixel_d=2)
+    net.set_active_subnet(**sub)
+    x = torch.from_numpy(np.random.RandomState(3).rand(*shape).astype(np.float32)).to(dev)
+    with torch.no_grad():
+        y32 = net(x)
+        # put the random-weight output into the image range so that the clamp and every uint8 level are exercised
+        lo, hi = float(y32.min()), float(y32.max())
+        last = net.dec_final_output_conv_block
+        last.bn.weight.data.mul_(1.2 / (hi - lo))
+        last.bn.bias.data.copy_((last.bn.bias.data - lo) * (1.2 / (hi - lo)) - 0.1)
+        last.bn.running_mean.data.mul_(1.0)
+        y32 = net(x)
+        net.set_output_dtype(torch.uint8)
+        y8 = net(x)
+        net.set_output_dtype(torch.float16)
+        y16 = net(x)
+        net.set_output_dtype(torch.float32)
+    assert y8.dtype == torch.uint8 and y8.shape == y32.shape and y8.is_contiguous()
+    want = (y32.clamp(0, 1) * 255.0).round().to(torch.uint8)          # torch.round = half to even, as numpy's
+    assert torch.equal(y8, want)
+    assert int(want.min()) == 0 and int(want.max()) == 255 and len(torch.unique(want)) > 200
+    assert y16.dtype == torch.float16 and torch.equal(y16, y32.to(torch.float16))
+    # the reference metric on the uint8 image equals the metric computed from the fp32 tensor
+    t = torch.rand_like(y32)
+    from ofa_b200 import metrics
+    assert metrics.psnr_y(y32, t) == pytest.approx(metrics.psnr_y(y8.float() / 255.0, t), abs=1e-9)
