@@ -47,6 +47,7 @@ def parse():
     ap.add_argument('--cpu-tile', type=int, default=256, help='LR tile edge of the bounded CPU-baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-train', action='store_true', help='skip the training-step measurements (the `train` object)')
+    ap.add_argument('--no-extras', action='store_true', help='skip the secondary configurations (the `extra` object)')
     ap.add_argument('--train-steps', type=int, default=20)
     ap.add_argument('--dtype', default='f16', choices=['f16', 'bf16', 'fp32'],
                     help='activation storage of our arm: f16 (default; meets the 0.01 dB PSNR criterion), bf16 (same speed) or fp32 (exact CUDA-core path)')
@@ -64,7 +65,7 @@ def peaks():
 
 
 # ncu --set full captures of the hot kernels (profiles/*.csv, written by tools/ncu_summary.py): DRAM bytes per launch
-NCU_PROFILES = {'dw7x7 C384 planar': 'r1_ncu_dw7_planar_v3.csv', 'mbconv expand 64->384 planar': 'r1_ncu_expand_planar_v1.csv',
+NCU_PROFILES = {'dw7x7 C384 planar': 'r2_ncu_dw7_planar_dual_issuer.csv', 'mbconv expand 64->384 planar': 'r1_ncu_expand_planar_v1.csv',
                 'mbconv project 384->64 planar': 'r1_ncu_project_planar_v1.csv', 'conv5x5 64->3 rows-tc': 'r1_ncu_conv_out_rows_v1.csv'}
 
 
@@ -362,11 +363,137 @@ def run_train(dev, dist, rank, world, which, steps, warmup):
     return {'config': ('C3: OFAMobileNetS4 progressive-shrinking step' if which == 'c3' else
                        'C4: OFAMobileNetX4 joint 2x/4x step with teacher distillation (kd 0.5)') +
                       ', batch 64 x 96x96 HR patches per GPU, dynamic_batch_size 2, bf16 + fp32 masters, fused Adam' +
-                      (', flat NCCL all-reduce (tail overlapped with backward)' if world > 1 else ''),
+                      ((', flat NCCL all-reduce' + (' (tail overlapped with backward)' if which == 'c3' else '')) if world > 1 else ''),
             'ms_per_step': ms_per_step, 'patches_per_s': world * per_gpu / (ms_per_step / 1e3),
             'hr_mpix_per_s': world * per_gpu * 96 * 96 / 1e6 / (ms_per_step / 1e3),
             'library_launches_per_step': int(launches), 'allreduce_ms': ar_ms, 'graphed': False,
             'steps': steps, 'warmup': warmup, 'scaling': 'weak', 'timing': 'CUDA events around the timed steps, max over ranks'}
+
+
+def run_extras(args, dev, dist, rank, world, net, x_host, flush):
+    """Secondary measurements, each a handful of forwards (max over ranks where ranks take part):
+      serial_latency : one frame, pinned host -> device -> net -> fp32 image -> pinned host, nothing overlapped
+      e2e_uint8      : the pipelined e2e loop with the uint8 image output (set_output_dtype), 4x less D2H
+      lr1080_to_8k   : LR 1920x1080 -> 7680x4320 (second frame size)
+      c1             : S4 smallest sub-network (ks 3, e 3, d 2, one PixelShuffle stage), 1x3x256x256 -> 512x512, eager and
+                       as a CUDA graph (BASELINE.json configs[0])
+      tile_sharded   : (N > 1) ONE 960x540 frame cut into N tiles with a 64-px LR halo, one tile per rank, no collective
+                       (parallel.tiled_forward): single-frame latency, strong scaling"""
+    import ofa_b200
+    from ofa_b200 import parallel as P
+    from ofa_b200.elastic_nn.networks import OFAMobileNetS4
+    out = {}
+    H, W = args.lr_h, args.lr_w
+
+    def maxr(ms):
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def ev_ms(fn, reps=5, warm=2):
+        with torch.no_grad():
+            for _ in range(warm):
+                fn()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(reps):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn()
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+        return float(np.median(ts))
+
+    # serial per-frame latency (no overlap between copies and compute)
+    y_host = torch.empty(1, 3, 4 * H, 4 * W, dtype=torch.float32).pin_memory()
+    x_d = torch.empty(1, 3, H, W, device=dev)
+
+    def serial():
+        x_d.copy_(x_host, non_blocking=True)
+        y_host.copy_(net(x_d), non_blocking=True)
+    out['serial_latency'] = {'ms_per_frame': maxr(ev_ms(serial)), 'what': 'H2D (pinned) + forward + D2H of the fp32 image, one stream'}
+
+    # uint8 image output: same forward, the last epilogue writes tensor2img_np's uint8
+    net.set_output_dtype(torch.uint8)
+    y8_host = [torch.empty(1, 3, 4 * H, 4 * W, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    cs = torch.cuda.Stream(device=dev)
+    st = {'i': 0}
+
+    def e2e_u8():
+        i = st['i'] & 1
+        st['i'] += 1
+        x_d.copy_(x_host, non_blocking=True)
+        y = net(x_d)
+        ready = torch.cuda.Event()
+        ready.record()
+        with torch.cuda.stream(cs):
+            cs.wait_event(ready)
+            y8_host[i].copy_(y, non_blocking=True)
+            y.record_stream(cs)
+    with torch.no_grad():
+        for _ in range(3):
+            e2e_u8()
+        torch.cuda.current_stream().wait_stream(cs)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            e2e_u8()
+        torch.cuda.current_stream().wait_stream(cs)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = maxr(e0.elapsed_time(e1)) / args.steps
+    out['e2e_uint8'] = {'value': world * 16 * H * W / 1e6 / (ms / 1e3), 'unit': UNIT, 'ms_per_step': ms,
+                        'h2d_bytes_per_step': 12 * H * W, 'd2h_bytes_per_step': 3 * 16 * H * W,
+                        'what': 'as e2e, uint8 image output (tensor2img_np in the last epilogue); L2 not flushed between steps'}
+    net.set_output_dtype(torch.float32)
+
+    # LR 1920x1080 -> 8K
+    if (H, W) == (540, 960):
+        xb = torch.rand(1, 3, 1080, 1920, device=dev)
+        ms = maxr(ev_ms(lambda: net(xb), reps=3, warm=1))
+        out['lr1080_to_8k'] = {'ms_per_step': ms, 'value': world * 16 * 1080 * 1920 / 1e6 / (ms / 1e3), 'unit': UNIT}
+        del xb
+
+    # C1: smallest sub-network, 2x, 256x256
+    if rank == 0:
+        c1 = OFAMobileNetS4(ks_list=[3, 5, 7], expand_ratio_list=[3, 4, 6], depth_list=[2, 3, 4], pixelshuffle_depth_list=[1])
+        synth_weights(c1, WEIGHT_SEED + 2)
+        c1.set_active_subnet(ks=3, e=3, d=2, pixel_d=1)
+        c1 = c1.to(dev).eval()
+        x1 = torch.rand(1, 3, 256, 256, device=dev)
+        eager = ev_ms(lambda: c1(x1), reps=20, warm=5)
+        with torch.no_grad():
+            g = torch.cuda.CUDAGraph()
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                c1(x1)
+            torch.cuda.current_stream().wait_stream(s)
+            with torch.cuda.graph(g):
+                y1 = c1(x1)
+        graph = ev_ms(g.replay, reps=20, warm=5)
+        out['c1'] = {'workload': 'S4 smallest sub-network (ks 3, e 3, d 2, 1 PixelShuffle stage), 1x3x256x256 -> %dx%d' % (y1.shape[2], y1.shape[3]),
+                     'eager_ms': eager, 'graph_ms': graph, 'value': y1.shape[2] * y1.shape[3] / 1e6 / (graph / 1e3), 'unit': UNIT}
+        del c1, g
+
+    # one frame, tile-sharded over the ranks (strong scaling of the latency)
+    if world > 1:
+        ty = 2 if world >= 4 else 1
+        tx = world // ty
+        xf = x_host.to(dev)
+
+        def tiled():
+            P.tiled_forward(net, xf, ty, tx, halo=P.S4_HALO_LR, scale=4, rank=rank, world=world)
+        ms = maxr(ev_ms(tiled))
+        out['tile_sharded'] = {'tiles': [ty, tx], 'halo_lr_px': P.S4_HALO_LR, 'latency_ms': ms,
+                               'value': 16 * H * W / 1e6 / (ms / 1e3), 'unit': UNIT, 'scaling': 'strong'}
+    return out
 
 
 def run_ours(args):
@@ -496,21 +623,24 @@ def run_ours(args):
                 net(x_dev)
         torch.cuda.synchronize()
         OF.set_profiler(None)
+        # a tag can cover launches of different sizes (the PixelShuffle conv runs at 1x and at 2x resolution): flops and
+        # bytes are SUMMED over the launches, so the rates are true averages (round 1 kept the first launch's figures)
         agg = {}
         for tag, flops, nbytes, e0, e1 in rec:
-            a = agg.setdefault(tag, [0.0, 0, flops, nbytes])
+            a = agg.setdefault(tag, [0.0, 0, 0.0, 0.0])
             a[0] += e0.elapsed_time(e1)
             a[1] += 1
+            a[2] += flops
+            a[3] += nbytes
         total = sum(a[0] for a in agg.values())
         pk = peaks()
         table = []
         for tag, (ms, cnt, flops, nbytes) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
-            avg_s = ms / cnt / 1e3
             table.append({'kernel': tag, 'share': ms / total, 'launches_per_step': cnt // 3, 'avg_ms': ms / cnt,
-                          'GBps': nbytes / avg_s / 1e9, 'TFLOPs': flops / avg_s / 1e12})
+                          'GBps': nbytes / (ms / 1e3) / 1e9, 'TFLOPs': flops / (ms / 1e3) / 1e12})
         top = table[0]
         tag = top['kernel']
-        _, _, flops, nbytes = agg[tag]
+        flops, nbytes = agg[tag][2] / agg[tag][1], agg[tag][3] / agg[tag][1]
         tensor_bound = tag.startswith('conv') and tag.endswith('tc') and (flops / nbytes) > 247
         if tensor_bound:
             roof = {'bound': 'tensor', 'achieved': top['TFLOPs'], 'peak': pk['tensor_sustained'], 'unit': 'TFLOP/s',
@@ -522,13 +652,16 @@ def run_ours(args):
         roof.update({'kernel': tag, 'share_of_step': top['share'], 'peak_source': pk['source'],
                      'algorithmic_bytes': nbytes, 'kernels': table[:8]})
 
+    # ---- secondary configurations: reported, not the headline ---------------------------------------
+    extra = run_extras(args, dev, dist, rank, world, net, x_host, flush) if not args.no_extras else None
+
     # ---- the workload WITH a collective: progressive-shrinking training steps (C3 on S4, C4 on X4) -------------
     train = None
     if not args.no_train:
         del net
         torch.cuda.empty_cache()
         train = {'c3': run_train(dev, dist, rank, world, 'c3', args.train_steps, 8),
-                 'c4': run_train(dev, dist, rank, world, 'c4', max(4, args.train_steps // 2), 4)}
+                 'c4': run_train(dev, dist, rank, world, 'c4', max(4, args.train_steps // 2), 8)}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -549,7 +682,7 @@ def run_ours(args):
             'e2e': {'value': e2e_val, 'unit': UNIT, 'h2d_bytes_per_step': x_host.numel() * 4,
                     'd2h_bytes_per_step': y_host.numel() * 4},
             'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu,
-            'train': train,
+            'train': train, 'extra': extra,
         }
         print(json.dumps(line))
     if dist is not None:

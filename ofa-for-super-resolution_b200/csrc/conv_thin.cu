@@ -28,12 +28,13 @@ namespace {
 // (1) thin-output conv on tcgen05
 // ==================================================================================================
 constexpr int CO_MPIX = 128;               // pixels of one image row per tile = UMMA M
-constexpr int CO_RING = 12;                // image rows resident (16 KiB each)
+constexpr int CO_RING = 10;                // image rows resident (16 KiB each)
 constexpr int CO_ROW_BYTES = CO_MPIX * 128;
 constexpr int CO_RB = 32;                  // output rows per work item
 constexpr int CO_ACC = 8;                  // accumulator stages (16 TMEM columns each)
 constexpr int CO_PPITCH = CO_MPIX + 4;     // floats per row of the transpose buffer
-constexpr int CO_THREADS = 6 * 32;         // TMA, MMA, 4 epilogue warps
+constexpr int CO_THREADS = 11 * 32;        // TMA, MMA issuer 0, epilogue set 0 (4 warps), epilogue set 1 (4), MMA issuer 1
+constexpr int CO_ISSUER1_WARP = 10;
 
 struct ConvOutParams {
   int N, H, W, cout, ks, f16;
@@ -43,16 +44,17 @@ struct ConvOutParams {
   TV y;
 };
 
-// KS_ / COUT_: compile-time kernel size and output channels (0 = take them from the parameters)
-template <int KS_, int COUT_>
+// KS_ / COUT_: compile-time kernel size and output channels (0 = take them from the parameters); OUT_: output format
+// known at compile time (OFA_F32 / OFA_U8 planar images; -1 = any, through TV::st)
+template <int KS_, int COUT_, int OUT_>
 __global__ void __launch_bounds__(CO_THREADS, 1)
 conv_out_rows_kernel(const __grid_constant__ CUtensorMap tm_x, const ConvOutParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
   uint8_t* sA = smem;                                              // ring of image rows
   uint8_t* sB = sA + CO_RING * CO_ROW_BYTES;                       // ks x [16 rows x 128 B] weights, swizzled
-  float* sP = reinterpret_cast<float*>(sB + 5 * 2048);             // 2 x [16][CO_PPITCH] transpose buffers
-  float* s_scale = sP + 2 * 16 * CO_PPITCH;
+  float* sP = reinterpret_cast<float*>(sB + 5 * 2048);             // 2 sets x 2 x [16][CO_PPITCH] transpose buffers
+  float* s_scale = sP + 4 * 16 * CO_PPITCH;
   float* s_shift = s_scale + 8;
   uint64_t* full = reinterpret_cast<uint64_t*>(s_shift + 8);
   uint64_t* empty = full + CO_RING;
@@ -83,7 +85,8 @@ conv_out_rows_kernel(const __grid_constant__ CUtensorMap tm_x, const ConvOutPara
   ptx::fence_proxy_async();
   if (warp == 0 && lane == 0) ptx::prefetch_tmap(&tm_x);
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < CO_RING; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+    // both MMA issuers release a ring row (each commits at every output row, see below)
+    for (int s = 0; s < CO_RING; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 2); }
     for (int a = 0; a < CO_ACC; ++a) { ptx::mbar_init(&tfull[a], 1); ptx::mbar_init(&tempty[a], 4); }
     ptx::fence_barrier_init();
   }
@@ -114,11 +117,15 @@ conv_out_rows_kernel(const __grid_constant__ CUtensorMap tm_x, const ConvOutPara
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    // (Tried: two issuer warps on alternate output rows, as in the depthwise kernel -- one warp issues a tcgen05.mma only
-    // every ~51 clocks, an M128 x N16 x K16 one occupies the pipe for ~36.  Slower here, 0.278 -> 0.330 ms at C2: the
-    // four epilogue warps are the co-limiter and the extra spinning warp takes issue slots from them.)
+  } else if (warp == 1 || warp == CO_ISSUER1_WARP) {
+    // ===================== MMA issuers =====================
+    // An M128 x N16 x K16 MMA occupies the tensor pipe for ~36 clocks (4.5 KB of operands at 128 B/clk) but one warp
+    // issues a tcgen05.mma only every ~51 (csrc/experiments/umma_rate_probe.cu), and one set of four epilogue warps
+    // needs about as long per output row as the 20 MMAs take.  Output rows ALTERNATE between two (issuer, epilogue set)
+    // pairs; each row has its own accumulator stage.  Both issuers walk every row -- waits and ring bookkeeping stay in
+    // step -- and both commit the release of the oldest ring row (it was read by MMAs of both; a commit only tracks its
+    // own thread's).
+    const int issuer = warp == 1 ? 0 : 1;
     const int fmt = p.f16 ? 0 : 1;
     const uint32_t idesc = ptx::umma_idesc_f16(128, 16, fmt, fmt, 0, 0);
     const uint32_t sA_addr = ptx::smem_u32(sA), sB_addr = ptx::smem_u32(sB);
@@ -138,21 +145,23 @@ conv_out_rows_kernel(const __grid_constant__ CUtensorMap tm_x, const ConvOutPara
           ptx::mbar_wait(&full[waited], wph);
           if (++waited == CO_RING) { waited = 0; wph ^= 1; }
         }
-        ptx::mbar_wait(&tempty[acc], accph ^ 1);
-        ptx::tc_fence_after();
-        const uint32_t d0 = tmem_base + (uint32_t)(acc * 16);
+        if ((j & 1) == issuer) {
+          ptx::mbar_wait(&tempty[acc], accph ^ 1);
+          ptx::tc_fence_after();
+          const uint32_t d0 = tmem_base + (uint32_t)(acc * 16);
 #pragma unroll
-        for (int ky = 0; ky < (KS_ ? KS_ : 5); ++ky) {
-          if (ky >= ks) break;
-          int slot = head + ky;
-          if (slot >= CO_RING) slot -= CO_RING;
-          const uint64_t da = ptx::umma_desc_sw128(sA_addr + (uint32_t)(slot * CO_ROW_BYTES), 1024);
-          const uint64_t db = ptx::umma_desc_sw128(sB_addr + (uint32_t)(ky * 2048), 1024);
+          for (int ky = 0; ky < (KS_ ? KS_ : 5); ++ky) {
+            if (ky >= ks) break;
+            int slot = head + ky;
+            if (slot >= CO_RING) slot -= CO_RING;
+            const uint64_t da = ptx::umma_desc_sw128(sA_addr + (uint32_t)(slot * CO_ROW_BYTES), 1024);
+            const uint64_t db = ptx::umma_desc_sw128(sB_addr + (uint32_t)(ky * 2048), 1024);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            ptx::umma_elect(d0, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (uint32_t)(ky | k));
+            for (int k = 0; k < 4; ++k)
+              ptx::umma_elect(d0, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (uint32_t)(ky | k));
+          }
+          ptx::umma_commit_elect(&tfull[acc]);
         }
-        ptx::umma_commit_elect(&tfull[acc]);
         ptx::umma_commit_elect(&empty[head]);          // the oldest row is not used by later output rows
         if (++head == CO_RING) head = 0;
         if (++acc == CO_ACC) { acc = 0; accph ^= 1; }
@@ -164,7 +173,8 @@ conv_out_rows_kernel(const __grid_constant__ CUtensorMap tm_x, const ConvOutPara
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5): lane = pixel of the row segment =====================
+    // ===================== epilogue sets (warps 2..5 / 6..9): lane = pixel of the row segment =====================
+    const int eset = (warp - 2) >> 2;          // rows j with (j & 1) == eset
     const int quarter = warp & 3;
     const int xl = quarter * 32 + lane;
     int acc = 0, pb = 0; uint32_t accph = 0;
@@ -176,6 +186,10 @@ conv_out_rows_kernel(const __grid_constant__ CUtensorMap tm_x, const ConvOutPara
       const int X = x0 + xl;
       const bool valid = xl >= R && xl < CO_MPIX - R && X < p.W;
       for (int j = 0; j < rows; ++j) {
+        if ((j & 1) != eset) {                  // the other set's row
+          if (++acc == CO_ACC) { acc = 0; accph ^= 1; }
+          continue;
+        }
         ptx::mbar_wait(&tfull[acc], accph);
         ptx::tc_fence_after();
         uint32_t v[16];
@@ -185,10 +199,10 @@ conv_out_rows_kernel(const __grid_constant__ CUtensorMap tm_x, const ConvOutPara
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
         if (++acc == CO_ACC) { acc = 0; accph ^= 1; }
-        float* P = sP + pb * 16 * CO_PPITCH;
+        float* P = sP + (eset * 2 + pb) * 16 * CO_PPITCH;
 #pragma unroll
         for (int c = 0; c < 16; ++c) P[c * CO_PPITCH + xl] = __uint_as_float(v[c]);
-        ptx::named_bar_sync(1, 128);
+        ptx::named_bar_sync(1 + eset, 128);
         if (valid) {
           const int Y = y0 + j;
 #pragma unroll
@@ -200,7 +214,9 @@ conv_out_rows_kernel(const __grid_constant__ CUtensorMap tm_x, const ConvOutPara
               if (kx < ks) s += P[(kx * cout + co) * CO_PPITCH + xl + kx - R];
             float o = apply_act(fmaf(s, s_scale[co], s_shift[co]), p.epi.act);
             if (p.epi.res.ptr) o += p.epi.res.ld(p.epi.res.off(n, co, Y, X));
-            if (p.y.dtype == OFA_F32) reinterpret_cast<float*>(p.y.ptr)[p.y.off(n, co, Y, X)] = o;
+            if (OUT_ == OFA_F32) reinterpret_cast<float*>(p.y.ptr)[p.y.off(n, co, Y, X)] = o;
+            else if (OUT_ == OFA_U8)
+              reinterpret_cast<uint8_t*>(p.y.ptr)[p.y.off(n, co, Y, X)] = (uint8_t)rintf(fminf(fmaxf(o, 0.f), 1.f) * 255.f);
             else p.y.st(p.y.off(n, co, Y, X), o);
           }
         }
@@ -373,18 +389,22 @@ int launch_conv_out_rows(const OfaConvArgs* a, cudaStream_t st) {
   int rc = encode_tmap(&tx, p.f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a->x.ptr, dims,
                        strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
-  const size_t smem = 1024 + CO_RING * CO_ROW_BYTES + 5 * 2048 + 2 * 16 * CO_PPITCH * 4 + 64 + (2 * CO_RING + 2 * CO_ACC) * 8 + 64;
+  const size_t smem = 1024 + CO_RING * CO_ROW_BYTES + 5 * 2048 + 4 * 16 * CO_PPITCH * 4 + 64 + (2 * CO_RING + 2 * CO_ACC) * 8 + 64;
   const int num_work = p.N * p.strips * p.row_blocks;
   int grid = sm_count();
   if (grid > num_work) grid = num_work;
-#define OFA_CO_LAUNCH(K_, C_)                                                                                       \
+#define OFA_CO_LAUNCH(K_, C_, O_)                                                                                    \
   do {                                                                                                              \
-    OFA_CUDA(cudaFuncSetAttribute(conv_out_rows_kernel<K_, C_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    conv_out_rows_kernel<K_, C_><<<grid, CO_THREADS, smem, st>>>(tx, p);                                            \
+    OFA_CUDA(cudaFuncSetAttribute(conv_out_rows_kernel<K_, C_, O_>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                  (int)smem));                                                                      \
+    conv_out_rows_kernel<K_, C_, O_><<<grid, CO_THREADS, smem, st>>>(tx, p);                                        \
   } while (0)
-  if (p.ks == 5 && p.cout == 3) OFA_CO_LAUNCH(5, 3);
-  else if (p.ks == 3 && p.cout == 3) OFA_CO_LAUNCH(3, 3);
-  else OFA_CO_LAUNCH(0, 0);
+  const int od = a->y.dtype;
+  if (p.ks == 5 && p.cout == 3 && od == OFA_F32) OFA_CO_LAUNCH(5, 3, OFA_F32);
+  else if (p.ks == 5 && p.cout == 3 && od == OFA_U8) OFA_CO_LAUNCH(5, 3, OFA_U8);
+  else if (p.ks == 3 && p.cout == 3 && od == OFA_F32) OFA_CO_LAUNCH(3, 3, OFA_F32);
+  else if (p.ks == 3 && p.cout == 3 && od == OFA_U8) OFA_CO_LAUNCH(3, 3, OFA_U8);
+  else OFA_CO_LAUNCH(0, 0, -1);
 #undef OFA_CO_LAUNCH
   return check_launch("conv_out_rows_kernel");
 }
