@@ -39,6 +39,7 @@ constexpr int BD_THREADS = 352;          // 11 warps: TMA producer, MMA issuer, 
 constexpr int BD_T1H = 136;              // ring slot rows of t1 (128 + 6 halo rows, rounded up to the 4-row E tiles)
 constexpr int BD_BAR_OFF = 222720;       // barrier block at a fixed offset behind the largest role's buffers
 constexpr int BD_SMEM = 1024 + BD_BAR_OFF + 512;
+constexpr int BD_PJ_STAGES = 8;          // project role: operand stages (the stand-alone kernel has 9; here D's buffers set the size)
 
 struct BandParams {
   int N, H, W, mid, mt, kcs, xf16;
@@ -242,14 +243,12 @@ __device__ __forceinline__ void role_expand(uint8_t* smem, uint64_t* bars, uint3
                   for (int i = 0; i < 4; ++i) {
                     float a = fmaf(__uint_as_float(v[j * 8 + 2 * i]), scale, shift);
                     float b = fmaf(__uint_as_float(v[j * 8 + 2 * i + 1]), scale, shift);
-                    a = fminf(fmaxf(a, 0.f), 6.f);
-                    b = fminf(fmaxf(b, 0.f), 6.f);
                     if (edge) {
                       const int px = j * 8 + 2 * i;
                       if (px < lo || px >= hi) a = 0.f;
                       if (px + 1 < lo || px + 1 >= hi) b = 0.f;
                     }
-                    pk[i] = pack16(a, b, F16);
+                    pk[i] = pack16_relu6(a, b, F16);
                   }
                   *reinterpret_cast<uint4*>(dst + ((j ^ (lane & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 }
@@ -457,9 +456,7 @@ __device__ __forceinline__ void role_depthwise(uint8_t* smem, uint64_t* bars, ui
           for (int i = 0; i < 28; ++i) {
             float a = fmaf(__uint_as_float(v[2 * i]), scale, shift);
             float b = fmaf(__uint_as_float(v[2 * i + 1]), scale, shift);
-            a = fminf(fmaxf(a, 0.f), 6.f);
-            b = fminf(fmaxf(b, 0.f), 6.f);
-            pk[i] = pack16(a, b, F16);
+            pk[i] = pack16_relu6(a, b, F16);
           }
           if (issuer) ptx::tma_store_wait_read<1>();
           ptx::named_bar_sync(1, 32 * DW_EPI_WARPS);
@@ -506,13 +503,13 @@ __device__ __forceinline__ void role_project(uint8_t* smem, uint64_t* bars, uint
                                              const CUtensorMap* tm_r, const CUtensorMap* tm_y,
                                              const CUtensorMap* tm_yp, const BandParams& p) {
   uint8_t* sA = smem;
-  uint8_t* sW = sA + PJ_A_STAGES * PJ_A_BYTES;
+  uint8_t* sW = sA + BD_PJ_STAGES * PJ_A_BYTES;
   uint8_t* sR = sW + PJ_MAX_KC * 8192;
   float* s_scale = reinterpret_cast<float*>(sR + 2 * PJ_R_BYTES);
   float* s_shift = s_scale + 64;
   uint64_t* a_full = bars;
-  uint64_t* a_empty = a_full + PJ_A_STAGES;
-  uint64_t* tfull = a_empty + PJ_A_STAGES;
+  uint64_t* a_empty = a_full + BD_PJ_STAGES;
+  uint64_t* tfull = a_empty + BD_PJ_STAGES;
   uint64_t* tempty = tfull + PJ_ACC_STAGES;
   uint64_t* r_full = tempty + PJ_ACC_STAGES;
   uint64_t* r_empty = r_full + 2;
@@ -555,7 +552,7 @@ __device__ __forceinline__ void role_project(uint8_t* smem, uint64_t* bars, uint
             for (int h = 0; h < 2; ++h)
               ptx::tma_load_4d(sA + s * PJ_A_BYTES + h * 8192, tm_t2l, &a_full[s], bcol[h], min(brow[h], DW_TH - 1),
                                kc * 64, g.slot);
-            if (++s == PJ_A_STAGES) { s = 0; ph ^= 1; }
+            if (++s == BD_PJ_STAGES) { s = 0; ph ^= 1; }
           }
         }
         base += g.p_tiles;
@@ -589,7 +586,7 @@ __device__ __forceinline__ void role_project(uint8_t* smem, uint64_t* bars, uint
             ptx::umma_elect(d0, da, db + (uint64_t)(k * 2), idesc, (uint32_t)(kc | k));
           }
           ptx::umma_commit_elect(&a_empty[s]);
-          if (++s == PJ_A_STAGES) { s = 0; ph ^= 1; }
+          if (++s == BD_PJ_STAGES) { s = 0; ph ^= 1; }
         }
         ptx::umma_commit_elect(&tfull[acc]);
         if (++acc == PJ_ACC_STAGES) { acc = 0; accph ^= 1; }
@@ -706,10 +703,10 @@ mbconv_band_kernel(const __grid_constant__ CUtensorMap tm_x4, const __grid_const
       for (int a = 0; a < DW_ACC_STAGES; ++a) { ptx::mbar_init(&tfull[a], 1); ptx::mbar_init(&tempty[a], DW_EPI_WARPS); }
       for (int b = 0; b < 2; ++b) { ptx::mbar_init(&b_full[b], 1); ptx::mbar_init(&b_empty[b], 1); }
     } else {
-      uint64_t* a_full = bars; uint64_t* a_empty = a_full + PJ_A_STAGES; uint64_t* tfull = a_empty + PJ_A_STAGES;
+      uint64_t* a_full = bars; uint64_t* a_empty = a_full + BD_PJ_STAGES; uint64_t* tfull = a_empty + BD_PJ_STAGES;
       uint64_t* tempty = tfull + PJ_ACC_STAGES; uint64_t* r_full = tempty + PJ_ACC_STAGES; uint64_t* r_empty = r_full + 2;
       uint64_t* w_bar = r_empty + 2;
-      for (int s = 0; s < PJ_A_STAGES; ++s) { ptx::mbar_init(&a_full[s], 1); ptx::mbar_init(&a_empty[s], 1); }
+      for (int s = 0; s < BD_PJ_STAGES; ++s) { ptx::mbar_init(&a_full[s], 1); ptx::mbar_init(&a_empty[s], 1); }
       for (int a = 0; a < PJ_ACC_STAGES; ++a) { ptx::mbar_init(&tfull[a], 1); ptx::mbar_init(&tempty[a], 4); }
       for (int b = 0; b < 2; ++b) { ptx::mbar_init(&r_full[b], 1); ptx::mbar_init(&r_empty[b], 1); }
       ptx::mbar_init(w_bar, 1);
@@ -717,7 +714,7 @@ mbconv_band_kernel(const __grid_constant__ CUtensorMap tm_x4, const __grid_const
     ptx::fence_barrier_init();
   }
   if (role == 2 && threadIdx.x < 64) {
-    float* s_scale = reinterpret_cast<float*>(smem + PJ_A_STAGES * PJ_A_BYTES + PJ_MAX_KC * 8192 + 2 * PJ_R_BYTES);
+    float* s_scale = reinterpret_cast<float*>(smem + BD_PJ_STAGES * PJ_A_BYTES + PJ_MAX_KC * 8192 + 2 * PJ_R_BYTES);
     float sc, sh;
     bn_fold(p.g3, p.b3, p.m3, p.v3, p.eps3, threadIdx.x, sc, sh);
     s_scale[threadIdx.x] = sc;

@@ -169,9 +169,12 @@ expand_planar_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
               for (int i = 0; i < 4; ++i) {
                 float a = fmaf(__uint_as_float(v[j * 8 + 2 * i]), scale, shift);
                 float b = fmaf(__uint_as_float(v[j * 8 + 2 * i + 1]), scale, shift);
-                if (RELU6) { a = fminf(fmaxf(a, 0.f), 6.f); b = fminf(fmaxf(b, 0.f), 6.f); }
-                else { a = apply_act(a, p.act); b = apply_act(b, p.act); }
-                pk[i] = pack16(a, b, F16);
+                if (RELU6) {
+                  pk[i] = pack16_relu6(a, b, F16);
+                } else {
+                  a = apply_act(a, p.act); b = apply_act(b, p.act);
+                  pk[i] = pack16(a, b, F16);
+                }
               }
               *reinterpret_cast<uint4*>(dst + ((j ^ (lane & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
@@ -442,9 +445,12 @@ dw_planar_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       for (int i = 0; i < 28; ++i) {
         float a = fmaf(__uint_as_float(v[2 * i]), scale, shift);
         float b = fmaf(__uint_as_float(v[2 * i + 1]), scale, shift);
-        if (RELU6) { a = fminf(fmaxf(a, 0.f), 6.f); b = fminf(fmaxf(b, 0.f), 6.f); }
-        else { a = apply_act(a, p.act); b = apply_act(b, p.act); }
-        pk[i] = pack16(a, b, F16);
+        if (RELU6) {
+          pk[i] = pack16_relu6(a, b, F16);
+        } else {
+          a = apply_act(a, p.act); b = apply_act(b, p.act);
+          pk[i] = pack16(a, b, F16);
+        }
       }
       if (issuer) ptx::tma_store_wait_read<1>();       // the store that last read staging tile `ob` is done
       ptx::named_bar_sync(1, 32 * DW_EPI_WARPS);
@@ -530,6 +536,16 @@ project_planar_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
       int s = 0, rb = 0; uint32_t ph = 0, rph = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int n = t / p.tiles_per_img, p0 = (t - n * p.tiles_per_img) * PJ_MPIX;
+        for (int kc = 0; kc < p.kcs; ++kc) {
+          ptx::mbar_wait(&a_empty[s], ph ^ 1);
+          ptx::mbar_arrive_expect_tx(&a_full[s], PJ_A_BYTES);
+          ptx::tma_load_3d(sA + s * PJ_A_BYTES, &tm_a, &a_full[s], p0, kc * 64, n);
+          ptx::tma_load_3d(sA + s * PJ_A_BYTES + 8192, &tm_a, &a_full[s], p0 + 64, kc * 64, n);
+          if (++s == PJ_A_STAGES) { s = 0; ph ^= 1; }
+        }
+        // The residual / output staging tile AFTER the operand loads: it is freed by the epilogue of the PREVIOUS tile,
+        // and waiting for it first (round 1) kept the producer from running ahead -- tile t's loads could only start
+        // once tile t-1 was loaded, multiplied and drained: one HBM latency (~2 us) per tile, 8000 clocks per tile.
         ptx::mbar_wait(&r_empty[rb], rph ^ 1);
         if (p.has_res) {
           ptx::mbar_arrive_expect_tx(&r_full[rb], PJ_R_BYTES);
@@ -538,13 +554,6 @@ project_planar_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
           ptx::mbar_arrive(&r_full[rb]);
         }
         if (++rb == 2) { rb = 0; rph ^= 1; }
-        for (int kc = 0; kc < p.kcs; ++kc) {
-          ptx::mbar_wait(&a_empty[s], ph ^ 1);
-          ptx::mbar_arrive_expect_tx(&a_full[s], PJ_A_BYTES);
-          ptx::tma_load_3d(sA + s * PJ_A_BYTES, &tm_a, &a_full[s], p0, kc * 64, n);
-          ptx::tma_load_3d(sA + s * PJ_A_BYTES + 8192, &tm_a, &a_full[s], p0 + 64, kc * 64, n);
-          if (++s == PJ_A_STAGES) { s = 0; ph ^= 1; }
-        }
       }
     }
   } else if (warp == 1) {

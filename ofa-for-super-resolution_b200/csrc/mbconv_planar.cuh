@@ -48,7 +48,7 @@ __device__ __forceinline__ int dw_b_off(int n, int k) { return (n >> 3) * 256 + 
 
 // ---- project ----
 constexpr int PJ_MPIX = 128;                  // pixels per tile = UMMA M
-constexpr int PJ_A_STAGES = 8;
+constexpr int PJ_A_STAGES = 9;
 constexpr int PJ_A_BYTES = 16384;             // 2 boxes of 64 pixels x 64 channels
 constexpr int PJ_MAX_KC = 6;
 constexpr int PJ_ACC_STAGES = 4;

@@ -101,6 +101,17 @@ __device__ __forceinline__ uint32_t pack16(float a, float b, int f16) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+// pack16(relu6(a), relu6(b)) in two instructions: the conversion clamps at zero (cvt.rn.relu), a packed min clamps at 6.
+// Bit-identical to clamping in fp32 first: rounding is monotonic and 0 and 6 are exact in both 16-bit formats.
+__device__ __forceinline__ uint32_t pack16_relu6(float a, float b, int f16) {
+  uint32_t r;
+  if (f16) {
+    asm("{\n\t.reg .b32 t;\n\tcvt.rn.relu.f16x2.f32 t, %2, %1;\n\tmin.f16x2 %0, t, %3;\n\t}" : "=r"(r) : "f"(a), "f"(b), "r"(0x46004600u));
+  } else {
+    asm("{\n\t.reg .b32 t;\n\tcvt.rn.relu.bf16x2.f32 t, %2, %1;\n\tmin.bf16x2 %0, t, %3;\n\t}" : "=r"(r) : "f"(a), "f"(b), "r"(0x40C040C0u));
+  }
+  return r;
+}
 __device__ __forceinline__ float2 unpack16(uint32_t u, int f16) {
   if (f16) return __half22float2(*reinterpret_cast<const __half2*>(&u));
   return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
