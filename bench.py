@@ -48,6 +48,7 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-train', action='store_true', help='skip the training-step measurements (the `train` object)')
     ap.add_argument('--no-extras', action='store_true', help='skip the secondary configurations (the `extra` object)')
+    ap.add_argument('--eager', action='store_true', help='launch the forward eagerly instead of replaying its CUDA graph')
     ap.add_argument('--train-steps', type=int, default=20)
     ap.add_argument('--dtype', default='f16', choices=['f16', 'bf16', 'fp32'],
                     help='activation storage of our arm: f16 (default; meets the 0.01 dB PSNR criterion), bf16 (same speed) or fp32 (exact CUDA-core path)')
@@ -226,13 +227,35 @@ def build_net(dev):
 
 def pin_rank_to_cores(local_rank, local_world):
     """Several ranks share the box's host cores: give each rank its own slice so that eight Python launch loops (and the
-    NCCL proxy threads they spawn) do not migrate over each other.  No-op when it cannot be done."""
+    NCCL proxy threads they spawn) do not migrate over each other.  The slice is taken from the cores NVML reports as
+    local to the rank's GPU (same NUMA node: the pinned frame buffers are first-touched there, and the device -> host
+    copies do not cross the socket link), shared evenly by the ranks whose GPUs report the same set.  No-op when it
+    cannot be done."""
     try:
-        cores = sorted(os.sched_getaffinity(0))
-        per = max(1, len(cores) // max(1, local_world))
-        mine = cores[local_rank * per:(local_rank + 1) * per]
-        if mine:
-            os.sched_setaffinity(0, mine)
+        allowed = sorted(os.sched_getaffinity(0))
+        groups = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            words = (max(allowed) // 64) + 1
+            masks = []
+            for r in range(local_world):
+                h = pynvml.nvmlDeviceGetHandleByIndex(r)
+                m = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+                cores = [64 * w + b for w in range(words) for b in range(64) if (int(m[w]) >> b) & 1]
+                masks.append(tuple(c for c in cores if c in allowed))
+            if all(masks):
+                groups = masks
+        except Exception:
+            groups = None
+        if groups is None:
+            groups = [tuple(allowed)] * local_world
+        mine = groups[local_rank]
+        peers = [r for r in range(local_world) if groups[r] == mine]
+        per = max(1, len(mine) // len(peers))
+        k = peers.index(local_rank)
+        sl = list(mine[k * per:(k + 1) * per]) or list(mine)
+        os.sched_setaffinity(0, sl)
     except Exception:
         pass
 
@@ -551,7 +574,16 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    # The forward is launched as a CUDA-graph replay (ofa_b200.GraphedModule: same kernels, captured once; the
+    # multi-job weight pack is part of the graph); the eager launch path is reported in `extra.eager`.
+    fast = ofa_b200.GraphedModule(net) if not args.eager else net
+    # e2e: two captures with their own output buffers -- frame k's device -> host copy reads one while frame k+1 fills the other
+    fast2 = ofa_b200.GraphedModule(net, copies=2) if not args.eager else net
+
     def step_resident():
+        return fast(x_dev)
+
+    def step_eager():
         return net(x_dev)
 
     # e2e: the call a user makes (net(x)) with the frame coming from pinned host memory and the fp32 SR image
@@ -584,13 +616,16 @@ def run_ours(args):
         h2d_stream.wait_stream(torch.cuda.current_stream())   # the other buffer's last reader has been queued
         upload(i ^ 1)                                   # next frame's copy overlaps this frame's compute
         xd = x_devs[i]
-        y = net(xd)
+        if e2e_state['done'][i] is not None:            # this graph copy's output buffer: frame k-2's copy-out has read it
+            torch.cuda.current_stream().wait_event(e2e_state['done'][i])
+        y = fast2(xd)
         ready = torch.cuda.Event()
         ready.record()
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(ready)
             y_hosts[i].copy_(y, non_blocking=True)
-            y.record_stream(copy_stream)
+            if args.eager:
+                y.record_stream(copy_stream)
             done = torch.cuda.Event()
             done.record()
         e2e_state['done'][i] = done
@@ -602,11 +637,18 @@ def run_ours(args):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    B.launch_count_reset()
+    # kernels of ours inside the timed region: the launches of one forward (counted by the library on an eager pass; a
+    # graph replay executes the same kernel nodes) x the timed steps
+    with torch.no_grad():
+        net(x_dev)
+        B.launch_count_reset()
+        net(x_dev)
+    torch.cuda.synchronize()
+    launches = B.launch_count() * args.steps
     total_ms = timed(step_resident, args.steps, args.warmup)
-    launches = B.launch_count() * args.steps // (args.steps + args.warmup)
     clocks = sampler.finish() if sampler else None
     e2e_ms = timed(step_e2e, args.steps, args.warmup, drain=e2e_drain)
+    eager_ms = timed(step_eager, args.steps, args.warmup) if not args.eager else total_ms
 
     ms_per_step = total_ms / args.steps
     value = world * out_pix / 1e6 / (ms_per_step / 1e3)
@@ -654,6 +696,9 @@ def run_ours(args):
 
     # ---- secondary configurations: reported, not the headline ---------------------------------------
     extra = run_extras(args, dev, dist, rank, world, net, x_host, flush) if not args.no_extras else None
+    if extra is not None:
+        extra['eager'] = {'ms_per_step': eager_ms / args.steps, 'value': world * out_pix / 1e6 / (eager_ms / args.steps / 1e3),
+                          'unit': UNIT, 'what': 'the same forward launched eagerly (net(x)) instead of as a CUDA-graph replay'}
 
     # ---- the workload WITH a collective: progressive-shrinking training steps (C3 on S4, C4 on X4) -------------
     train = None
@@ -678,7 +723,9 @@ def run_ours(args):
             'dtype': args.dtype, 'data': 'synthetic',
             'config': {'workload': workload_text(W, H),
                        'l2': 'flushed between timed iterations (256 MiB write); per-step activations are also >> L2',
-                       'timing': 'CUDA events per step on the launch stream, summed, max over ranks'},
+                       'timing': 'CUDA events per step on the launch stream, summed, max over ranks',
+                       'launch': ('eager net(x)' if args.eager else
+                                  'CUDA-graph replay of net.forward (ofa_b200.GraphedModule), one graph launch per frame')},
             'e2e': {'value': e2e_val, 'unit': UNIT, 'h2d_bytes_per_step': x_host.numel() * 4,
                     'd2h_bytes_per_step': y_host.numel() * 4},
             'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu,

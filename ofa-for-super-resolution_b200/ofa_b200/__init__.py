@@ -10,4 +10,6 @@ from . import backend, functional  # noqa: F401
 from .functional import (set_compute_dtype, get_compute_dtype, set_impl, set_train_dtype, get_train_dtype,  # noqa: F401
                          set_mid_dtype, check_finite, set_overflow_policy, invalidate_packed_weights)
 
-__version__ = '0.1.0'
+from .graphs import GraphedModule  # noqa: F401,E402
+
+__version__ = '0.2.0'

@@ -502,3 +502,25 @@ def test_uint8_and_fp16_image_outputs(dev, kind, shape):
     t = torch.rand_like(y32)
     from ofa_b200 import metrics
     assert metrics.psnr_y(y32, t) == pytest.approx(metrics.psnr_y(y8.float() / 255.0, t), abs=1e-9)
+
+
+def test_graphed_module_matches_eager_and_follows_subnet_and_weights(dev):
+    """ofa_b200.GraphedModule: bit-identical to the eager forward, one graph per (shape, sub-network), replays see
+    weight updates, `copies=2` alternates output buffers."""
+    import ofa_b200
+    net, spec, _ = build('s4', [1, 2], 48, dev)
+    fast = ofa_b200.GraphedModule(net, copies=2)
+    x = torch.from_numpy(np.random.RandomState(4).rand(1, 3, 40, 48).astype(np.float32)).to(dev)
+    with torch.no_grad():
+        for sub in (dict(ks=7, e=6, d=4, pixel_d=2), dict(ks=3, e=3, d=2, pixel_d=1)):
+            net.set_active_subnet(**sub)
+            y_eager = net(x)
+            y1 = fast(x).clone()
+            y2 = fast(x)                       # second copy
+            assert torch.equal(y1, y_eager) and torch.equal(y2, y_eager)
+        for p in net.parameters():
+            if p.dim() == 4:
+                p.data.mul_(0.9)
+        y_eager = net(x)
+        assert torch.equal(fast(x), y_eager) and torch.equal(fast(x), y_eager)
+    assert len(fast._graphs) == 4
