@@ -152,7 +152,8 @@ class DynamicMBConvLayer(MyModule):
 
     @property
     def module_str(self):
-        return '(O%d, E%.1f, K%d)' % (self.active_out_channel, self.active_expand_ratio, self.active_kernel_size)
+        core = '(O%d, E%.1f, K%d)' % (self.active_out_channel, self.active_expand_ratio, self.active_kernel_size)
+        return 'SE' + core if self.use_se else core
 
     @property
     def config(self):
