@@ -159,6 +159,10 @@ expand_planar_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
             ptx::tmem_ld16(t_addr + (uint32_t)(bx * 64 + 32), v + 32);
             ptx::tmem_ld16(t_addr + (uint32_t)(bx * 64 + 48), v + 48);
             ptx::tmem_ld_wait();
+            // (The TMA engine takes one 128-byte row request every ~8.6 clocks -- 15 B/clk per SM; UTMACMDFLUSH holds 26 %
+            // of the stall samples, profiles/r2_ncu_expand_planar.csv -- and that, not HBM, bounds this kernel.  Tried:
+            // storing every other sub-block straight from registers, a lane's 128 contiguous bytes as eight 16-byte
+            // st.global: 0.096 -> 0.150 ms, the scattered half-sector writes are far worse.)
             if (lane == 0) ptx::tma_store_wait_read<EX_SBUFS - 1>();   // staging buffer `sb` is free again
             __syncwarp();
             uint8_t* dst = sbuf + sb * EX_SBUF_BYTES + lane * 128;
