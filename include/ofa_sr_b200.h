@@ -184,6 +184,13 @@ int ofa_pack_weights_multi(const OfaPackJob* jobs_device, int32_t njobs, void* s
  *   apply : y = act(gamma*(x-mean)*rsqrt(var+eps)+beta) is ofa_affine_act with mean/var = batch stats
  * ------------------------------------------------------------------------------------------- */
 int ofa_bn_stats(const OfaTensor4* x, float* mean, float* var_biased, void* stream);
+/* The whole training-mode DynamicBatchNorm2d.bn_forward (+ the activation / residual that follows it) in ONE call and three
+ * launches: batch statistics (split reduction), finalize -- which also updates the running-statistics slice and bumps
+ * num_batches_tracked when running_mean is given and momentum != 0 --, then y = act(BN(x)) [+ residual].
+ * batch_mean / batch_var [C] receive the statistics used (the backward needs them). */
+int ofa_bn_train_fwd(const OfaTensor4* x, const OfaTensor4* y, const float* gamma, const float* beta, float* running_mean,
+                     float* running_var, float momentum, float eps, int32_t act, const OfaTensor4* residual,
+                     float* batch_mean, float* batch_var, int64_t* num_batches_tracked, void* stream);
 int ofa_bn_update_running(const float* mean, const float* var_biased, int64_t count,
                           float* running_mean, float* running_var, float momentum, int32_t C,
                           int64_t* num_batches_tracked, void* stream);
@@ -302,6 +309,10 @@ int ofa_bn_bwd_apply(const OfaTensor4* x, const OfaTensor4* dy, const OfaTensor4
                      const float* gamma, const float* beta, const float* mean, const float* var,
                      float eps, int32_t act, int32_t training, const float* sum_dz,
                      const float* sum_dz_xhat, void* stream);
+/* ofa_bn_bwd_reduce followed (dx != NULL) by ofa_bn_bwd_apply in one call */
+int ofa_bn_train_bwd(const OfaTensor4* x, const OfaTensor4* dy, const OfaTensor4* dx, const float* gamma,
+                     const float* beta, const float* mean, const float* var, float eps, int32_t act, int32_t training,
+                     float* sum_dz, float* sum_dz_xhat, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (evaluation side) the validate metric on the device —

@@ -668,6 +668,37 @@ int ofa_conv_bwd_weight(const OfaTensor4* x, const OfaTensor4* dy, float* dw, in
                                 (cudaStream_t)stream);
 }
 
+int ofa_bn_train_fwd(const OfaTensor4* x, const OfaTensor4* y, const float* gamma, const float* beta, float* running_mean,
+                     float* running_var, float momentum, float eps, int32_t act, const OfaTensor4* residual,
+                     float* batch_mean, float* batch_var, int64_t* num_batches_tracked, void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  if ((rc = check_tensor(x, "x"))) return rc;
+  if ((rc = check_tensor(y, "y"))) return rc;
+  if ((rc = same_shape(x, y, "bn_train_fwd x vs y"))) return rc;
+  OFA_REQUIRE(batch_mean && batch_var, "ofa_bn_train_fwd: null statistics output");
+  OFA_REQUIRE((long long)x->n * x->h * x->w > 0, "ofa_bn_train_fwd: empty batch");
+  OFA_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "ofa_bn_train_fwd: running_mean / running_var");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool upd = running_mean != nullptr && momentum != 0.f;
+  if ((rc = launch_bn_stats_update(make_tv(x), batch_mean, batch_var, upd ? running_mean : nullptr,
+                                   upd ? running_var : nullptr, momentum,
+                                   upd ? reinterpret_cast<long long*>(num_batches_tracked) : nullptr, st))) return rc;
+  OfaEpilogue e;
+  memset(&e, 0, sizeof(e));
+  e.gamma = gamma; e.beta = beta; e.mean = batch_mean; e.var = batch_var; e.eps = eps; e.act = act; e.residual = residual;
+  if ((rc = check_epi(&e, y))) return rc;
+  return launch_affine_act(make_tv(x), make_tv(y), make_epi(&e), OFA_STORE_PLAIN, st);
+}
+
+int ofa_bn_train_bwd(const OfaTensor4* x, const OfaTensor4* dy, const OfaTensor4* dx, const float* gamma,
+                     const float* beta, const float* mean, const float* var, float eps, int32_t act, int32_t training,
+                     float* sum_dz, float* sum_dz_xhat, void* stream) {
+  int rc = ofa_bn_bwd_reduce(x, dy, gamma, beta, mean, var, eps, act, sum_dz, sum_dz_xhat, stream);
+  if (rc || dx == nullptr) return rc;
+  return ofa_bn_bwd_apply(x, dy, dx, gamma, beta, mean, var, eps, act, training, sum_dz, sum_dz_xhat, stream);
+}
+
 int ofa_bn_bwd_reduce(const OfaTensor4* x, const OfaTensor4* dy, const float* gamma, const float* beta,
                       const float* mean, const float* var, float eps, int32_t act, float* sum_dz,
                       float* sum_dz_xhat, void* stream) {

@@ -19,6 +19,8 @@ void keep_async_pool_resident();   // raise the default mempool's release thresh
 int launch_pack_weights_multi(const OfaPackJob* jobs_device, int njobs, cudaStream_t st);
 int launch_affine_act(const TV& x, const TV& y, const Epi& epi, int store, cudaStream_t st);
 int launch_bn_stats(const TV& x, float* mean, float* var, cudaStream_t st);
+int launch_bn_stats_update(const TV& x, float* mean, float* var, float* rm, float* rv, float momentum,
+                           long long* num_batches_tracked, cudaStream_t st);
 int launch_bn_update_running(const float* mean, const float* var, long long count, float* rm, float* rv,
                              float momentum, int C, long long* num_batches_tracked, cudaStream_t st);
 int launch_bn_bwd_reduce(const TV& x, const TV& dy, const float* gamma, const float* beta,

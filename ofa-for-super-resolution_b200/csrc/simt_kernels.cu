@@ -718,8 +718,11 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 
 __global__ void __launch_bounds__(BN_FIN_THREADS)
 bn_stats_final_kernel(const float* __restrict__ part, int splits, int C, float* __restrict__ mean,
-                      float* __restrict__ var) {
+                      float* __restrict__ var, float* __restrict__ rm, float* __restrict__ rv, float momentum, float unbias,
+                      long long* __restrict__ num_batches_tracked) {
   const int c = blockIdx.x * (BN_FIN_THREADS / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  // nn.BatchNorm2d's counter, bumped in the same launch (`bn.num_batches_tracked += 1`, dynamic_op.py:156)
+  if (num_batches_tracked && blockIdx.x == 0 && threadIdx.x == 0) *num_batches_tracked += 1;
   if (c >= C) return;
   double n = 0.0, sm = 0.0;
   for (int s = lane; s < splits; s += 32) {
@@ -738,8 +741,13 @@ bn_stats_final_kernel(const float* __restrict__ part, int splits, int C, float* 
   }
   m2 = warp_sum_d(m2);
   if (lane == 0) {
-    mean[c] = (float)m;
-    var[c] = (float)(n > 0.0 ? m2 / n : 0.0);
+    const float mf = (float)m, vf = (float)(n > 0.0 ? m2 / n : 0.0);
+    mean[c] = mf;
+    var[c] = vf;
+    if (rm) {   // running = (1 - momentum) * running + momentum * {mean, unbiased var} on the active slice, same launch
+      rm[c] = (1.f - momentum) * rm[c] + momentum * mf;
+      rv[c] = (1.f - momentum) * rv[c] + momentum * (vf * unbias);
+    }
   }
 }
 
@@ -781,7 +789,15 @@ static int bn_splits(const TV& x, long long* per_split, int vec8_blocks_per_sm) 
 }
 
 int launch_bn_stats(const TV& x, float* mean, float* var, cudaStream_t st) {
+  return launch_bn_stats_update(x, mean, var, nullptr, nullptr, 0.f, nullptr, st);
+}
+
+// batch statistics + (rm != nullptr) the running-statistics update and the num_batches_tracked bump in the finalize launch
+int launch_bn_stats_update(const TV& x, float* mean, float* var, float* rm, float* rv, float momentum,
+                           long long* num_batches_tracked, cudaStream_t st) {
   if (x.c == 0) return OFA_OK;
+  const long long count = (long long)x.n * x.h * x.w;
+  const float unbias = count > 1 ? (float)((double)count / (double)(count - 1)) : 1.f;
   long long per_split = 0;
   const int splits = bn_splits(x, &per_split, 4);
   float* part = nullptr;
@@ -809,7 +825,8 @@ int launch_bn_stats(const TV& x, float* mean, float* var, cudaStream_t st) {
     rc = check_launch("bn_stats_partial_kernel");
   }
   if (!rc) {
-    bn_stats_final_kernel<<<(x.c + BN_FIN_THREADS / 32 - 1) / (BN_FIN_THREADS / 32), BN_FIN_THREADS, 0, st>>>(part, splits, x.c, mean, var);
+    bn_stats_final_kernel<<<(x.c + BN_FIN_THREADS / 32 - 1) / (BN_FIN_THREADS / 32), BN_FIN_THREADS, 0, st>>>(
+        part, splits, x.c, mean, var, rm, rv, momentum, unbias, num_batches_tracked);
     rc = check_launch("bn_stats_final_kernel");
   }
   cudaFreeAsync(part, st);

@@ -85,6 +85,10 @@ SYMBOLS = {
                                      c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     'ofa_pack_weights_multi': (c_int32, [c_void_p, c_int32, c_void_p]),
     'ofa_bn_stats': (c_int32, [_T4, c_void_p, c_void_p, c_void_p]),
+    'ofa_bn_train_fwd': (c_int32, [_T4, _T4, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_int32, _T4,
+                                   c_void_p, c_void_p, c_void_p, c_void_p]),
+    'ofa_bn_train_bwd': (c_int32, [_T4, _T4, _T4, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int32, c_int32,
+                                   c_void_p, c_void_p, c_void_p]),
     'ofa_bn_update_running': (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_float, c_int32,
                                         c_void_p, c_void_p]),
     'ofa_affine_act': (c_int32, [_T4, _T4, _EP, c_int32, c_void_p]),

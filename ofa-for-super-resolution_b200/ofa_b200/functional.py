@@ -503,19 +503,24 @@ def _bn_fwd_impl(x, gamma, beta, running_mean, running_var, residual, training, 
     L = B.lib()
     st = _stream(x)
     tx = B.t4(x)
-    if training:
+    if training and x.numel() > 0:
+        # ONE library call: statistics, finalize (+ running-statistics slice update + num_batches_tracked bump in the same
+        # launch), normalise + activation [+ residual]
         stats = torch.empty((2, c), dtype=torch.float32, device=x.device)
         mean, var = stats[0], stats[1]
-        B.check(L.ofa_bn_stats(byref(tx), mean.data_ptr(), var.data_ptr(), st))
-        if running_mean is not None and momentum is not None and momentum != 0.0:
-            B.check(L.ofa_bn_update_running(mean.data_ptr(), var.data_ptr(), n * h * w,
-                                            B.fptr(running_mean), B.fptr(running_var), float(momentum), c,
-                                            bump.data_ptr() if bump is not None else None, st))
-            bump = None
-        if bump is not None:
+        y = B.new_nhwc(n, c, h, w, x.dtype, x.device)
+        ty = B.t4(y)
+        update = running_mean is not None and momentum is not None and momentum != 0.0
+        res_t4 = B.t4(residual) if residual is not None else None
+        B.check(L.ofa_bn_train_fwd(byref(tx), byref(ty), _null_or(gamma), _null_or(beta),
+                                   B.fptr(running_mean) if update else None, B.fptr(running_var) if update else None,
+                                   float(momentum) if update else 0.0, float(eps), int(act),
+                                   byref(res_t4) if res_t4 is not None else None, mean.data_ptr(), var.data_ptr(),
+                                   bump.data_ptr() if (bump is not None and update) else None, st))
+        if bump is not None and not update:
             bump += 1
-    else:
-        mean, var = running_mean, running_var
+        return y, mean, var
+    mean, var = running_mean, running_var
     y = B.new_nhwc(n, c, h, w, x.dtype, x.device)
     ty = B.t4(y)
     e, keep = B.epilogue(gamma, beta, mean, var, eps, act, residual)
@@ -535,15 +540,15 @@ def _bn_bwd_impl(x, gamma, beta, mean, var, training, eps, act, dy, need_dx, nee
     c_full = max(c, gamma.shape[0] if gamma is not None else c, beta.shape[0] if beta is not None else c)
     sums = torch.zeros((2, c_full), dtype=torch.float32, device=x.device)
     s0, s1 = sums[0], sums[1]
-    B.check(L.ofa_bn_bwd_reduce(byref(tx), byref(tdy), _null_or(gamma), _null_or(beta), B.fptr(mean),
-                                B.fptr(var), eps, act, s0.data_ptr(), s1.data_ptr(), st))
     dx = dgamma = dbeta = None
+    tdx = None
     if need_dx:
         dx = B.new_nhwc(n, c, h, w, x.dtype, dy.device)
         tdx = B.t4(dx)
-        B.check(L.ofa_bn_bwd_apply(byref(tx), byref(tdy), byref(tdx), _null_or(gamma), _null_or(beta),
-                                   B.fptr(mean), B.fptr(var), eps, act, int(training), s0.data_ptr(),
-                                   s1.data_ptr(), st))
+    # reduce (+ apply) in one library call
+    B.check(L.ofa_bn_train_bwd(byref(tx), byref(tdy), byref(tdx) if tdx is not None else None, _null_or(gamma),
+                               _null_or(beta), B.fptr(mean), B.fptr(var), eps, act, int(training), s0.data_ptr(),
+                               s1.data_ptr(), st))
     if gamma is not None and need_dgamma:
         dgamma = s1[:gamma.shape[0]]
     if beta is not None and need_dbeta:
