@@ -315,6 +315,68 @@ int ofa_bn_train_bwd(const OfaTensor4* x, const OfaTensor4* dy, const OfaTensor4
                      float* sum_dz, float* sum_dz_xhat, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * (a7 + a8 + a14) ONE MBConv block of the training step as one call each way — DynamicMBConvLayer.forward in train
+ * mode (dynamic_layers.py:70-84: expand 1x1 -> DynamicBatchNorm2d (batch statistics, running-slice update,
+ * num_batches_tracked, dynamic_op.py:148-167) -> act -> elastic depthwise -> BN -> act -> project 1x1 -> BN) inside
+ * MobileInvertedResidualBlock (proxyless_nets.py:44-51: + x), and its autograd.  Same kernels, order and results as the
+ * layer-by-layer entry points above (ofa_conv_fwd / ofa_bn_train_fwd / ofa_dw_fwd ... ofa_conv_bwd_weight); what it
+ * removes is host time: the eager progressive-shrinking step (progressive_shrinking.py:158-203) was bounded by the
+ * caller's launch loop.  16-bit dense NHWC activations, 64-channel trunk (cin = cout = 64), mid % 64 == 0, mid <= 384.
+ *   ws       caller-owned, 256-byte aligned, ofa_mbconv_train_workspace_bytes(...) bytes; the forward leaves the five
+ *            intermediates and the batch statistics the backward needs in it (keep it alive and unchanged until then)
+ *   BN       gamma / beta / running_* are the FULL-width arrays (prefix [:C] used); running_mean == NULL or
+ *            momentum == 0 skips the running update and the counter bump
+ *   backward dy, dx: [N, H, W, 64] like x.  Gradient arrays are full parameter size and ZERO-FILLED by the caller:
+ *            dw_exp / dw_proj take the parameter's strides, dgamma / dbeta prefixes are overwritten, dw_dw / dm75 / dm53
+ *            are accumulated into (dm75 / dm53 may be NULL when the active kernel size does not use the matrix).
+ *            With add_residual the identity branch's gradient is included in dx.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct OfaBnTrain {
+  const float* gamma;
+  const float* beta;
+  float* running_mean;
+  float* running_var;
+  int64_t* num_batches_tracked;
+  float momentum;
+  float eps;
+} OfaBnTrain;
+
+typedef struct OfaMBConvTrainArgs {
+  const void* x; /* [N, H, W, cin]  */
+  void* y;       /* [N, H, W, cout] (forward output; unused by the backward) */
+  int32_t dtype; /* OFA_BF16 | OFA_F16 */
+  int32_t n, h, w;
+  int32_t cin, mid, cout, ks, kmax, transform_on;
+  int32_t act;          /* activation after BN1 and BN2 (OFA_ACT_*) */
+  int32_t add_residual; /* 1: y = block(x) + x */
+  const float* w_exp;   /* [Mmax, cin_max, 1, 1] fp32 master, slice [:mid, :cin] read in place */
+  int64_t w_exp_so, w_exp_si;
+  const float* w_dw; /* [Mmax, kmax * kmax] */
+  const float* m75;
+  const float* m53;
+  const float* w_proj; /* [cout_max, Mmax, 1, 1] */
+  int64_t w_proj_so, w_proj_si;
+  OfaBnTrain bn_exp, bn_dw, bn_proj;
+  void* ws;
+  int64_t ws_bytes;
+} OfaMBConvTrainArgs;
+
+typedef struct OfaMBConvTrainGrads {
+  float* dw_exp;
+  float* dw_dw;
+  float* dm75;
+  float* dm53;
+  float* dw_proj;
+  float* dgamma[3]; /* expand, depthwise, project BatchNorm */
+  float* dbeta[3];
+} OfaMBConvTrainGrads;
+
+int64_t ofa_mbconv_train_workspace_bytes(int32_t n, int32_t h, int32_t w, int32_t cin, int32_t mid, int32_t cout);
+int ofa_mbconv_train_fwd(const OfaMBConvTrainArgs* a, void* stream);
+int ofa_mbconv_train_bwd(const OfaMBConvTrainArgs* a, const void* dy, void* dx, const OfaMBConvTrainGrads* g,
+                         void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * (evaluation side) the validate metric on the device —
  * psnr(rgb2y(tensor2img_np(a)), rgb2y(tensor2img_np(b))): sr_run_manager.py:364,496,567-597, ofa/utils.py:27-34.
  *   a, b           [N,3,H,W] images (any strides, fp32 or 16-bit), values clamped to [0,1] as the reference does

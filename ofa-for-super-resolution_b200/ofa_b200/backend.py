@@ -57,6 +57,27 @@ class OfaMBConvArgs(Structure):
                 ('w_exp_packed', c_void_p), ('w_proj_packed', c_void_p)]
 
 
+class OfaBnTrain(Structure):
+    _fields_ = [('gamma', c_void_p), ('beta', c_void_p), ('running_mean', c_void_p), ('running_var', c_void_p),
+                ('num_batches_tracked', c_void_p), ('momentum', c_float), ('eps', c_float)]
+
+
+class OfaMBConvTrainArgs(Structure):
+    _fields_ = [('x', c_void_p), ('y', c_void_p), ('dtype', c_int32), ('n', c_int32), ('h', c_int32), ('w', c_int32),
+                ('cin', c_int32), ('mid', c_int32), ('cout', c_int32), ('ks', c_int32), ('kmax', c_int32),
+                ('transform_on', c_int32), ('act', c_int32), ('add_residual', c_int32),
+                ('w_exp', c_void_p), ('w_exp_so', c_int64), ('w_exp_si', c_int64),
+                ('w_dw', c_void_p), ('m75', c_void_p), ('m53', c_void_p),
+                ('w_proj', c_void_p), ('w_proj_so', c_int64), ('w_proj_si', c_int64),
+                ('bn_exp', OfaBnTrain), ('bn_dw', OfaBnTrain), ('bn_proj', OfaBnTrain),
+                ('ws', c_void_p), ('ws_bytes', c_int64)]
+
+
+class OfaMBConvTrainGrads(Structure):
+    _fields_ = [('dw_exp', c_void_p), ('dw_dw', c_void_p), ('dm75', c_void_p), ('dm53', c_void_p), ('dw_proj', c_void_p),
+                ('dgamma', c_void_p * 3), ('dbeta', c_void_p * 3)]
+
+
 class OfaPackJob(Structure):
     _fields_ = [('w', c_void_p), ('w_so', c_int64), ('w_si', c_int64), ('w_sh', c_int64), ('w_sw', c_int64),
                 ('cin', c_int32), ('cout', c_int32), ('ks', c_int32), ('cin_pad', c_int32), ('cout_pad', c_int32),
@@ -102,6 +123,10 @@ SYMBOLS = {
                                     c_void_p, c_void_p, c_int32, c_int32, c_int32, POINTER(OfaBn), c_int32, c_void_p]),
     'ofa_project_planar_fwd': (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                          c_int32, POINTER(OfaBn), c_void_p]),
+    'ofa_mbconv_train_workspace_bytes': (c_int64, [c_int32] * 6),
+    'ofa_mbconv_train_fwd': (c_int32, [POINTER(OfaMBConvTrainArgs), c_void_p]),
+    'ofa_mbconv_train_bwd': (c_int32, [POINTER(OfaMBConvTrainArgs), c_void_p, c_void_p, POINTER(OfaMBConvTrainGrads),
+                                       c_void_p]),
     'ofa_adam_step': (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_float, c_float, c_float,
                                 c_float, c_void_p]),
     'ofa_psnr_y_sse': (c_int32, [_T4, _T4, c_void_p, c_void_p]),

@@ -133,6 +133,11 @@ class DynamicMBConvLayer(MyModule):
             mid = self.inverted_bottleneck.conv.active_out_channel
         if self.stride == 1 and not _has_hooks(self.inverted_bottleneck.conv if self.inverted_bottleneck is not None
                                                else None, dwm, self.point_linear.conv):
+            if (self.inverted_bottleneck is not None and not self.use_se and OF._state['block_train']
+                    and OF.mbconv_train_supported(x, in_channel, mid, cout, residual, (bn_ex, bn_dw, bn_pl))):
+                # the whole block as one autograd node / one library call each way (the eager step is host-bound)
+                return OF.mbconv_train(x, self.inverted_bottleneck.conv.conv.weight, dwm.conv.weight, m75, m53, w_pl, mid,
+                                       cout, ks, transform_on, act, bn_ex, bn_dw, bn_pl, residual is not None)
             # one autograd node per conv + BN + act layer (same library calls; the eager step is launch-rate-bound)
             if self.inverted_bottleneck is not None:
                 h = OF.conv_bn_act(h, self.inverted_bottleneck.conv.conv.weight, in_channel, mid, 1, bn_ex, act)

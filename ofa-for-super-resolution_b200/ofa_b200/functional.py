@@ -10,6 +10,7 @@ Tensors produced here are logical NCHW stored channels-last (NHWC memory); input
 strides (the user's NCHW fp32 image is read in place).
 """
 import ctypes
+import os
 from ctypes import byref
 
 import torch
@@ -17,7 +18,7 @@ import torch
 from . import backend as B
 
 _state = {'compute_dtype': torch.float16, 'impl': B.IMPL_AUTO, 'mid_dtype': B.OFA_F16, 'train_dtype': torch.float32,
-          'overflow': 'none'}
+          'overflow': 'none', 'block_train': os.environ.get('OFA_BLOCK_TRAIN', '1') != '0'}
 
 
 def check_finite(t):
@@ -65,6 +66,12 @@ def get_train_dtype():
 
 def get_compute_dtype():
     return _state['compute_dtype']
+
+
+def set_block_train(on):
+    """Training MBConv blocks as one library call each way (MBConvTrainFn, default on; OFA_BLOCK_TRAIN=0 or False here
+    selects the layer-by-layer autograd nodes -- same kernels, same results, more host time)."""
+    _state['block_train'] = bool(on)
 
 
 def set_impl(impl):
@@ -631,6 +638,119 @@ class DwBnActFn(torch.autograd.Function):
         if dz is not None:
             dx, dw7, dm75, dm53 = _dw_bwd_impl(x, w7, m75, m53, ks, transform_on, dz, ng[0], need_filter)
         return dx, dw7, dm75, dm53, None, None, dgamma, dbeta, None, None, None, None, None, None, None
+
+
+class MBConvTrainFn(torch.autograd.Function):
+    """One MBConv block of the training step -- expand 1x1 -> BN -> act -> elastic depthwise -> BN -> act -> project 1x1
+    -> BN [+ x] (dynamic_layers.py:70-84, proxyless_nets.py:44-51) -- as ONE autograd node and ONE library call each way
+    (ofa_mbconv_train_fwd / _bwd: the same kernels in the same order as ConvBnActFn -> DwBnActFn -> ConvBnActFn).  The
+    eager step was bounded by this interpreter loop, not by the GPU (tools/hosttime_train.py)."""
+
+    @staticmethod
+    def forward(ctx, x, w_exp, w7, m75, m53, w_proj, g1, b1, g2, b2, g3, b3, cfg):
+        mid, cout, ks, transform_on, act, add_residual, bns = cfg
+        n, cin, h, w = x.shape
+        L = B.lib()
+        nbytes = L.ofa_mbconv_train_workspace_bytes(n, h, w, cin, mid, cout)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        y = B.new_nhwc(n, cout, h, w, x.dtype, x.device)
+        a = B.OfaMBConvTrainArgs()
+        a.x, a.y, a.dtype = x.data_ptr(), y.data_ptr(), B.dtype_code(x.dtype)
+        a.n, a.h, a.w = n, h, w
+        a.cin, a.mid, a.cout, a.ks, a.kmax, a.transform_on = cin, mid, cout, ks, w7.shape[-1], int(bool(transform_on))
+        a.act, a.add_residual = int(act), int(bool(add_residual))
+        a.w_exp = B.fptr(w_exp)
+        a.w_exp_so, a.w_exp_si = w_exp.stride(0), w_exp.stride(1)
+        a.w_dw, a.m75, a.m53 = B.fptr(w7), _null_or(m75), _null_or(m53)
+        a.w_proj = B.fptr(w_proj)
+        a.w_proj_so, a.w_proj_si = w_proj.stride(0), w_proj.stride(1)
+        for slot, gamma, beta, (rm, rv, momentum, eps, bump) in ((a.bn_exp, g1, b1, bns[0]), (a.bn_dw, g2, b2, bns[1]),
+                                                                  (a.bn_proj, g3, b3, bns[2])):
+            update = rm is not None and momentum is not None and momentum != 0.0
+            slot.gamma, slot.beta = B.fptr(gamma), B.fptr(beta)
+            slot.running_mean = B.fptr(rm) if update else None
+            slot.running_var = B.fptr(rv) if update else None
+            slot.num_batches_tracked = bump.data_ptr() if (bump is not None and update) else None
+            slot.momentum = float(momentum) if update else 0.0
+            slot.eps = float(eps)
+            if bump is not None and not update:
+                bump += 1
+        a.ws, a.ws_bytes = ws.data_ptr(), nbytes
+        B.check(L.ofa_mbconv_train_fwd(byref(a), _stream(x)))
+        ctx.save_for_backward(x, w_exp, w7, m75, m53, w_proj, g1, b1, g2, b2, g3, b3, ws)
+        ctx.args = a
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w_exp, w7, m75, m53, w_proj, g1, b1, g2, b2, g3, b3, ws = ctx.saved_tensors
+        a = ctx.args
+        if not dy.is_contiguous(memory_format=torch.channels_last) or dy.dtype != x.dtype:
+            dy = dy.to(x.dtype).contiguous(memory_format=torch.channels_last)
+        n, cin, h, w = x.shape
+        dx = B.new_nhwc(n, cin, h, w, x.dtype, x.device)
+        kmax = w7.shape[-1]
+        use75 = bool(a.transform_on) and a.ks < kmax and m75 is not None
+        use53 = bool(a.transform_on) and a.ks < kmax and a.ks == 3 and m53 is not None
+        # every parameter gradient (full supernet size, zero outside the active slice) in ONE zero-filled buffer
+        params = [w_exp, w7, w_proj, g1, b1, g2, b2, g3, b3]
+        if m75 is not None:
+            params.append(m75)
+        if m53 is not None:
+            params.append(m53)
+        flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=x.device)
+        parts = flat.split([p.numel() for p in params])
+        base = flat.data_ptr()
+        g = B.OfaMBConvTrainGrads()
+        ptrs = []
+        off = 0
+        for p in params:
+            ptrs.append(base + 4 * off)
+            off += p.numel()
+        g.dw_exp, g.dw_dw, g.dw_proj = ptrs[0], ptrs[1], ptrs[2]
+        g.dgamma[0], g.dbeta[0], g.dgamma[1], g.dbeta[1], g.dgamma[2], g.dbeta[2] = ptrs[3:9]
+        k = 9
+        d75 = d53 = None
+        if m75 is not None:
+            g.dm75 = ptrs[k]
+            d75 = parts[k].view(m75.shape) if use75 else None
+            k += 1
+        if m53 is not None:
+            g.dm53 = ptrs[k]
+            d53 = parts[k].view(m53.shape) if use53 else None
+        B.check(B.lib().ofa_mbconv_train_bwd(byref(a), dy.data_ptr(), dx.data_ptr(), byref(g), _stream(x)))
+        return (dx, parts[0].view(w_exp.shape), parts[1].view(w7.shape), d75, d53, parts[2].view(w_proj.shape),
+                parts[3], parts[4], parts[5], parts[6], parts[7], parts[8], None)
+
+
+def mbconv_train_supported(x, cin, mid, cout, residual, bns):
+    """The block-level training call: 16-bit NHWC activations of the training dtype, 64-channel trunk, BatchNorms in
+    batch-statistics mode without a set_running_statistics override."""
+    tdt = _state['train_dtype']
+    if tdt == torch.float32 or x.dtype != tdt or not _is_half_nhwc(x):
+        return False
+    if cin != 64 or cout != 64 or mid % 64 != 0 or not 64 <= mid <= 384:
+        return False
+    if residual is not None and residual is not x:
+        return False
+    if _profiler is not None or x.numel() == 0 or (x.data_ptr() & 15):
+        return False
+    for bn in bns:
+        if bn is None or 'forward' in bn.__dict__ or bn.weight is None or bn.bias is None:
+            return False
+        if not (bn.training or not bn.track_running_stats):
+            return False
+    return True
+
+
+def mbconv_train(x, w_exp, w7, m75, m53, w_proj, mid, cout, ks, transform_on, act, bn_exp, bn_dw, bn_proj, add_residual):
+    modes = []
+    for bn in (bn_exp, bn_dw, bn_proj):
+        training, momentum, bump = _bn_mode(bn)
+        modes.append((bn.running_mean, bn.running_var, momentum, bn.eps, bump))
+    cfg = (mid, cout, ks, transform_on, act, add_residual, modes)
+    return MBConvTrainFn.apply(x, w_exp, w7, m75, m53, w_proj, bn_exp.weight, bn_exp.bias, bn_dw.weight, bn_dw.bias,
+                               bn_proj.weight, bn_proj.bias, cfg)
 
 
 def bn_hooked(*bns):

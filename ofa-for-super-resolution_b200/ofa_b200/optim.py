@@ -104,6 +104,8 @@ class FusedAdam:
             elif p.grad is not None:
                 p.grad.zero_()
 
+    _RING = 4
+
     def step(self):
         assert [p.data_ptr() for p in self.params] == self._ptrs, 'parameters were re-allocated: rebuild FusedAdam'
         ptrs, touched = [], []
@@ -121,8 +123,24 @@ class FusedAdam:
             self._grad_pinned = torch.tensor(ptrs, dtype=torch.int64).pin_memory()
             self._grad_dev.copy_(self._grad_pinned, non_blocking=True)
         else:
-            # pageable source: the copy is staged before copy_ returns, so the list can change next step
-            self._grad_dev.copy_(torch.tensor(ptrs, dtype=torch.int64))
+            # a blocking copy from pageable memory synchronises the stream: the host could never run ahead of the GPU
+            # into the next step.  Upload from a small ring of pinned buffers instead; a slot is reused only after the
+            # copy that last read it has completed (it is _RING steps old by then).
+            ring = self.__dict__.setdefault('_grad_ring', [])
+            if len(ring) < self._RING:
+                ring.append([torch.empty(len(ptrs), dtype=torch.int64).pin_memory(), None])
+                slot = ring[-1]
+                self._ring_pos = len(ring) % self._RING
+            else:
+                slot = ring[self._ring_pos]
+                self._ring_pos = (self._ring_pos + 1) % self._RING
+                if slot[1] is not None:
+                    slot[1].synchronize()
+            slot[0].copy_(torch.tensor(ptrs, dtype=torch.int64))
+            self._grad_dev.copy_(slot[0], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self._grad_dev.device))
+            slot[1] = ev
         dev = self.params[0].device
         B.check(B.lib().ofa_adam_step(self._table.data_ptr(), self._chunks.data_ptr(), len(self.params),
                                       self._chunks.shape[0], self._grad_dev.data_ptr(), self._steps.data_ptr(),
