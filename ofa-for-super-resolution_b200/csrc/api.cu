@@ -2,6 +2,7 @@
 #include "ofa_common.cuh"
 #include "kernels.h"
 
+#include <stdlib.h>
 #include <string.h>
 
 namespace ofa {
@@ -26,6 +27,11 @@ int check_launch(const char* what) {
   if (e != cudaSuccess) return fail(OFA_ERR_CUDA, "%s launch failed: %s", what, cudaGetErrorString(e));
   launch_counter()++;
   return OFA_OK;
+}
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("OFA_PDL"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on == 1;
 }
 int sm_count() {
   static int cache[64] = {0};

@@ -174,6 +174,7 @@ __device__ __forceinline__ void emit16(const ConvTcParams& p, const float* s_sca
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                const ConvTcParams p) {
+  pdl_wait();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
   const int taps = p.ks * p.ks;
@@ -576,7 +577,7 @@ int launch_conv_tc(const OfaConvArgs* a_in, cudaStream_t st) {
   const int num_work = p.N * p.tiles_h * p.tiles_w * (p.n_splits / p.inner_splits);
   int grid = sm_count();
   if (grid > num_work) grid = num_work;
-  conv_tc_kernel<<<grid, NUM_THREADS, smem, st>>>(tx, tw, p);
+  launch_pdl(conv_tc_kernel, dim3(grid), dim3(NUM_THREADS), smem, st, tx, tw, p);
   return check_launch("conv_tc_kernel");
 }
 

@@ -61,6 +61,7 @@ __device__ __forceinline__ float2 bf2_unpack(uint32_t u) {
 template <int KS, int TH, int TW>
 __global__ void __launch_bounds__(32 * TH, 2)
 dw_fast_kernel(const __grid_constant__ CUtensorMap tmap_x, const DwParams p) {
+  pdl_wait();
   using L = DwSmem<KS, TH, TW>;
   constexpr int THREADS = 32 * TH;
   extern __shared__ uint8_t smem_raw[];
@@ -189,7 +190,7 @@ int launch_tile(const OfaTensor4* x, DwParams& p, cudaStream_t st) {
   if (rc) return rc;
   OFA_CUDA(cudaFuncSetAttribute(dw_fast_kernel<KS, TH, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
   dim3 grid((unsigned)(p.N * p.tiles_w * p.tiles_h), p.C / CH);
-  dw_fast_kernel<KS, TH, TW><<<grid, 32 * TH, L::TOTAL, st>>>(tm, p);
+  launch_pdl(dw_fast_kernel<KS, TH, TW>, dim3(grid), dim3(32 * TH), L::TOTAL, st, tm, p);
   return check_launch("dw_fast_kernel");
 }
 

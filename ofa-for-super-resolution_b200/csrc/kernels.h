@@ -17,6 +17,7 @@ int launch_pack_weight(const float* w, long long w_so, long long w_si, long long
                        cudaStream_t st);
 void keep_async_pool_resident();   // raise the default mempool's release threshold once per device (cudaMallocAsync scratch)
 int launch_pack_weights_multi(const OfaPackJob* jobs_device, int njobs, cudaStream_t st);
+int launch_pack_weights4(const OfaPackJob* jobs_host, int njobs, cudaStream_t st);   // <= 4 jobs by value, one launch
 int launch_affine_act(const TV& x, const TV& y, const Epi& epi, int store, cudaStream_t st);
 int launch_bn_stats(const TV& x, float* mean, float* var, cudaStream_t st);
 int launch_bn_stats_update(const TV& x, float* mean, float* var, float* rm, float* rv, float momentum,

@@ -26,7 +26,8 @@ struct TrainLayout {
   int64_t P;
   int64_t z1, a1, z2, a2, z3;     // byte offsets of the saved activations
   int64_t stats;                  // 2 * (mid + mid + cout) floats: mean1 var1 mean2 var2 mean3 var3
-  int64_t wexp, wproj;            // forward-only packed 16-bit weights
+  int64_t wexp, wproj;            // packed 16-bit weights of the two forward convs
+  int64_t wexp_t, wproj_t;        // ... and of the two data-gradient convs (transposed slices), packed by the forward
   int64_t total;
 };
 
@@ -43,6 +44,8 @@ TrainLayout train_layout(int n, int h, int w, int mid, int cout) {
   L.stats = o; o += align256((int64_t)sizeof(float) * 2 * (2 * mid + cout));
   L.wexp = o; o += align256((int64_t)384 * 64 * 2);
   L.wproj = o; o += align256((int64_t)64 * 384 * 2);
+  L.wexp_t = o; o += align256((int64_t)64 * 384 * 2);
+  L.wproj_t = o; o += align256((int64_t)384 * 64 * 2);
   L.total = o;
   return L;
 }
@@ -155,11 +158,24 @@ int ofa_mbconv_train_fwd(const OfaMBConvTrainArgs* a, void* stream) {
   float* stats = reinterpret_cast<float*>(ws + L.stats);
   float *mean1 = stats, *var1 = stats + a->mid, *mean2 = stats + 2 * a->mid, *var2 = stats + 3 * a->mid,
         *mean3 = stats + 4 * a->mid, *var3 = stats + 4 * a->mid + a->cout;
-  // the active weight slices, read in place from the full parameters
-  if ((rc = launch_pack_weight(a->w_exp, a->w_exp_so, a->w_exp_si, 0, 0, a->cin, a->mid, 1, a->cin,
-                               (a->mid + 15) / 16 * 16, OFA_STORE_PLAIN, f16, ws + L.wexp, st))) return rc;
-  if ((rc = launch_pack_weight(a->w_proj, a->w_proj_so, a->w_proj_si, 0, 0, a->mid, a->cout, 1, a->mid,
-                               (a->cout + 15) / 16 * 16, OFA_STORE_PLAIN, f16, ws + L.wproj, st))) return rc;
+  // the active weight slices, read in place from the full parameters: the two forward copies and the two transposed
+  // copies the backward's data-gradient convs use (the weights cannot change in between: autograd's version check), one
+  // launch for all four
+  {
+    OfaPackJob jobs[4];
+    memset(jobs, 0, sizeof(jobs));
+    const int dt = a->dtype;
+    auto job = [&](int k, const float* w, int64_t so, int64_t si, int cin, int cout, void* out) {
+      jobs[k].w = w; jobs[k].w_so = so; jobs[k].w_si = si; jobs[k].w_sh = 0; jobs[k].w_sw = 0;
+      jobs[k].cin = cin; jobs[k].cout = cout; jobs[k].ks = 1; jobs[k].cin_pad = cin; jobs[k].cout_pad = (cout + 15) / 16 * 16;
+      jobs[k].store = OFA_STORE_PLAIN; jobs[k].dtype = dt; jobs[k].out = out;
+    };
+    job(0, a->w_exp, a->w_exp_so, a->w_exp_si, a->cin, a->mid, ws + L.wexp);
+    job(1, a->w_proj, a->w_proj_so, a->w_proj_si, a->mid, a->cout, ws + L.wproj);
+    job(2, a->w_exp, a->w_exp_si, a->w_exp_so, a->mid, a->cin, ws + L.wexp_t);     // dX = conv(dZ1, W_exp^T): mid -> cin
+    job(3, a->w_proj, a->w_proj_si, a->w_proj_so, a->cout, a->mid, ws + L.wproj_t); // dA2 = conv(dZ3, W_proj^T): cout -> mid
+    if ((rc = launch_pack_weights4(jobs, 4, st))) return rc;
+  }
   if ((rc = pointwise_tc(x, z1, ws + L.wexp, a->cin, a->mid, nullptr, st))) return rc;
   if ((rc = bn_fwd(z1, a1, a->bn_exp, mean1, var1, a->act, nullptr, st))) return rc;
   if (!dw_fast_supported(&a1, &z2, a->ks, nullptr))
@@ -204,26 +220,23 @@ int ofa_mbconv_train_bwd(const OfaMBConvTrainArgs* a, const void* dy_ptr, void* 
   const OfaTensor4 dx = nhwc16(dx_ptr, a->dtype, a->n, a->cin, a->h, a->w);
 
   // stream-ordered scratch: dz3, two mid-wide gradient buffers (the BatchNorm apply overwrites its input gradient in
-  // place is NOT assumed: reduce + apply read one and write the other), the active-filter gradient, two packed weights
+  // place is NOT assumed: reduce + apply read one and write the other), the active-filter gradient
   const int64_t midb = align256(L.P * a->mid * 2), outb = align256(L.P * a->cout * 2);
   const int64_t dwab = align256((int64_t)sizeof(float) * a->mid * a->ks * a->ks);
-  const int64_t wb = align256((int64_t)384 * 64 * 2);
   char* scratch = nullptr;
   keep_async_pool_resident();
-  OFA_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&scratch), (size_t)(outb + 2 * midb + dwab + 2 * wb), st));
+  OFA_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&scratch), (size_t)(outb + 2 * midb + dwab), st));
   const OfaTensor4 dz3 = nhwc16(scratch, a->dtype, a->n, a->cout, a->h, a->w);
   const OfaTensor4 gA = nhwc16(scratch + outb, a->dtype, a->n, a->mid, a->h, a->w);
   const OfaTensor4 gB = nhwc16(scratch + outb + midb, a->dtype, a->n, a->mid, a->h, a->w);
   float* dwa = reinterpret_cast<float*>(scratch + outb + 2 * midb);
-  void* wproj_t = scratch + outb + 2 * midb + dwab;
-  void* wexp_t = scratch + outb + 2 * midb + dwab + wb;
+  const void* wproj_t = ws + L.wproj_t;
+  const void* wexp_t = ws + L.wexp_t;
 
   do {
     // BN3 (no activation; the residual branch passes dy through unchanged)
     if ((rc = bn_bwd(z3, dy, dz3, a->bn_proj, mean3, var3, OFA_ACT_NONE, g->dbeta[2], g->dgamma[2], st))) break;
     // project 1x1: data gradient = conv of dz3 with W_proj^T (cout -> mid), weight gradient on tcgen05
-    if ((rc = launch_pack_weight(a->w_proj, a->w_proj_si, a->w_proj_so, 0, 0, a->cout, a->mid, 1, a->cout,
-                                 (a->mid + 15) / 16 * 16, OFA_STORE_PLAIN, f16, wproj_t, st))) break;
     if ((rc = pointwise_tc(dz3, gA, wproj_t, a->cout, a->mid, nullptr, st))) break;                    // gA = d(a2)
     if (!wgrad_tc_supported(&a2, &dz3, a->mid, a->cout, 1)) { rc = fail(OFA_ERR_UNSUPPORTED, "mbconv training block: project weight gradient"); break; }
     if ((rc = launch_wgrad_tc(&a2, &dz3, g->dw_proj, a->w_proj_so, a->w_proj_si, 0, 0, a->mid, a->cout, 1, st))) break;
@@ -237,8 +250,6 @@ int ofa_mbconv_train_bwd(const OfaMBConvTrainArgs* a, const void* dy_ptr, void* 
     // BN1 + act
     if ((rc = bn_bwd(z1, gA, gB, a->bn_exp, mean1, var1, a->act, g->dbeta[0], g->dgamma[0], st))) break;  // gB = d(z1)
     // expand 1x1: dx = conv(dz1, W_exp^T) [+ dy: the identity branch], weight gradient
-    if ((rc = launch_pack_weight(a->w_exp, a->w_exp_si, a->w_exp_so, 0, 0, a->mid, a->cin, 1, a->mid,
-                                 (a->cin + 15) / 16 * 16, OFA_STORE_PLAIN, f16, wexp_t, st))) break;
     if ((rc = pointwise_tc(gB, dx, wexp_t, a->mid, a->cin, a->add_residual ? &dy : nullptr, st))) break;
     if (!wgrad_tc_supported(&x, &gB, a->cin, a->mid, 1)) { rc = fail(OFA_ERR_UNSUPPORTED, "mbconv training block: expand weight gradient"); break; }
     rc = launch_wgrad_tc(&x, &gB, g->dw_exp, a->w_exp_so, a->w_exp_si, 0, 0, a->cin, a->mid, 1, st);

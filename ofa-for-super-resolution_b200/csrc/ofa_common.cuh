@@ -1,5 +1,6 @@
 // Shared host/device helpers of libofa_sr_b200 (B200 / sm_100a only).
 #pragma once
+#include <string.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -31,6 +32,34 @@ int sm_count();                      // cached per device
     if (e__ != cudaSuccess)                                                              \
       return ::ofa::fail(OFA_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__)); \
   } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// Programmatic dependent launch.  The training step is ~550 short launches (a few to a few tens of microseconds each)
+// in one stream; with plain stream ordering every kernel's launch latency and block ramp-up sit between two kernels.
+// Kernels that start with pdl_wait() may be launched with launch_pdl(): their blocks are scheduled while the
+// preceding kernel drains and block in griddepcontrol.wait until it has completed and its writes are visible --
+// the same ordering as before, minus the launch gap.  pdl_wait() must come before the first global-memory access;
+// without the launch attribute it is a no-op.  OFA_PDL=0 launches everything with plain stream ordering.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+bool pdl_enabled();   // api.cu: OFA_PDL != "0"
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // ------------------------------------------------------------------------------------------------
 // strided 4-D activation view usable on the device

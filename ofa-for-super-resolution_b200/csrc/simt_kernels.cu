@@ -237,6 +237,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, long long w_so, 
                                    long long w_sh, long long w_sw, int cin, int cout, int ks,
                                    int cin_pad, int cout_pad, int store, int f16,
                                    uint16_t* __restrict__ out) {
+  pdl_wait();
   long long total = (long long)ks * ks * cout_pad * cin_pad;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -264,7 +265,7 @@ int launch_pack_weight(const float* w, long long w_so, long long w_si, long long
   if (total == 0) return OFA_OK;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 1184) blocks = 1184;
-  pack_weight_kernel<<<blocks, 256, 0, st>>>(w, w_so, w_si, w_sh, w_sw, cin, cout, ks, cin_pad, cout_pad, store, f16,
+  launch_pdl(pack_weight_kernel, dim3(blocks), dim3(256), 0, st, w, w_so, w_si, w_sh, w_sw, cin, cout, ks, cin_pad, cout_pad, store, f16,
                                              reinterpret_cast<uint16_t*>(out));
   return check_launch("pack_weight_kernel");
 }
@@ -272,6 +273,7 @@ int launch_pack_weight(const float* w, long long w_so, long long w_si, long long
 // the same pack for a device-resident list of jobs (blockIdx.y = job): one launch refreshes every 16-bit weight copy a
 // forward pass is going to use
 __global__ void pack_weights_multi_kernel(const OfaPackJob* __restrict__ jobs) {
+  pdl_wait();
   const OfaPackJob j = jobs[blockIdx.y];
   const int ks = j.ks, cin_pad = j.cin_pad, cout_pad = j.cout_pad;
   const int f16 = j.dtype == OFA_F16 ? 1 : 0;
@@ -294,9 +296,50 @@ __global__ void pack_weights_multi_kernel(const OfaPackJob* __restrict__ jobs) {
   }
 }
 
+// up to four jobs passed BY VALUE (kernel parameters): the training block packs its two forward and two
+// data-gradient weight copies with one launch and no device-side job table
+struct PackJobs4 { OfaPackJob j[4]; };
+
+__device__ __forceinline__ void pack_job(const OfaPackJob& j, int start, int stride) {
+  const int ks = j.ks, cin_pad = j.cin_pad, cout_pad = j.cout_pad;
+  const int f16 = j.dtype == OFA_F16 ? 1 : 0;
+  const float* __restrict__ w = j.w;
+  uint16_t* __restrict__ out = reinterpret_cast<uint16_t*>(j.out);
+  const int total = ks * ks * cout_pad * cin_pad;
+  for (int i = start; i < total; i += stride) {
+    const int ci = i % cin_pad;
+    const int r = i / cin_pad;
+    const int o = r % cout_pad;
+    const int tap = r / cout_pad;
+    const int ky = tap / ks, kx = tap - ky * ks;
+    float v = 0.f;
+    if (ci < j.cin && o < j.cout) {
+      int oo = o;
+      if (j.store == OFA_STORE_PIXELSHUFFLE2) { const int q = j.cout >> 2; oo = 4 * (o % q) + o / q; }
+      v = w[oo * j.w_so + ci * j.w_si + ky * j.w_sh + kx * j.w_sw];
+    }
+    out[i] = cvt16(v, f16);
+  }
+}
+
+__global__ void pack_weights4_kernel(const __grid_constant__ PackJobs4 jobs) {
+  pdl_wait();
+  pack_job(jobs.j[blockIdx.y], blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+}
+
+int launch_pack_weights4(const OfaPackJob* jobs_host, int njobs, cudaStream_t st) {
+  if (njobs <= 0) return OFA_OK;
+  if (njobs > 4) return fail(OFA_ERR_ARG, "launch_pack_weights4: at most 4 jobs");
+  PackJobs4 pj;
+  memset(&pj, 0, sizeof(pj));
+  for (int i = 0; i < njobs; ++i) pj.j[i] = jobs_host[i];
+  launch_pdl(pack_weights4_kernel, dim3(24, (unsigned)njobs), dim3(256), 0, st, pj);
+  return check_launch("pack_weights4_kernel");
+}
+
 int launch_pack_weights_multi(const OfaPackJob* jobs_device, int njobs, cudaStream_t st) {
   if (njobs <= 0) return OFA_OK;
-  pack_weights_multi_kernel<<<dim3(24, (unsigned)njobs), 256, 0, st>>>(jobs_device);
+  launch_pdl(pack_weights_multi_kernel, dim3(dim3(24, (unsigned)njobs)), dim3(256), 0, st, jobs_device);
   return check_launch("pack_weights_multi_kernel");
 }
 
@@ -358,6 +401,7 @@ template <bool HAS_RES>
 __global__ void __launch_bounds__(256)
 affine_act_vec8_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const uint4* __restrict__ res, Epi epi,
                        int f16, unsigned nvec, unsigned V) {
+  pdl_wait();
   const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
   const int c0 = 8 * (int)(gid % V);
   float sc[8], sh[8];
@@ -475,10 +519,10 @@ int launch_affine_act(const TV& x, const TV& y, const Epi& epi, int store, cudaS
     const uint4* xp = reinterpret_cast<const uint4*>(x.ptr);
     uint4* yp = reinterpret_cast<uint4*>(y.ptr);
     if (epi.res.ptr)
-      affine_act_vec8_kernel<true><<<nb, 256, 0, st>>>(xp, yp, reinterpret_cast<const uint4*>(epi.res.ptr), epi,
+      launch_pdl(affine_act_vec8_kernel<true>, dim3(nb), dim3(256), 0, st, xp, yp, reinterpret_cast<const uint4*>(epi.res.ptr), epi,
                                                        x.dtype == OFA_F16, nvec, V);
     else
-      affine_act_vec8_kernel<false><<<nb, 256, 0, st>>>(xp, yp, nullptr, epi, x.dtype == OFA_F16, nvec, V);
+      launch_pdl(affine_act_vec8_kernel<false>, dim3(nb), dim3(256), 0, st, xp, yp, nullptr, epi, x.dtype == OFA_F16, nvec, V);
     return check_launch("affine_act_vec8_kernel");
   }
   if (store == OFA_STORE_PLAIN && total < (1ll << 32) && tv_pair_ok(x) && tv_pair_ok(y) &&
@@ -623,6 +667,7 @@ bn_stats_partial_nhwc_kernel(TV x, float* __restrict__ part, long long per_split
 __global__ void __launch_bounds__(256)
 bn_stats_partial_vec8_kernel(const uint4* __restrict__ x, int f16, int V, long long P, float* __restrict__ part,
                              long long per_split) {
+  pdl_wait();
   __shared__ float red[3][2048];
   const int cg = threadIdx.x % V, pl = threadIdx.x / V, PL = blockDim.x / V, C = 8 * V;
   const long long p_lo = (long long)blockIdx.y * per_split;
@@ -720,6 +765,7 @@ __global__ void __launch_bounds__(BN_FIN_THREADS)
 bn_stats_final_kernel(const float* __restrict__ part, int splits, int C, float* __restrict__ mean,
                       float* __restrict__ var, float* __restrict__ rm, float* __restrict__ rv, float momentum, float unbias,
                       long long* __restrict__ num_batches_tracked) {
+  pdl_wait();
   const int c = blockIdx.x * (BN_FIN_THREADS / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   // nn.BatchNorm2d's counter, bumped in the same launch (`bn.num_batches_tracked += 1`, dynamic_op.py:156)
   if (num_batches_tracked && blockIdx.x == 0 && threadIdx.x == 0) *num_batches_tracked += 1;
@@ -811,7 +857,7 @@ int launch_bn_stats_update(const TV& x, float* mean, float* var, float* rm, floa
   } else if (bn_vec8_ok(x)) {
     const int V = x.c / 8;
     dim3 grid(1, splits);
-    bn_stats_partial_vec8_kernel<<<grid, V * (256 / V), 0, st>>>(reinterpret_cast<const uint4*>(x.ptr),
+    launch_pdl(bn_stats_partial_vec8_kernel, dim3(grid), dim3(V * (256 / V)), 0, st, reinterpret_cast<const uint4*>(x.ptr),
                                                                 x.dtype == OFA_F16, V, (long long)x.n * x.h * x.w,
                                                                 part, per_split);
     rc = check_launch("bn_stats_partial_vec8_kernel");
@@ -825,7 +871,7 @@ int launch_bn_stats_update(const TV& x, float* mean, float* var, float* rm, floa
     rc = check_launch("bn_stats_partial_kernel");
   }
   if (!rc) {
-    bn_stats_final_kernel<<<(x.c + BN_FIN_THREADS / 32 - 1) / (BN_FIN_THREADS / 32), BN_FIN_THREADS, 0, st>>>(
+    launch_pdl(bn_stats_final_kernel, dim3((x.c + BN_FIN_THREADS / 32 - 1) / (BN_FIN_THREADS / 32)), dim3(BN_FIN_THREADS), 0, st, 
         part, splits, x.c, mean, var, rm, rv, momentum, unbias, num_batches_tracked);
     rc = check_launch("bn_stats_final_kernel");
   }
@@ -944,6 +990,7 @@ bn_bwd_reduce_partial_vec8_kernel(const uint4* __restrict__ x, const uint4* __re
                                   long long P, const float* __restrict__ gamma, const float* __restrict__ beta,
                                   const float* __restrict__ mean, const float* __restrict__ var, float eps, int act,
                                   float* __restrict__ part, long long per_split) {
+  pdl_wait();
   __shared__ float red[2][2048];
   const int cg = threadIdx.x % V, pl = threadIdx.x / V, PL = blockDim.x / V, C = 8 * V;
   const long long p_lo = (long long)blockIdx.y * per_split;
@@ -1037,6 +1084,7 @@ bn_bwd_reduce_partial_smallc_kernel(TV x, TV dy, const float* __restrict__ gamma
 __global__ void __launch_bounds__(BN_FIN_THREADS)
 bn_bwd_reduce_final_kernel(const float* __restrict__ part, int splits, int C, float* __restrict__ sum_dz,
                            float* __restrict__ sum_dz_xhat) {
+  pdl_wait();
   const int c = blockIdx.x * (BN_FIN_THREADS / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (c >= C) return;
   double t0 = 0.0, t1 = 0.0;
@@ -1071,7 +1119,7 @@ int launch_bn_bwd_reduce(const TV& x, const TV& dy, const float* gamma, const fl
   } else if (bn_vec8_ok(x) && tv_vec8_ok(dy) && dy.dtype == x.dtype) {
     const int V = x.c / 8;
     dim3 grid(1, splits);
-    bn_bwd_reduce_partial_vec8_kernel<<<grid, V * (256 / V), 0, st>>>(
+    launch_pdl(bn_bwd_reduce_partial_vec8_kernel, dim3(grid), dim3(V * (256 / V)), 0, st, 
         reinterpret_cast<const uint4*>(x.ptr), reinterpret_cast<const uint4*>(dy.ptr), x.dtype == OFA_F16, V,
         (long long)x.n * x.h * x.w, gamma, beta, mean, var, eps, act, part, per_split);
     rc = check_launch("bn_bwd_reduce_partial_vec8_kernel");
@@ -1087,7 +1135,7 @@ int launch_bn_bwd_reduce(const TV& x, const TV& dy, const float* gamma, const fl
     rc = check_launch("bn_bwd_reduce_partial_kernel");
   }
   if (!rc) {
-    bn_bwd_reduce_final_kernel<<<(x.c + BN_FIN_THREADS / 32 - 1) / (BN_FIN_THREADS / 32), BN_FIN_THREADS, 0, st>>>(part, splits, x.c, sum_dz, sum_dz_xhat);
+    launch_pdl(bn_bwd_reduce_final_kernel, dim3((x.c + BN_FIN_THREADS / 32 - 1) / (BN_FIN_THREADS / 32)), dim3(BN_FIN_THREADS), 0, st, part, splits, x.c, sum_dz, sum_dz_xhat);
     rc = check_launch("bn_bwd_reduce_final_kernel");
   }
   cudaFreeAsync(part, st);
@@ -1157,6 +1205,7 @@ bn_bwd_apply_vec8_kernel(const uint4* __restrict__ x, const uint4* __restrict__ 
                          const float* __restrict__ mean, const float* __restrict__ var, float eps, int act,
                          int training, const float* __restrict__ sum_dz, const float* __restrict__ sum_dz_xhat,
                          float invP, int f16, unsigned nvec, unsigned V) {
+  pdl_wait();
   const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
   const int c0 = 8 * (int)(gid % V);
   // dx = a * (dz - k1 - xhat * k2),  xhat = x * rstd + nm,  z = g * xhat + b
@@ -1200,7 +1249,7 @@ int launch_bn_bwd_apply(const TV& x, const TV& dy, const TV& dx, const float* ga
   if (total < (1ll << 34) && tv_vec8_ok(x) && tv_vec8_ok(dy) && tv_vec8_ok(dx) && dy.dtype == x.dtype &&
       dx.dtype == x.dtype) {
     const unsigned nvec = (unsigned)(total / 8), V = (unsigned)(x.c / 8);
-    bn_bwd_apply_vec8_kernel<<<vec8_blocks(nvec, V, 256, 3), 256, 0, st>>>(
+    launch_pdl(bn_bwd_apply_vec8_kernel, dim3(vec8_blocks(nvec, V, 256, 3)), dim3(256), 0, st, 
         reinterpret_cast<const uint4*>(x.ptr), reinterpret_cast<const uint4*>(dy.ptr), reinterpret_cast<uint4*>(dx.ptr),
         gamma, beta, mean, var, eps, act, training, sum_dz, sum_dz_xhat,
         1.f / (float)((long long)x.n * x.h * x.w), x.dtype == OFA_F16, nvec, V);
@@ -1297,6 +1346,7 @@ template <> struct PairRaw<false> {
 template <int KS, bool F32>
 __global__ void __launch_bounds__(DwRows<KS>::THREADS, DwRows<KS>::BLOCKS_PER_SM)
 dw_bwd_filter_rows_kernel(TV x, TV dy, float* __restrict__ dw, int rows_per_block) {
+  pdl_wait();
   typedef typename PairRaw<F32>::T Raw;
   constexpr int R = KS / 2, RG = DwRows<KS>::RG, T = KS * KS;
   __shared__ float red[RG][64][T];
@@ -1374,8 +1424,8 @@ static void launch_dw_rows(const TV& x, const TV& dy, float* dw, cudaStream_t st
   if (rpb < DwRows<KS>::RG) rpb = DwRows<KS>::RG;
   sp = (rows + rpb - 1) / rpb;
   dim3 grid(cb, (unsigned)sp);
-  if (x.dtype == OFA_F32) dw_bwd_filter_rows_kernel<KS, true><<<grid, DwRows<KS>::THREADS, 0, st>>>(x, dy, dw, rpb);
-  else dw_bwd_filter_rows_kernel<KS, false><<<grid, DwRows<KS>::THREADS, 0, st>>>(x, dy, dw, rpb);
+  if (x.dtype == OFA_F32) launch_pdl(dw_bwd_filter_rows_kernel<KS, true>, dim3(grid), dim3(DwRows<KS>::THREADS), 0, st, x, dy, dw, rpb);
+  else launch_pdl(dw_bwd_filter_rows_kernel<KS, false>, dim3(grid), dim3(DwRows<KS>::THREADS), 0, st, x, dy, dw, rpb);
 }
 
 int launch_dw_bwd_filter(const TV& x, const TV& dy, int ks, float* dw, cudaStream_t st) {
@@ -1416,6 +1466,7 @@ int launch_dw_bwd_filter(const TV& x, const TV& dy, int ks, float* dw, cudaStrea
 // per (channel, tap) so that consecutive threads touch consecutive addresses
 __global__ void active_filter_bwd_crop_kernel(int kmax, int ks, int C, const float* __restrict__ dwa,
                                               float* __restrict__ dw7) {
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= C * ks * ks) return;
   const int c = i / (ks * ks), t = i - c * ks * ks;
@@ -1433,6 +1484,7 @@ __global__ void __launch_bounds__(AFB_CH)
 active_filter_bwd_kernel(const float* __restrict__ w7, int kmax, const float* __restrict__ m75,
                          const float* __restrict__ m53, int ks, int C, const float* __restrict__ dwa,
                          float* __restrict__ dw7, float* __restrict__ dm75, float* __restrict__ dm53) {
+  pdl_wait();
   __shared__ float s_src[25][AFB_CH + 1];     // the values the current matrix multiplied (per channel)
   __shared__ float s_g[25][AFB_CH + 1];       // the gradient of that matrix product's output (per channel)
   const int c = blockIdx.x * AFB_CH + threadIdx.x;
@@ -1509,10 +1561,10 @@ int launch_active_filter_bwd(const float* w7, int kmax, const float* m75, const 
   if (C == 0) return OFA_OK;
   if (!transform_on || ks == kmax) {
     const int total = C * ks * ks;
-    active_filter_bwd_crop_kernel<<<(total + 255) / 256, 256, 0, st>>>(kmax, ks, C, dwa, dw7);
+    launch_pdl(active_filter_bwd_crop_kernel, dim3((total + 255) / 256), dim3(256), 0, st, kmax, ks, C, dwa, dw7);
     return check_launch("active_filter_bwd_crop_kernel");
   }
-  active_filter_bwd_kernel<<<(C + AFB_CH - 1) / AFB_CH, AFB_CH, 0, st>>>(w7, kmax, m75, m53, ks, C, dwa, dw7, dm75,
+  launch_pdl(active_filter_bwd_kernel, dim3((C + AFB_CH - 1) / AFB_CH), dim3(AFB_CH), 0, st, w7, kmax, m75, m53, ks, C, dwa, dw7, dm75,
                                                                        dm53);
   return check_launch("active_filter_bwd_kernel");
 }

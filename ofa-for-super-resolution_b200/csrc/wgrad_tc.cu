@@ -52,6 +52,7 @@ __device__ __forceinline__ void wg_unit(const WgradParams& p, int u, int& tap, i
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_m, const __grid_constant__ CUtensorMap tm_n,
                 const WgradParams p, const int group_size) {
+  pdl_wait();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES);
@@ -242,7 +243,7 @@ int launch_wgrad_tc(const OfaTensor4* x, const OfaTensor4* dy, float* dw, long l
   }
   const size_t smem = 1024 + WG_STAGES * WG_STAGE_BYTES + 128;
   OFA_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  wgrad_tc_kernel<<<p.groups * p.splits, WG_THREADS, smem, st>>>(tmm, tmn, p, gs);
+  launch_pdl(wgrad_tc_kernel, dim3(p.groups * p.splits), dim3(WG_THREADS), smem, st, tmm, tmn, p, gs);
   return check_launch("wgrad_tc_kernel");
 }
 
