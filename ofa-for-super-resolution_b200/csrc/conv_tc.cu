@@ -24,6 +24,7 @@
 #include "sm100_ptx.cuh"
 
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace ofa {
@@ -82,6 +83,7 @@ struct ConvTcParams {
   const float* gamma; const float* beta; const float* mean; const float* var; float eps;
   TV y;
   TV res;
+  unsigned long long* trace;   // debug (OFA_CONV_TC_TRACE=1): per-CTA clock stamps of the pipeline stages, else nullptr
 };
 
 __device__ __forceinline__ int packed_to_conv_channel(int op, int cout, int store) {
@@ -174,7 +176,10 @@ __device__ __forceinline__ void emit16(const ConvTcParams& p, const float* s_sca
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                const ConvTcParams p) {
+  const long long t_entry = clock64();
   pdl_wait();
+#define OFA_TRACE(slot) do { if (p.trace && blockIdx.x < 16) p.trace[blockIdx.x * 16 + (slot)] = (unsigned long long)clock64(); } while (0)
+  if (p.trace && blockIdx.x < 16 && threadIdx.x == 0) { p.trace[blockIdx.x * 16 + 0] = (unsigned long long)t_entry; OFA_TRACE(1); }
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
   const int taps = p.ks * p.ks;
@@ -231,6 +236,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);   // warp-uniform by construction
+  if (threadIdx.x == 0) OFA_TRACE(2);                                   // prologue done
 
   const int tiles_per_img = p.tiles_h * p.tiles_w;
   const int outer_splits = p.n_splits / p.inner_splits;
@@ -288,6 +294,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     int as = 0, bs = 0, acc = 0;
     uint32_t aph = 0, bph = 0, accph = 0;
     if (p.b_resident) ptx::mbar_wait(bres_bar, 0);
+    if (lane == 0) OFA_TRACE(3);                                        // resident weights landed
     for (int wi = blockIdx.x; wi < num_work; wi += gridDim.x) {
       const int split0 = wi % outer_splits;
       const int as_item = as;           // first A stage of this work item
@@ -302,6 +309,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         uint32_t first = 0;             // 0 until the first MMA of this accumulator has been issued
         for (int kc = 0; kc < p.kcs; ++kc) {
           if (s == 0) ptx::mbar_wait(&a_full[a_cur], a_cur_ph);
+          if (lane == 0 && wi == blockIdx.x && s == 0) OFA_TRACE(4 + (kc < 6 ? kc : 5));   // K chunk kc of the first item landed
           ptx::tc_fence_after();
           const uint32_t a_base = ptx::smem_u32(sA) + (uint32_t)(a_cur * a_stride);
           uint32_t b_res = sB_addr + (uint32_t)((kc * p.cout_pad + row0) * 128);   // resident: tap-major blocks
@@ -336,6 +344,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         }
         if (s == p.inner_splits - 1) { as = a_cur; aph = a_cur_ph; }
         ptx::umma_commit_elect(&tfull[acc]);
+        if (lane == 0 && wi == blockIdx.x && s == 0) OFA_TRACE(10);      // first accumulator's MMAs issued
         if (++acc == 2) { acc = 0; accph ^= 1; }
       }
     }
@@ -358,6 +367,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       for (int s = 0; s < p.inner_splits; ++s) {
         const int col0 = (split0 * p.inner_splits + s) * p.BN;
         ptx::mbar_wait(&tfull[acc], accph);
+        if (threadIdx.x == 64 && wi == blockIdx.x) OFA_TRACE(11 + (s < 3 ? s : 2));   // accumulator s complete
         ptx::tc_fence_after();
         const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * acc_cols + m * p.BN);
         uint8_t* stage = s_stage + ew * STAGE_BYTES;
@@ -431,8 +441,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     }
   }
 
+  if (threadIdx.x == 64) OFA_TRACE(14);                                 // epilogue warp 2 done
   ptx::tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) OFA_TRACE(15);
+#undef OFA_TRACE
   if (warp == 2) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
@@ -573,11 +586,34 @@ int launch_conv_tc(const OfaConvArgs* a_in, cudaStream_t st) {
                          const_cast<void*>(a->w_bf16), dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
-  OFA_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  static int trace_on = -1;
+  if (trace_on < 0) { const char* e = getenv("OFA_CONV_TC_TRACE"); trace_on = (e && e[0] == '1') ? 1 : 0; }
+  p.trace = nullptr;
+  if (trace_on) {
+    static unsigned long long* tbuf = nullptr;
+    if (!tbuf) cudaMalloc(reinterpret_cast<void**>(&tbuf), 16 * 16 * sizeof(unsigned long long));
+    cudaMemsetAsync(tbuf, 0, 16 * 16 * sizeof(unsigned long long), st);
+    p.trace = tbuf;
+  }
+  static unsigned char attr_done[64] = {0};
+  if (once_per_device(attr_done))
+    OFA_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   const int num_work = p.N * p.tiles_h * p.tiles_w * (p.n_splits / p.inner_splits);
   int grid = sm_count();
   if (grid > num_work) grid = num_work;
   launch_pdl(conv_tc_kernel, dim3(grid), dim3(NUM_THREADS), smem, st, tx, tw, p);
+  if (trace_on) {
+    unsigned long long h[16 * 16];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, p.trace, sizeof(h), cudaMemcpyDeviceToHost);
+    for (int b = 0; b < 2; ++b) {
+      const unsigned long long* t = h + b * 16;
+      fprintf(stderr, "conv_tc trace cin %d cout %d ks %d P %d cta %d (clk from entry): pdl_wait %lld prologue %lld weights %lld A0 %lld A1 %lld A5 %lld mma_issued %lld acc0 %lld acc1 %lld acc2 %lld epi_done %lld end %lld\n",
+              p.cin, p.cout, p.ks, p.N * p.H * p.W, b, (long long)(t[1] - t[0]), (long long)(t[2] - t[0]), (long long)(t[3] - t[0]), (long long)(t[4] - t[0]),
+              t[5] ? (long long)(t[5] - t[0]) : -1ll, t[9] ? (long long)(t[9] - t[0]) : -1ll, (long long)(t[10] - t[0]), (long long)(t[11] - t[0]),
+              t[12] ? (long long)(t[12] - t[0]) : -1ll, t[13] ? (long long)(t[13] - t[0]) : -1ll, (long long)(t[14] - t[0]), (long long)(t[15] - t[0]));
+    }
+  }
   return check_launch("conv_tc_kernel");
 }
 

@@ -3,8 +3,10 @@
 //
 //   * a CTA owns a TH x TW pixel tile of one 64-channel chunk; the (TH+ks-1) x (TW+ks-1) x 64 halo
 //     box arrives with ONE TMA load whose out-of-bounds zero fill is the conv's zero padding;
-//   * while the load is in flight all threads derive the chunk's active filters from the 7x7
-//     weights and the learned 7->5 / 5->3 matrices (the transform is applied on the fly);
+//   * the active filters (7x7 weights through the learned 7->5 / 5->3 matrices, rotated for the data gradient)
+//     are derived ONCE per launch by dw_prep_filters_kernel; a CTA fetches its chunk's ks*ks x 64 floats with one bulk
+//     copy on the same mbarrier as the halo (round 1 re-derived them in every tile's CTA: dependent global loads that
+//     held 42 % of the kernel's stall samples and made ks = 3 cost as much as ks = 7);
 //   * lane = channel pair, so every shared-memory access of a warp is one conflict-free 128-byte
 //     pixel row; each thread slides a window over 16 output pixels per pass so one smem word feeds
 //     up to ks taps; math is packed fp32x2 FMA (fma.rn.f32x2), fp32 accumulation.
@@ -33,6 +35,7 @@ struct DwParams {
   const float* w7;
   const float* m75;
   const float* m53;
+  const float* filt;   // [C / 64][KS * KS][64] fp32 active filters (already rotated when flip), from dw_prep_filters_kernel
   const float* gamma; const float* beta; const float* mean; const float* var; float eps;
   int act;
   uint16_t* y;
@@ -47,9 +50,7 @@ struct DwSmem {
   static constexpr int TILE_BYTES = HALO_H * HALO_W * CH * 2;
   static constexpr int FILT_OFF = (TILE_BYTES + 127) / 128 * 128;
   static constexpr int FILT_BYTES = KS * KS * CH * 4;
-  static constexpr int K5_OFF = FILT_OFF + FILT_BYTES;
-  static constexpr int K5_BYTES = CH * 25 * 4;
-  static constexpr int SS_OFF = K5_OFF + K5_BYTES;
+  static constexpr int SS_OFF = FILT_OFF + FILT_BYTES;
   static constexpr int BAR_OFF = SS_OFF + 2 * CH * 4;
   static constexpr int TOTAL = BAR_OFF + 16 + 128;  // + alignment slack
 };
@@ -59,7 +60,7 @@ __device__ __forceinline__ float2 bf2_unpack(uint32_t u) {
 }
 
 template <int KS, int TH, int TW>
-__global__ void __launch_bounds__(32 * TH, 2)
+__global__ void __launch_bounds__(32 * TH, TH == 12 ? 3 : 2)
 dw_fast_kernel(const __grid_constant__ CUtensorMap tmap_x, const DwParams p) {
   pdl_wait();
   using L = DwSmem<KS, TH, TW>;
@@ -68,7 +69,6 @@ dw_fast_kernel(const __grid_constant__ CUtensorMap tmap_x, const DwParams p) {
   uint8_t* smem = smem_raw + ((128u - (ptx::smem_u32(smem_raw) & 127u)) & 127u);   // keeps the shared address space
   const uint32_t* tile = reinterpret_cast<const uint32_t*>(smem);           // [HALO_H][HALO_W][32] words
   float* filt = reinterpret_cast<float*>(smem + L::FILT_OFF);               // [KS*KS][CH]
-  float* k5s = reinterpret_cast<float*>(smem + L::K5_OFF);                  // [CH][25]
   float* s_scale = reinterpret_cast<float*>(smem + L::SS_OFF);
   float* s_shift = s_scale + CH;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
@@ -85,53 +85,18 @@ dw_fast_kernel(const __grid_constant__ CUtensorMap tmap_x, const DwParams p) {
   if (tid == 0) {
     ptx::mbar_init(bar, 1);
     ptx::fence_barrier_init();
-    ptx::mbar_arrive_expect_tx(bar, (uint32_t)L::TILE_BYTES);
+    ptx::mbar_arrive_expect_tx(bar, (uint32_t)(L::TILE_BYTES + L::FILT_BYTES));
     ptx::tma_load_4d(smem, &tmap_x, bar, c0, w0 - R, h0 - R, n);
+    // the chunk's active filters were derived once per launch (dw_prep_filters_kernel): one 12.5 KB bulk copy instead of
+    // every tile's CTA re-deriving them with dependent global loads (42 % of the warp-stall samples of the old kernel)
+    ptx::bulk_load(filt, p.filt + (size_t)blockIdx.y * KS * KS * CH, (uint32_t)L::FILT_BYTES, bar);
   }
-
-  // ---- active filters of this channel chunk (overlaps the TMA load) -------------------------------
-  const int kmax = p.kmax;
-  const bool transform = p.transform_on && KS < kmax;
-  const bool step75 = transform && kmax == 7 && p.m75 != nullptr;
   if (tid < CH) {
     int c = c0 + tid;
     float g = p.gamma ? p.gamma[c] : 1.f, b = p.beta ? p.beta[c] : 0.f;
     float m = p.mean ? p.mean[c] : 0.f, rstd = p.var ? rsqrtf(p.var[c] + p.eps) : 1.f;
     s_scale[tid] = g * rstd;
     s_shift[tid] = b - m * g * rstd;
-  }
-  if (step75) {
-    for (int it = tid; it < CH * 25; it += THREADS) {
-      int c = it / 25, j = it - c * 25;
-      const float* w = p.w7 + (size_t)(c0 + c) * 49;
-      float acc = 0.f;
-#pragma unroll 5
-      for (int i = 0; i < 25; ++i) acc = fmaf(w[(i / 5 + 1) * 7 + (i % 5 + 1)], p.m75[j * 25 + i], acc);
-      k5s[c * 25 + j] = acc;
-    }
-  }
-  __syncthreads();
-  for (int it = tid; it < CH * KS * KS; it += THREADS) {
-    int c = it % CH, j = it / CH;
-    const float* w = p.w7 + (size_t)(c0 + c) * kmax * kmax;
-    float v;
-    if (!transform) {
-      const int s = kmax / 2 - R;
-      v = w[(j / KS + s) * kmax + (j % KS + s)];
-    } else {
-      const float* cur = step75 ? (k5s + c * 25) : w;
-      const int kc = step75 ? 5 : kmax;
-      if (KS == kc) {
-        v = cur[j];
-      } else {  // KS == 3
-        const int s = kc / 2 - 1;
-        float acc = 0.f;
-#pragma unroll
-        for (int i = 0; i < 9; ++i) acc = fmaf(cur[(i / 3 + s) * kc + (i % 3 + s)], p.m53[j * 9 + i], acc);
-        v = acc;
-      }
-    }
-    filt[(p.flip ? KS * KS - 1 - j : j) * CH + c] = v;   // flip: 180-degree rotation = the data-gradient filter
   }
   __syncthreads();
   ptx::mbar_wait(bar, 0);
@@ -148,7 +113,7 @@ dw_fast_kernel(const __grid_constant__ CUtensorMap tmap_x, const DwParams p) {
     float2 acc[RUN];
 #pragma unroll
     for (int i = 0; i < RUN; ++i) acc[i] = make_float2(0.f, 0.f);
-#pragma unroll(KS == 7 ? 1 : KS)                       // ks = 7 fully unrolled hoists 7 rows of loads and spills
+#pragma unroll(KS >= 5 ? 1 : KS)                       // ks >= 5 fully unrolled hoists rows of loads and spills
     for (int ky = 0; ky < KS; ++ky) {
       const uint32_t* row = tile + ((warp + ky) * L::HALO_W + x0) * 32 + lane;
       float2 in[RUN + KS - 1];
@@ -176,6 +141,67 @@ dw_fast_kernel(const __grid_constant__ CUtensorMap tmap_x, const DwParams p) {
   }
 }
 
+// Active filters of every channel, once per launch: out[chunk][tap][c % 64] (tap order rotated by 180 degrees when
+// flip: the data-gradient filter).  One block per PREP_CH channels: the weights and the two transform matrices are staged
+// in shared memory first (coalesced loads), then the 7 -> 5 step runs over (channel, output tap) pairs and the -> 3 step
+// over (channel, tap) -- same fmaf order as active_filter_channel (ofa_common.cuh), so the values are bit-identical to it.
+constexpr int PREP_CH = 16;
+
+__global__ void __launch_bounds__(256)
+dw_prep_filters_kernel(const float* __restrict__ w7, int kmax, const float* __restrict__ m75,
+                       const float* __restrict__ m53, int transform_on, int ks, int flip, float* __restrict__ out) {
+  pdl_wait();
+  __shared__ float s_w[PREP_CH * 49];
+  __shared__ float s_m75[625];
+  __shared__ float s_m53[81];
+  __shared__ float s_k5[PREP_CH * 25];
+  const int c0 = blockIdx.x * PREP_CH;
+  const int tid = threadIdx.x;
+  const int kk = kmax * kmax;
+  const bool transform = transform_on && ks < kmax;
+  const bool step75 = transform && kmax == 7 && m75 != nullptr;
+  for (int i = tid; i < PREP_CH * kk; i += blockDim.x) s_w[i] = w7[(size_t)c0 * kk + i];
+  if (step75) for (int i = tid; i < 625; i += blockDim.x) s_m75[i] = m75[i];
+  if (transform && ks == 3) for (int i = tid; i < 81; i += blockDim.x) s_m53[i] = m53[i];
+  __syncthreads();
+  if (step75) {
+    for (int it = tid; it < PREP_CH * 25; it += blockDim.x) {
+      const int c = it / 25, j = it - c * 25;
+      const float* w = s_w + c * 49;
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < 25; ++i) acc = fmaf(w[(i / 5 + 1) * 7 + (i % 5 + 1)], s_m75[j * 25 + i], acc);
+      s_k5[c * 25 + j] = acc;
+    }
+    __syncthreads();
+  }
+  const int R = ks / 2;
+  const int chunk = c0 / CH, cc0 = c0 % CH;
+  float* o = out + (size_t)chunk * ks * ks * CH + cc0;
+  for (int it = tid; it < PREP_CH * ks * ks; it += blockDim.x) {
+    const int c = it % PREP_CH, j = it / PREP_CH;
+    const float* w = s_w + c * kk;
+    float v;
+    if (!transform) {
+      const int s = kmax / 2 - R;
+      v = w[(j / ks + s) * kmax + (j % ks + s)];
+    } else {
+      const float* cur = step75 ? (s_k5 + c * 25) : w;
+      const int kc = step75 ? 5 : kmax;
+      if (ks == kc) {
+        v = cur[j];
+      } else {  // ks == 3
+        const int s = kc / 2 - 1;
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) acc = fmaf(cur[(i / 3 + s) * kc + (i % 3 + s)], s_m53[j * 9 + i], acc);
+        v = acc;
+      }
+    }
+    o[(flip ? ks * ks - 1 - j : j) * CH + c] = v;   // flip: 180-degree rotation = the data-gradient filter
+  }
+}
+
 template <int KS, int TH, int TW>
 int launch_tile(const OfaTensor4* x, DwParams& p, cudaStream_t st) {
   using L = DwSmem<KS, TH, TW>;
@@ -188,7 +214,9 @@ int launch_tile(const OfaTensor4* x, DwParams& p, cudaStream_t st) {
   int rc = encode_tmap(&tm, p.f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x->ptr, dims,
                        strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
   if (rc) return rc;
-  OFA_CUDA(cudaFuncSetAttribute(dw_fast_kernel<KS, TH, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+  static unsigned char attr_done[64] = {0};   // one per template instance
+  if (once_per_device(attr_done))
+    OFA_CUDA(cudaFuncSetAttribute(dw_fast_kernel<KS, TH, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
   dim3 grid((unsigned)(p.N * p.tiles_w * p.tiles_h), p.C / CH);
   launch_pdl(dw_fast_kernel<KS, TH, TW>, dim3(grid), dim3(32 * TH), L::TOTAL, st, tm, p);
   return check_launch("dw_fast_kernel");
@@ -228,11 +256,22 @@ int launch_dw_fast(const OfaTensor4* x, const OfaTensor4* y, const float* w7, in
   }
   p.y = reinterpret_cast<uint16_t*>(y->ptr);
   p.f16 = x->dtype == OFA_F16 ? 1 : 0;
-  switch (ks) {
-    case 3: return launch_ks<3>(x, p, st);
-    case 5: return launch_ks<5>(x, p, st);
-    default: return launch_ks<7>(x, p, st);
+  // the active (transformed, for the data gradient rotated) filters of all channels, once per launch
+  float* filt = nullptr;
+  keep_async_pool_resident();
+  OFA_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&filt), (size_t)p.C * ks * ks * sizeof(float), st));
+  launch_pdl(dw_prep_filters_kernel, dim3(p.C / PREP_CH), dim3(256), 0, st, w7, kmax, m75, m53, transform_on, ks, flip, filt);
+  int rc = check_launch("dw_prep_filters_kernel");
+  p.filt = filt;
+  if (!rc) {
+    switch (ks) {
+      case 3: rc = launch_ks<3>(x, p, st); break;
+      case 5: rc = launch_ks<5>(x, p, st); break;
+      default: rc = launch_ks<7>(x, p, st); break;
+    }
   }
+  cudaFreeAsync(filt, st);
+  return rc;
 }
 
 }  // namespace ofa

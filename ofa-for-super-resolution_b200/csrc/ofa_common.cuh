@@ -48,6 +48,16 @@ __device__ __forceinline__ void pdl_wait() {
 
 bool pdl_enabled();   // api.cu: OFA_PDL != "0"
 
+// true the first time it is called with `done` on the current device: per-function launch attributes (dynamic
+// shared-memory size) are set once per device instead of before every launch (a driver call per launch)
+inline bool once_per_device(unsigned char (&done)[64]) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+  if (done[dev]) return false;
+  done[dev] = 1;
+  return true;
+}
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg;
