@@ -4,7 +4,7 @@
 //   * a CTA owns a TH x TW pixel tile of one 64-channel chunk; the (TH+ks-1) x (TW+ks-1) x 64 halo
 //     box arrives with ONE TMA load whose out-of-bounds zero fill is the conv's zero padding;
 //   * the active filters (7x7 weights through the learned 7->5 / 5->3 matrices, rotated for the data gradient)
-//     are derived ONCE per launch by dw_prep_filters_kernel; a CTA fetches its chunk's ks*ks x 64 floats with one bulk
+//     are derived ONCE per launch by active_filter_kernel (simt_kernels.cu, chunked layout); a CTA fetches its chunk's ks*ks x 64 floats with one bulk
 //     copy on the same mbarrier as the halo (round 1 re-derived them in every tile's CTA: dependent global loads that
 //     held 42 % of the kernel's stall samples and made ks = 3 cost as much as ks = 7);
 //   * lane = channel pair, so every shared-memory access of a warp is one conflict-free 128-byte
@@ -35,7 +35,7 @@ struct DwParams {
   const float* w7;
   const float* m75;
   const float* m53;
-  const float* filt;   // [C / 64][KS * KS][64] fp32 active filters (already rotated when flip), from dw_prep_filters_kernel
+  const float* filt;   // [C / 64][KS * KS][64] fp32 active filters (already rotated when flip), from launch_active_filter_chunked
   const float* gamma; const float* beta; const float* mean; const float* var; float eps;
   int act;
   uint16_t* y;
@@ -87,7 +87,7 @@ dw_fast_kernel(const __grid_constant__ CUtensorMap tmap_x, const DwParams p) {
     ptx::fence_barrier_init();
     ptx::mbar_arrive_expect_tx(bar, (uint32_t)(L::TILE_BYTES + L::FILT_BYTES));
     ptx::tma_load_4d(smem, &tmap_x, bar, c0, w0 - R, h0 - R, n);
-    // the chunk's active filters were derived once per launch (dw_prep_filters_kernel): one 12.5 KB bulk copy instead of
+    // the chunk's active filters were derived once per launch (active_filter_kernel): one 12.5 KB bulk copy instead of
     // every tile's CTA re-deriving them with dependent global loads (42 % of the warp-stall samples of the old kernel)
     ptx::bulk_load(filt, p.filt + (size_t)blockIdx.y * KS * KS * CH, (uint32_t)L::FILT_BYTES, bar);
   }
@@ -138,67 +138,6 @@ dw_fast_kernel(const __grid_constant__ CUtensorMap tmap_x, const DwParams p) {
         }
       }
     }
-  }
-}
-
-// Active filters of every channel, once per launch: out[chunk][tap][c % 64] (tap order rotated by 180 degrees when
-// flip: the data-gradient filter).  One block per PREP_CH channels: the weights and the two transform matrices are staged
-// in shared memory first (coalesced loads), then the 7 -> 5 step runs over (channel, output tap) pairs and the -> 3 step
-// over (channel, tap) -- same fmaf order as active_filter_channel (ofa_common.cuh), so the values are bit-identical to it.
-constexpr int PREP_CH = 16;
-
-__global__ void __launch_bounds__(256)
-dw_prep_filters_kernel(const float* __restrict__ w7, int kmax, const float* __restrict__ m75,
-                       const float* __restrict__ m53, int transform_on, int ks, int flip, float* __restrict__ out) {
-  pdl_wait();
-  __shared__ float s_w[PREP_CH * 49];
-  __shared__ float s_m75[625];
-  __shared__ float s_m53[81];
-  __shared__ float s_k5[PREP_CH * 25];
-  const int c0 = blockIdx.x * PREP_CH;
-  const int tid = threadIdx.x;
-  const int kk = kmax * kmax;
-  const bool transform = transform_on && ks < kmax;
-  const bool step75 = transform && kmax == 7 && m75 != nullptr;
-  for (int i = tid; i < PREP_CH * kk; i += blockDim.x) s_w[i] = w7[(size_t)c0 * kk + i];
-  if (step75) for (int i = tid; i < 625; i += blockDim.x) s_m75[i] = m75[i];
-  if (transform && ks == 3) for (int i = tid; i < 81; i += blockDim.x) s_m53[i] = m53[i];
-  __syncthreads();
-  if (step75) {
-    for (int it = tid; it < PREP_CH * 25; it += blockDim.x) {
-      const int c = it / 25, j = it - c * 25;
-      const float* w = s_w + c * 49;
-      float acc = 0.f;
-#pragma unroll
-      for (int i = 0; i < 25; ++i) acc = fmaf(w[(i / 5 + 1) * 7 + (i % 5 + 1)], s_m75[j * 25 + i], acc);
-      s_k5[c * 25 + j] = acc;
-    }
-    __syncthreads();
-  }
-  const int R = ks / 2;
-  const int chunk = c0 / CH, cc0 = c0 % CH;
-  float* o = out + (size_t)chunk * ks * ks * CH + cc0;
-  for (int it = tid; it < PREP_CH * ks * ks; it += blockDim.x) {
-    const int c = it % PREP_CH, j = it / PREP_CH;
-    const float* w = s_w + c * kk;
-    float v;
-    if (!transform) {
-      const int s = kmax / 2 - R;
-      v = w[(j / ks + s) * kmax + (j % ks + s)];
-    } else {
-      const float* cur = step75 ? (s_k5 + c * 25) : w;
-      const int kc = step75 ? 5 : kmax;
-      if (ks == kc) {
-        v = cur[j];
-      } else {  // ks == 3
-        const int s = kc / 2 - 1;
-        float acc = 0.f;
-#pragma unroll
-        for (int i = 0; i < 9; ++i) acc = fmaf(cur[(i / 3 + s) * kc + (i % 3 + s)], s_m53[j * 9 + i], acc);
-        v = acc;
-      }
-    }
-    o[(flip ? ks * ks - 1 - j : j) * CH + c] = v;   // flip: 180-degree rotation = the data-gradient filter
   }
 }
 
@@ -260,8 +199,7 @@ int launch_dw_fast(const OfaTensor4* x, const OfaTensor4* y, const float* w7, in
   float* filt = nullptr;
   keep_async_pool_resident();
   OFA_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&filt), (size_t)p.C * ks * ks * sizeof(float), st));
-  launch_pdl(dw_prep_filters_kernel, dim3(p.C / PREP_CH), dim3(256), 0, st, w7, kmax, m75, m53, transform_on, ks, flip, filt);
-  int rc = check_launch("dw_prep_filters_kernel");
+  int rc = launch_active_filter_chunked(w7, kmax, m75, m53, transform_on, ks, p.C, flip, filt, st);
   p.filt = filt;
   if (!rc) {
     switch (ks) {

@@ -7,6 +7,8 @@ namespace ofa {
 // ---- simt_kernels.cu ----------------------------------------------------------------------------
 int launch_active_filter(const float* w7, int kmax, const float* m75, const float* m53, int transform_on,
                          int ks, int C, float* out, cudaStream_t st);
+int launch_active_filter_chunked(const float* w7, int kmax, const float* m75, const float* m53, int transform_on,
+                                 int ks, int C, int flip, float* out, cudaStream_t st);   // [C / 64][ks * ks][64]
 int launch_dw_simt(const TV& x, const TV& y, const float* w7, int kmax, const float* m75,
                    const float* m53, int transform_on, int ks, int flip, const Epi& epi, cudaStream_t st);
 int launch_conv_simt(const TV& x, const TV& y, const float* w, long long w_so, long long w_si,

@@ -8,22 +8,89 @@
 namespace ofa {
 
 // =================================================================================================
-// (a1) active depthwise filter  — one thread per channel
+// (a1) active depthwise filter
 // =================================================================================================
-__global__ void active_filter_kernel(const float* __restrict__ w7, int kmax,
-                                     const float* __restrict__ m75, const float* __restrict__ m53,
-                                     int transform_on, int ks, int C, float* __restrict__ out) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float f[49], tmp[25];
-  active_filter_channel(w7 + (size_t)c * kmax * kmax, kmax, m75, m53, transform_on, ks, f, tmp);
-  for (int j = 0; j < ks * ks; ++j) out[(size_t)c * ks * ks + j] = f[j];
+// One block per AF_CH channels: the weights and the two transform matrices are staged in shared memory (coalesced
+// loads), then the 7 -> 5 step runs over (channel, output tap) pairs and the -> 3 step over (channel, tap) -- the same
+// fmaf order as active_filter_channel (ofa_common.cuh), so the values are bit-identical to the per-channel form the
+// other kernels use.  (Round 1 ran one THREAD per channel: 625 dependent FMAs, ~13 us per call.)
+//   chunked == 0: out[c][tap]                (ofa_dw_active_filter, the planar depthwise kernel)
+//   chunked == 1: out[c / 64][tap'][c % 64]  with tap' = ks*ks - 1 - tap when flip (the data-gradient filter): the
+//                 layout dw_fast_kernel fetches with one bulk copy per 64-channel chunk
+constexpr int AF_CH = 16;
+
+__global__ void __launch_bounds__(256)
+active_filter_kernel(const float* __restrict__ w7, int kmax, const float* __restrict__ m75,
+                     const float* __restrict__ m53, int transform_on, int ks, int C, int chunked, int flip,
+                     float* __restrict__ out) {
+  pdl_wait();
+  __shared__ float s_w[AF_CH * 49];
+  __shared__ float s_m75[625];
+  __shared__ float s_m53[81];
+  __shared__ float s_k5[AF_CH * 25];
+  const int c0 = blockIdx.x * AF_CH;
+  const int nch = min(AF_CH, C - c0);
+  const int tid = threadIdx.x;
+  const int kk = kmax * kmax, T = ks * ks;
+  const bool transform = transform_on && ks < kmax;
+  const bool step75 = transform && kmax == 7 && m75 != nullptr;
+  for (int i = tid; i < nch * kk; i += blockDim.x) s_w[i] = w7[(size_t)c0 * kk + i];
+  if (step75) for (int i = tid; i < 625; i += blockDim.x) s_m75[i] = m75[i];
+  if (transform && ks == 3) for (int i = tid; i < 81; i += blockDim.x) s_m53[i] = m53[i];
+  __syncthreads();
+  if (step75) {
+    for (int it = tid; it < nch * 25; it += blockDim.x) {
+      const int c = it / 25, j = it - c * 25;
+      const float* w = s_w + c * 49;
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < 25; ++i) acc = fmaf(w[(i / 5 + 1) * 7 + (i % 5 + 1)], s_m75[j * 25 + i], acc);
+      s_k5[c * 25 + j] = acc;
+    }
+    __syncthreads();
+  }
+  const int R = ks / 2;
+  for (int it = tid; it < AF_CH * T; it += blockDim.x) {
+    const int c = it % AF_CH, j = it / AF_CH;
+    if (c >= nch) continue;
+    const float* w = s_w + c * kk;
+    float v;
+    if (!transform) {
+      const int s = kmax / 2 - R;
+      v = w[(j / ks + s) * kmax + (j % ks + s)];
+    } else {
+      const float* cur = step75 ? (s_k5 + c * 25) : w;
+      const int kc = step75 ? 5 : kmax;
+      if (ks == kc) {
+        v = cur[j];
+      } else {  // ks == 3
+        const int s = kc / 2 - 1;
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) acc = fmaf(cur[(i / 3 + s) * kc + (i % 3 + s)], s_m53[j * 9 + i], acc);
+        v = acc;
+      }
+    }
+    const int cg = c0 + c;
+    if (chunked) out[((size_t)(cg >> 6) * T + (flip ? T - 1 - j : j)) * 64 + (cg & 63)] = v;
+    else out[(size_t)cg * T + j] = v;
+  }
 }
 
 int launch_active_filter(const float* w7, int kmax, const float* m75, const float* m53,
                          int transform_on, int ks, int C, float* out, cudaStream_t st) {
   if (C == 0) return OFA_OK;
-  active_filter_kernel<<<(C + 63) / 64, 64, 0, st>>>(w7, kmax, m75, m53, transform_on, ks, C, out);
+  launch_pdl(active_filter_kernel, dim3((C + AF_CH - 1) / AF_CH), dim3(256), 0, st, w7, kmax, m75, m53, transform_on, ks, C, 0, 0,
+             out);
+  return check_launch("active_filter_kernel");
+}
+
+// C % 64 == 0: [C / 64][ks * ks][64], rotated by 180 degrees when flip
+int launch_active_filter_chunked(const float* w7, int kmax, const float* m75, const float* m53, int transform_on, int ks,
+                                 int C, int flip, float* out, cudaStream_t st) {
+  if (C == 0) return OFA_OK;
+  launch_pdl(active_filter_kernel, dim3((C + AF_CH - 1) / AF_CH), dim3(256), 0, st, w7, kmax, m75, m53, transform_on, ks, C, 1,
+             flip, out);
   return check_launch("active_filter_kernel");
 }
 
