@@ -193,6 +193,7 @@ int ofa_conv_fwd(const OfaConvArgs* a, int32_t impl, void* stream) {
     return launch_conv_simt(make_tv(&a->x), make_tv(&a->y), a->w, a->w_so, a->w_si, a->w_sh, a->w_sw, a->cin,
                             a->cout, a->ks, a->flip, a->store, make_epi(&a->epi), st);
   }
+  if (impl != OFA_IMPL_SIMT && conv_stem_tc_supported(a)) return launch_conv_stem_tc(a, st);
   if (impl != OFA_IMPL_SIMT && conv_stem_supported(a)) return launch_conv_stem(a, st);
   bool tc_ok = conv_tc_supported(a);
   if (impl == OFA_IMPL_FAST && !tc_ok)

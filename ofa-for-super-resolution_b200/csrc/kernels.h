@@ -57,6 +57,9 @@ int launch_conv_tc(const OfaConvArgs* a, cudaStream_t st);
 bool conv_out_rows_supported(const OfaConvArgs* a);
 int launch_conv_out_rows(const OfaConvArgs* a, cudaStream_t st);
 bool conv_stem_supported(const OfaConvArgs* a);
+// conv_stem_tc.cu : the same stems as an im2col GEMM on tcgen05 (NHWC 16-bit output, 64 channels)
+bool conv_stem_tc_supported(const OfaConvArgs* a);
+int launch_conv_stem_tc(const OfaConvArgs* a, cudaStream_t st);
 int launch_conv_stem(const OfaConvArgs* a, cudaStream_t st);
 
 // ---- wgrad_tc.cu : dense-conv weight gradient on tcgen05 (pixels are K; both operands MN-major) ---------

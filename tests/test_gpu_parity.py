@@ -305,7 +305,8 @@ def test_conv_out_rows(dev, ks, cout, dtype):
 @pytest.mark.parametrize('ks,cin', [(5, 3), (3, 3), (3, 1)])
 @pytest.mark.parametrize('out', [torch.float16, torch.bfloat16, torch.float32])
 def test_conv_stem(dev, ks, cin, out):
-    """a9, the stem (3 -> 64 on the user's fp32 NCHW image): exact fp32 arithmetic, 16-bit NHWC output."""
+    """a9, the stem (3 -> 64 on the user's fp32 NCHW image).  16-bit NHWC output: the im2col tcgen05 kernel (operands
+    rounded to the output format, fp32 accumulation); fp32 output: the exact CUDA-core kernel."""
     from ofa_b200 import functional as OF, backend as B
     import ofa_b200
     ofa_b200.set_impl(B.IMPL_AUTO)
