@@ -371,6 +371,10 @@ typedef struct OfaMBConvTrainGrads {
   float* dbeta[3];
 } OfaMBConvTrainGrads;
 
+/* The three weight-gradient computations of a block do not feed its data-gradient chain: with mode 1 ofa_mbconv_train_bwd
+ * runs them on a second, lower-priority stream beside it (fork / join inside the call, so the caller's stream semantics
+ * are unchanged).  mode 0 (library default): everything on the caller's stream.  Returns the previous mode. */
+int ofa_train_side_mode(int32_t mode);
 int64_t ofa_mbconv_train_workspace_bytes(int32_t n, int32_t h, int32_t w, int32_t cin, int32_t mid, int32_t cout);
 int ofa_mbconv_train_fwd(const OfaMBConvTrainArgs* a, void* stream);
 int ofa_mbconv_train_bwd(const OfaMBConvTrainArgs* a, const void* dy, void* dx, const OfaMBConvTrainGrads* g,

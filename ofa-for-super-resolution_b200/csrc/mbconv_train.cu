@@ -15,6 +15,7 @@
 #include "ofa_common.cuh"
 #include "kernels.h"
 
+#include <stdlib.h>
 #include <string.h>
 
 namespace ofa {
@@ -123,12 +124,54 @@ int bn_bwd(const OfaTensor4& z, const OfaTensor4& dy, const OfaTensor4& dz, cons
                              dgamma, st);
 }
 
+
+// Side stream of the backward: the three weight-gradient computations of a block (project wgrad, depthwise filter
+// gradient + transform chain, expand wgrad) do not feed the block's data-gradient chain, so they run on a second,
+// lower-priority stream beside it: fork after the BatchNorm backward that produces their dZ, join before the call
+// returns (ofa_train_side_mode(1)).  At batch 64 x 24 x 24 every kernel is one latency-bound wave, so the two chains fill
+// each other's gaps: max-sub-network step 8.48 -> 8.18 ms.  A deferred join (the main stream never waiting inside the
+// backward pass, scratch released on the side stream) was measured and dropped: freeing on another stream than the one
+// that allocates defeats the stream-ordered pool's reuse (12-100 ms steps).
+struct SideCtx {
+  cudaStream_t s;
+  cudaEvent_t fork[3], join;
+  bool ok;
+};
+
+SideCtx g_side[64];
+unsigned char g_side_init[64] = {0};
+int g_side_mode = 0;
+
+SideCtx* side_ctx() {
+  if (!g_side_mode) return nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!g_side_init[dev]) {
+    g_side_init[dev] = 1;
+    SideCtx& c = g_side[dev];
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    c.ok = cudaStreamCreateWithPriority(&c.s, cudaStreamNonBlocking, lo) == cudaSuccess;
+    for (int i = 0; i < 3 && c.ok; ++i) c.ok = cudaEventCreateWithFlags(&c.fork[i], cudaEventDisableTiming) == cudaSuccess;
+    if (c.ok) c.ok = cudaEventCreateWithFlags(&c.join, cudaEventDisableTiming) == cudaSuccess;
+    if (!c.ok) cudaGetLastError();
+  }
+  return g_side[dev].ok ? &g_side[dev] : nullptr;
+}
+
 }  // namespace
 }  // namespace ofa
 
 using namespace ofa;
 
 extern "C" {
+
+int ofa_train_side_mode(int32_t mode) {
+  OFA_REQUIRE(mode == 0 || mode == 1, "ofa_train_side_mode: mode must be 0 or 1");
+  const int old = g_side_mode;
+  g_side_mode = mode;
+  return old;
+}
 
 int64_t ofa_mbconv_train_workspace_bytes(int32_t n, int32_t h, int32_t w, int32_t cin, int32_t mid, int32_t cout) {
   (void)cin;
@@ -219,41 +262,59 @@ int ofa_mbconv_train_bwd(const OfaMBConvTrainArgs* a, const void* dy_ptr, void* 
   const OfaTensor4 dy = nhwc16(dy_ptr, a->dtype, a->n, a->cout, a->h, a->w);
   const OfaTensor4 dx = nhwc16(dx_ptr, a->dtype, a->n, a->cin, a->h, a->w);
 
-  // stream-ordered scratch: dz3, two mid-wide gradient buffers (the BatchNorm apply overwrites its input gradient in
-  // place is NOT assumed: reduce + apply read one and write the other), the active-filter gradient
+  // stream-ordered scratch: dz3, four mid-wide gradient buffers (d(a2), d(z2), d(a1), d(z1): kept apart so the side
+  // stream can still read a dZ while the main chain has moved on), the active-filter gradient
   const int64_t midb = align256(L.P * a->mid * 2), outb = align256(L.P * a->cout * 2);
   const int64_t dwab = align256((int64_t)sizeof(float) * a->mid * a->ks * a->ks);
   char* scratch = nullptr;
   keep_async_pool_resident();
-  OFA_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&scratch), (size_t)(outb + 2 * midb + dwab), st));
+  OFA_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&scratch), (size_t)(outb + 4 * midb + dwab), st));
   const OfaTensor4 dz3 = nhwc16(scratch, a->dtype, a->n, a->cout, a->h, a->w);
-  const OfaTensor4 gA = nhwc16(scratch + outb, a->dtype, a->n, a->mid, a->h, a->w);
-  const OfaTensor4 gB = nhwc16(scratch + outb + midb, a->dtype, a->n, a->mid, a->h, a->w);
-  float* dwa = reinterpret_cast<float*>(scratch + outb + 2 * midb);
+  const OfaTensor4 da2 = nhwc16(scratch + outb, a->dtype, a->n, a->mid, a->h, a->w);
+  const OfaTensor4 dz2 = nhwc16(scratch + outb + midb, a->dtype, a->n, a->mid, a->h, a->w);
+  const OfaTensor4 da1 = nhwc16(scratch + outb + 2 * midb, a->dtype, a->n, a->mid, a->h, a->w);
+  const OfaTensor4 dz1 = nhwc16(scratch + outb + 3 * midb, a->dtype, a->n, a->mid, a->h, a->w);
+  float* dwa = reinterpret_cast<float*>(scratch + outb + 4 * midb);
   const void* wproj_t = ws + L.wproj_t;
   const void* wexp_t = ws + L.wexp_t;
+  SideCtx* side = side_ctx();
+  cudaStream_t ss = side ? side->s : st;     // where the weight gradients run
+  int forked = 0;
+  auto fork = [&](int i) {                    // side stream continues from this point of the main stream
+    if (!side) return;
+    cudaEventRecord(side->fork[i], st);
+    cudaStreamWaitEvent(side->s, side->fork[i], 0);
+    forked = 1;
+  };
 
   do {
     // BN3 (no activation; the residual branch passes dy through unchanged)
     if ((rc = bn_bwd(z3, dy, dz3, a->bn_proj, mean3, var3, OFA_ACT_NONE, g->dbeta[2], g->dgamma[2], st))) break;
-    // project 1x1: data gradient = conv of dz3 with W_proj^T (cout -> mid), weight gradient on tcgen05
-    if ((rc = pointwise_tc(dz3, gA, wproj_t, a->cout, a->mid, nullptr, st))) break;                    // gA = d(a2)
+    // project 1x1: weight gradient on tcgen05 (side), data gradient = conv of dz3 with W_proj^T (cout -> mid)
     if (!wgrad_tc_supported(&a2, &dz3, a->mid, a->cout, 1)) { rc = fail(OFA_ERR_UNSUPPORTED, "mbconv training block: project weight gradient"); break; }
-    if ((rc = launch_wgrad_tc(&a2, &dz3, g->dw_proj, a->w_proj_so, a->w_proj_si, 0, 0, a->mid, a->cout, 1, st))) break;
+    fork(0);
+    if ((rc = launch_wgrad_tc(&a2, &dz3, g->dw_proj, a->w_proj_so, a->w_proj_si, 0, 0, a->mid, a->cout, 1, ss))) break;
+    if ((rc = pointwise_tc(dz3, da2, wproj_t, a->cout, a->mid, nullptr, st))) break;
     // BN2 + act
-    if ((rc = bn_bwd(z2, gA, gB, a->bn_dw, mean2, var2, a->act, g->dbeta[1], g->dgamma[1], st))) break;  // gB = d(z2)
-    // depthwise: data gradient (rotated filter), filter gradient + chain rule through the 7->5->3 transforms
-    if ((rc = launch_dw_fast(&gB, &gA, a->w_dw, a->kmax, a->m75, a->m53, a->transform_on, a->ks, 1, nullptr, st))) break;  // gA = d(a1)
-    if ((rc = launch_dw_bwd_filter(make_tv(&a1), make_tv(&gB), a->ks, dwa, st))) break;
+    if ((rc = bn_bwd(z2, da2, dz2, a->bn_dw, mean2, var2, a->act, g->dbeta[1], g->dgamma[1], st))) break;
+    // depthwise: filter gradient + chain rule through the 7->5->3 transforms (side), data gradient (rotated filter)
+    fork(1);
+    if ((rc = launch_dw_bwd_filter(make_tv(&a1), make_tv(&dz2), a->ks, dwa, ss))) break;
     if ((rc = launch_active_filter_bwd(a->w_dw, a->kmax, a->m75, a->m53, a->transform_on, a->ks, a->mid, dwa, g->dw_dw,
-                                       g->dm75, g->dm53, st))) break;
+                                       g->dm75, g->dm53, ss))) break;
+    if ((rc = launch_dw_fast(&dz2, &da1, a->w_dw, a->kmax, a->m75, a->m53, a->transform_on, a->ks, 1, nullptr, st))) break;
     // BN1 + act
-    if ((rc = bn_bwd(z1, gA, gB, a->bn_exp, mean1, var1, a->act, g->dbeta[0], g->dgamma[0], st))) break;  // gB = d(z1)
-    // expand 1x1: dx = conv(dz1, W_exp^T) [+ dy: the identity branch], weight gradient
-    if ((rc = pointwise_tc(gB, dx, wexp_t, a->mid, a->cin, a->add_residual ? &dy : nullptr, st))) break;
-    if (!wgrad_tc_supported(&x, &gB, a->cin, a->mid, 1)) { rc = fail(OFA_ERR_UNSUPPORTED, "mbconv training block: expand weight gradient"); break; }
-    rc = launch_wgrad_tc(&x, &gB, g->dw_exp, a->w_exp_so, a->w_exp_si, 0, 0, a->cin, a->mid, 1, st);
+    if ((rc = bn_bwd(z1, da1, dz1, a->bn_exp, mean1, var1, a->act, g->dbeta[0], g->dgamma[0], st))) break;
+    // expand 1x1: weight gradient (side), dx = conv(dz1, W_exp^T) [+ dy: the identity branch]
+    if (!wgrad_tc_supported(&x, &dz1, a->cin, a->mid, 1)) { rc = fail(OFA_ERR_UNSUPPORTED, "mbconv training block: expand weight gradient"); break; }
+    fork(2);
+    if ((rc = launch_wgrad_tc(&x, &dz1, g->dw_exp, a->w_exp_so, a->w_exp_si, 0, 0, a->cin, a->mid, 1, ss))) break;
+    rc = pointwise_tc(dz1, dx, wexp_t, a->mid, a->cin, a->add_residual ? &dy : nullptr, st);
   } while (0);
+  if (forked) {                               // join: everything the side stream was given is ordered before what follows
+    cudaEventRecord(side->join, side->s);
+    cudaStreamWaitEvent(st, side->join, 0);
+  }
   cudaFreeAsync(scratch, st);
   return rc;
 }

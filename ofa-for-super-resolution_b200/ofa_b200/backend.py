@@ -123,6 +123,7 @@ SYMBOLS = {
                                     c_void_p, c_void_p, c_int32, c_int32, c_int32, POINTER(OfaBn), c_int32, c_void_p]),
     'ofa_project_planar_fwd': (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                          c_int32, POINTER(OfaBn), c_void_p]),
+    'ofa_train_side_mode': (c_int32, [c_int32]),
     'ofa_mbconv_train_workspace_bytes': (c_int64, [c_int32] * 6),
     'ofa_mbconv_train_fwd': (c_int32, [POINTER(OfaMBConvTrainArgs), c_void_p]),
     'ofa_mbconv_train_bwd': (c_int32, [POINTER(OfaMBConvTrainArgs), c_void_p, c_void_p, POINTER(OfaMBConvTrainGrads),

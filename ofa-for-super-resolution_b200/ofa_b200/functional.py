@@ -18,7 +18,8 @@ import torch
 from . import backend as B
 
 _state = {'compute_dtype': torch.float16, 'impl': B.IMPL_AUTO, 'mid_dtype': B.OFA_F16, 'train_dtype': torch.float32,
-          'overflow': 'none', 'block_train': os.environ.get('OFA_BLOCK_TRAIN', '1') != '0'}
+          'overflow': 'none', 'block_train': os.environ.get('OFA_BLOCK_TRAIN', '1') != '0',
+          'train_side': 0 if os.environ.get('OFA_TRAIN_SIDE', '1') == '0' else 1}
 
 
 def check_finite(t):
@@ -66,6 +67,21 @@ def get_train_dtype():
 
 def get_compute_dtype():
     return _state['compute_dtype']
+
+
+def set_train_side_stream(on):
+    """Weight gradients of the training MBConv blocks on a second, lower-priority CUDA stream beside the data-gradient chain
+    (ofa_train_side_mode; fork / join inside every block call).  Default on; OFA_TRAIN_SIDE=0 or False here disables."""
+    _state['train_side'] = 1 if on else 0
+    if B._lib is not None:
+        _side_mode_sync()
+
+
+def _side_mode_sync():
+    """Push the Python-side mode into the library (once the library is loaded)."""
+    if _state.get('train_side_pushed') != _state['train_side']:
+        B.lib().ofa_train_side_mode(_state['train_side'])
+        _state['train_side_pushed'] = _state['train_side']
 
 
 def set_block_train(on):
@@ -651,6 +667,7 @@ class MBConvTrainFn(torch.autograd.Function):
         mid, cout, ks, transform_on, act, add_residual, bns = cfg
         n, cin, h, w = x.shape
         L = B.lib()
+        _side_mode_sync()
         nbytes = L.ofa_mbconv_train_workspace_bytes(n, h, w, cin, mid, cout)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
         y = B.new_nhwc(n, cout, h, w, x.dtype, x.device)
