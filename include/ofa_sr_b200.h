@@ -249,8 +249,8 @@ int64_t ofa_mbconv_workspace_bytes(int32_t n, int32_t h, int32_t w, int32_t cin,
  * (dynamic_layers.py:70-84: the reference materialises both, at full size).  OFA_IMPL_BAND forces it on any supported
  * shape, OFA_IMPL_PLANAR3 forces the three stand-alone kernels.
  * impl: OFA_IMPL_AUTO runs the planar tcgen05 path (expand -> Toeplitz depthwise -> project on channel-planar 16-bit
- * intermediates) when cin = cout = 64, mid % 64 == 0, W % 8 == 0 AND the planes are frame-sized (H * W >= 8192 pixels
- * filling >= 25 % of the 128 (64) x 112-pixel depthwise tiles): the depthwise rebuilds its filter matrices per channel
+ * intermediates) when cin = cout = 64, mid % 64 == 0, W % 8 == 0 AND the planes have H * W >= 2304 pixels (48 x 48)
+ * filling >= 25 % of the 128 (64) x 112-pixel depthwise tiles: the depthwise rebuilds its filter matrices per channel
  * plane, so batches of small patches run faster on the three NHWC kernels, which AUTO picks otherwise.
  * OFA_IMPL_FAST forces the planar path whenever it is supported, OFA_IMPL_NHWC the NHWC kernels, OFA_IMPL_SIMT the
  * exact CUDA-core kernels. */

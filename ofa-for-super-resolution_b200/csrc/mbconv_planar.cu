@@ -663,16 +663,18 @@ bool mbconv_planar_supported(const OfaMBConvArgs* a) {
 // OFA_IMPL_AUTO's choice between the planar path and the three NHWC kernels (OFA_IMPL_FAST forces planar).  The planar
 // depthwise works per channel PLANE: its Toeplitz filter matrices are rebuilt for every plane (~6 us, hidden behind the
 // previous plane's tiles only when a plane has several tiles) and its tiles are 128 (64 for a short tail) x 112
-// pixels.  Batches of small images therefore run far below the frame rates: 64 x 384 planes of 48 x 48 took 1.07 ms per
-// block against ~0.25 ms on the NHWC kernels, 24 x 24 planes likewise.  Rule: planes of at least 8192 pixels that fill
-// at least a quarter of their tiles.
+// pixels.  Batches of small images therefore run below the frame rates.  Round 1: 64 x 384 planes of 48 x 48 took
+// 1.07 ms per block against ~0.25 ms on the NHWC kernels (rule: >= 8192 pixels).  Round 2 (filters precomputed per
+// launch, whole-warp Toeplitz build): 0.33 ms per block at 48 x 48, and the X4 teacher forward on 64 x 48 x 48 planes is
+// 7.28 ms planar against 7.55 ms NHWC (tools/bench_teacher_x4.py), while 24 x 24 planes (8 % tile fill) are 2.3x slower
+// planar.  Rule: planes of at least 2304 pixels (48 x 48) that fill at least a quarter of their tiles.
 bool mbconv_planar_preferred(const OfaMBConvArgs* a) {
   const OfaTensor4& x = a->x;
   const int tail = x.h % DW_TH;
   const long long rows = (long long)(x.h / DW_TH) * DW_TH + (tail == 0 ? 0 : tail <= DW_TH / 2 ? DW_TH / 2 : DW_TH);
   const long long cols = (long long)((x.w + DW_TW - 1) / DW_TW) * DW_TW;
   const long long area = (long long)x.h * x.w;
-  return area >= 8192 && 4 * area >= rows * cols;
+  return area >= 2304 && 4 * area >= rows * cols;
 }
 
 static CUtensorMapDataType dt16(int f16) {

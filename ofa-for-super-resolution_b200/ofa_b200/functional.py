@@ -1229,13 +1229,13 @@ def planar_supported(x, cin, mid, cout):
 
 def planar_preferred(x):
     """IMPL_AUTO's choice (mirrors mbconv_planar_preferred): the planar depthwise rebuilds its filter matrices per channel
-    plane and works in 128 (64) x 112-pixel tiles, so planes under 8192 pixels or filling < 25 % of their tiles -- batches
+    plane and works in 128 (64) x 112-pixel tiles, so planes under 2304 pixels (48 x 48) or filling < 25 % of their tiles -- batches
     of small patches -- take the three NHWC kernels; IMPL_FAST forces the planar path."""
     h, w = x.shape[2], x.shape[3]
     tail = h % 128
     rows = h // 128 * 128 + (0 if tail == 0 else 64 if tail <= 64 else 128)
     cols = (w + 111) // 112 * 112
-    return h * w >= 8192 and 4 * h * w >= rows * cols
+    return h * w >= 2304 and 4 * h * w >= rows * cols
 
 
 def band_preferred(x):

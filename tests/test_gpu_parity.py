@@ -463,7 +463,7 @@ def test_mbconv_planar_equals_nhwc_path(dev, dtype):
             assert y_planar.dtype == dtype and relerr(y_planar, y_nhwc) < (2 ** -6 if dtype == torch.bfloat16 else 2 ** -8)
     from ofa_b200 import functional as OF
     mk = lambda h, w: torch.empty(1, 64, h, w, dtype=dtype, device=dev).contiguous(memory_format=torch.channels_last)
-    assert not OF.planar_preferred(mk(24, 24)) and not OF.planar_preferred(mk(48, 48)) and not OF.planar_preferred(mk(8, 2048))
+    assert not OF.planar_preferred(mk(24, 24)) and OF.planar_preferred(mk(48, 48)) and not OF.planar_preferred(mk(8, 2048))
     assert OF.planar_preferred(mk(96, 96)) and OF.planar_preferred(mk(256, 256)) and OF.planar_preferred(mk(540, 960))
 
 

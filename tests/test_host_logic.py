@@ -178,13 +178,13 @@ def test_product_never_imports_oracle():
 
 def test_planar_dispatch_rule():
     """IMPL_AUTO's frame / patch rule (functional.planar_preferred, mirrored by mbconv_planar_preferred in the library):
-    planes of >= 8192 pixels that fill >= 25 % of their 128 (64-row tail) x 112 depthwise tiles take the planar
+    planes of >= 2304 pixels (48 x 48) that fill >= 25 % of their 128 (64-row tail) x 112 depthwise tiles take the planar
     tensor-core path; batches of small patches take the NHWC kernels."""
     from ofa_b200 import functional as OF
     mk = lambda h, w: torch.empty(1, 64, h, w, dtype=torch.float16)
-    for h, w, want in [(24, 24, False), (48, 48, False), (40, 56, False), (8, 2048, False), (64, 128, True),
+    for h, w, want in [(24, 24, False), (48, 48, True), (40, 56, False), (32, 64, False), (8, 2048, False), (64, 128, True), (64, 64, True),
                        (96, 96, True), (96, 120, True), (256, 256, True), (540, 960, True), (1080, 1920, True),
-                       (129, 56, False), (129, 64, True), (130, 232, True)]:
+                       (129, 56, True), (129, 24, False), (129, 64, True), (130, 232, True)]:
         assert OF.planar_preferred(mk(h, w)) is want, (h, w)
     assert OF.planar_supported(mk(24, 24), 64, 384, 64) and not OF.planar_supported(mk(24, 25), 64, 384, 64)
     assert not OF.planar_supported(mk(24, 24).float(), 64, 384, 64) and not OF.planar_supported(mk(24, 24), 64, 400, 64)
