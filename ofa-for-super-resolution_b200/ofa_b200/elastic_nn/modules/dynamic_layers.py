@@ -262,9 +262,13 @@ class DynamicConvLayer(MyModule):
         self.conv.active_out_channel = self.active_out_channel
         cin, cout = x.size(1), self.active_out_channel
         bn = self.bn.bn if self.use_bn else None
-        if OF.inference_mode_active(self):
-            return OF.conv_bn_act_infer(x, self.conv.conv.weight, cin, cout, self.kernel_size, bn, self._act_code,
-                                        cache=self.conv._packed)
+        if OF.inference_mode_active(self) and self.dilation == 1:
+            s = self.stride
+            if s != 1 and self.kernel_size == 1:
+                x, s = x[:, :, ::s, ::s], 1
+            y = OF.conv_bn_act_infer(x, self.conv.conv.weight, cin, cout, self.kernel_size, bn, self._act_code,
+                                     cache=self.conv._packed)
+            return y if s == 1 else y[:, :, ::s, ::s]     # BN and the activation are pointwise: subsample afterwards
         y = self.conv(x)
         if bn is not None:
             return DynamicBatchNorm2d.bn_forward(y, bn, cout, self._act_code)

@@ -99,11 +99,18 @@ class DynamicPointConv2d(nn.Module):
     def forward(self, x, out_channel=None):
         if out_channel is None:
             out_channel = self.active_out_channel
-        if self.stride != 1 or self.dilation != 1:
-            raise NotImplementedError('the B200 conv kernels cover stride 1 / dilation 1 (all SR nets)')
+        if self.dilation != 1 and self.kernel_size != 1:
+            raise NotImplementedError('the B200 conv kernels cover dilation 1 (every net of the reference uses 1)')
         in_channel = x.size(1)
         get_same_padding(self.kernel_size)
-        return OF.conv2d(x, self.conv.weight, in_channel, out_channel, self.kernel_size)
+        s = self.stride
+        if s != 1 and self.kernel_size == 1:
+            x = x[:, :, ::s, ::s]                 # 1x1, padding 0: a strided conv reads every s-th pixel
+            s = 1
+        y = OF.conv2d(x, self.conv.weight, in_channel, out_channel, self.kernel_size)
+        # k x k with "same" padding k // 2 (dynamic_op.py:110-111): the strided output is the stride-1 output at every
+        # s-th position (the MobileNetV3-style first conv, ofa_mbv3.py:41-43; not on the SR nets' path)
+        return y if s == 1 else y[:, :, ::s, ::s]
 
 
 class DynamicLinear(nn.Module):

@@ -177,3 +177,58 @@ def test_gpu_reorganize_middle_weights_with_se_keeps_function(dev, g):
         m.re_organize_middle_weights()
         after = m(x)
     assert relerr(after, before) < 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('ks,stride', [(3, 2), (1, 2), (5, 3)])
+def test_strided_dynamic_conv_layer_vs_torch(ks, stride):
+    """DynamicPointConv2d / DynamicConvLayer with stride > 1 (dynamic_op.py:104-112 passes the stride to F.conv2d with
+    same padding k // 2; ofa_mbv3.py:41-43 builds a stride-2 first conv): forward in eval and train mode and every
+    gradient against plain torch fp32 on the CPU."""
+    import numpy as np
+    import torch
+    import torch.nn.functional as F
+    from ofa_b200.elastic_nn.modules import DynamicConvLayer
+    dev = torch.device('cuda:0')
+    rs = np.random.RandomState(7 * ks + stride)
+    layer = DynamicConvLayer([3, 16], [24, 40], kernel_size=ks, stride=stride, act_func='relu6')
+    with torch.no_grad():
+        for p_ in layer.parameters():
+            p_.copy_(torch.from_numpy(rs.randn(*p_.shape).astype(np.float32) * 0.3))
+        layer.bn.bn.running_mean.copy_(torch.from_numpy(rs.randn(40).astype(np.float32) * 0.1))
+        layer.bn.bn.running_var.copy_(torch.from_numpy(rs.uniform(0.5, 1.5, 40).astype(np.float32)))
+    w = layer.conv.conv.weight.detach().clone()
+    g, b = layer.bn.bn.weight.detach().clone(), layer.bn.bn.bias.detach().clone()
+    rm, rv = layer.bn.bn.running_mean.clone(), layer.bn.bn.running_var.clone()
+    layer = layer.to(dev)
+    layer.active_out_channel = 24
+    x = torch.from_numpy(rs.randn(2, 16, 21, 30).astype(np.float32))
+
+    def ref(xin, training):
+        y = F.conv2d(xin, w[:24, :16], None, stride, ks // 2)
+        y = F.batch_norm(y, None if training else rm[:24], None if training else rv[:24], g[:24], b[:24], training, 0.1, 1e-5)
+        return torch.clamp(y, 0, 6)
+    import ofa_b200
+    layer.eval()
+    ofa_b200.set_compute_dtype(torch.float32)          # the exact kernels (the 16-bit inference path rounds to fp16)
+    try:
+        with torch.no_grad():
+            y = layer(x.to(dev))
+    finally:
+        ofa_b200.set_compute_dtype(torch.float16)
+    r = ref(x, False)
+    assert y.shape == r.shape and float((y.float().cpu() - r).abs().max()) < 1e-4 * max(1.0, float(r.abs().max()))
+    layer.train()
+    xd = x.to(dev).requires_grad_(True)
+    y = layer(xd)
+    dy = torch.from_numpy(rs.randn(*y.shape).astype(np.float32))
+    y.backward(dy.to(dev))
+    xr = x.clone().requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    yr = torch.clamp(F.batch_norm(F.conv2d(xr, wr[:24, :16], None, stride, ks // 2), None, None, g[:24], b[:24], True, 0.1, 1e-5), 0, 6)
+    yr.backward(dy)
+    assert float((y.detach().cpu() - yr.detach()).abs().max()) < 1e-3
+    assert float((xd.grad.cpu() - xr.grad).abs().max()) < 1e-3 * max(1.0, float(xr.grad.abs().max()))
+    gw = layer.conv.conv.weight.grad.cpu()
+    assert float((gw - wr.grad).abs().max()) < 1e-3 * max(1.0, float(wr.grad.abs().max()))
+    assert float(gw[24:].abs().max()) == 0.0                      # inactive output channels: no gradient
