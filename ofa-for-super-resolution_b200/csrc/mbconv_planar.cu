@@ -748,14 +748,18 @@ int launch_dw_planar(const void* x, void* y, int N, int C, int H, int W, const f
   p.NC = N * C; p.C = C; p.H = H; p.W = W; p.ks = ks; p.kmax = kmax; p.transform_on = transform_on; p.f16 = f16;
   p.act = act;
   // the transformed filters (centre crop + learned 7->5->3 matrices, dynamic_op.py:46-71) once per launch
+  // ... unless the active kernel size IS the stored one: then the [C][ks * ks] active filter is the parameter itself
+  // (the max sub-network of the headline frame: one 5 us launch per block less)
   float* filt = nullptr;
-  keep_async_pool_resident();
-  OFA_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&filt), (size_t)C * ks * ks * sizeof(float), st));
-  {
+  if (ks == kmax) {
+    p.filt = w7;
+  } else {
+    keep_async_pool_resident();
+    OFA_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&filt), (size_t)C * ks * ks * sizeof(float), st));
     const int rc0 = launch_active_filter(w7, kmax, m75, m53, transform_on, ks, C, filt, st);
     if (rc0) { cudaFreeAsync(filt, st); return rc0; }
+    p.filt = filt;
   }
-  p.filt = filt;
   if (bn) { p.gamma = bn->gamma; p.beta = bn->beta; p.mean = bn->mean; p.var = bn->var; p.eps = bn->eps; }
   p.tiles_x = (W + DW_TW - 1) / DW_TW;
   p.tiles_y = (H + DW_TH - 1) / DW_TH;
@@ -803,7 +807,7 @@ int launch_dw_planar(const void* x, void* y, int N, int C, int H, int W, const f
 #undef OFA_DW_LAUNCH_KS
 #undef OFA_DW_LAUNCH
   const int rc_launch = check_launch("dw_planar_kernel");
-  cudaFreeAsync(filt, st);
+  if (filt) cudaFreeAsync(filt, st);
   return rc_launch;
 }
 
