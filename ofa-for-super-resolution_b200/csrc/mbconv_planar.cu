@@ -97,6 +97,10 @@ expand_planar_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
 
   if (warp == 0) {
     if (lane == 0) {
+      // Programmatic dependent launch: everything above (barriers, TMEM, tensor-map fetches) ran while the previous
+      // kernel was still draining on other SMs.  The packed weights may come from the launch just before this one
+      // (blocks that pack per call), so they too are loaded only after the wait.
+      pdl_wait();
       ptx::mbar_arrive_expect_tx(w_bar, (uint32_t)(p.mt * 16384));
       for (int m = 0; m < p.mt; ++m) ptx::tma_load_3d(sW + m * 16384, &tm_w, w_bar, 0, m * 128, 0);
       int s = 0; uint32_t ph = 0;
@@ -223,6 +227,7 @@ constexpr int DWP_A_STAGES = 4;
 struct DwPlanarParams {
   int NC, C, H, W, ks, kmax, transform_on, f16, act;
   const float* filt;   // [C][ks * ks] active filters (fp32), derived once per launch by active_filter_kernel
+  int filt_from_kernel; // 1: `filt` is the output of the launch preceding this one (else the parameter itself)
   const float* gamma; const float* beta; const float* mean; const float* var; float eps;
   int tiles_x, tiles_y;
   int total_tiles;
@@ -283,6 +288,7 @@ dw_planar_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      pdl_wait();                                   // the planes are the previous kernel's output
       int s = 0; uint32_t ph = 0;
       for (int t = t_begin; t < t_end; ++t) {
         int pc, y0, x0;
@@ -384,6 +390,7 @@ dw_planar_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       dst_off[h] = dw_b_off(n, kh * 8);
     }
     __syncwarp();
+    if (p.filt_from_kernel) pdl_wait();             // transformed filters: written by the launch just before this one
     for (int t = t_begin; t < t_end; ++t) {
       int pc, y0, x0;
       dw_decode(p, t, pc, y0, x0);
@@ -535,6 +542,7 @@ project_planar_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
 
   if (warp == 0) {
     if (lane == 0) {
+      pdl_wait();                                   // the planes, the trunk and possibly the packed weights: earlier launches
       ptx::mbar_arrive_expect_tx(w_bar, (uint32_t)(p.kcs * 8192));
       for (int kc = 0; kc < p.kcs; ++kc) ptx::tma_load_3d(sW + kc * 8192, &tm_w, w_bar, kc * 64, 0, 0);
       int s = 0, rb = 0; uint32_t ph = 0, rph = 0;
@@ -730,7 +738,7 @@ int launch_expand_planar(const void* x, void* y, const void* wexp_p, int N, int 
   do {                                                                                                            \
     OFA_CUDA(cudaFuncSetAttribute(expand_planar_kernel<F16_, R6_>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                   (int)smem));                                                                    \
-    expand_planar_kernel<F16_, R6_><<<grid, EX_THREADS, smem, st>>>(tx, tw, ty, p);                               \
+    launch_pdl(expand_planar_kernel<F16_, R6_>, dim3(grid), dim3(EX_THREADS), smem, st, tx, tw, ty, p);                               \
   } while (0)
   if (f16 && relu6) OFA_EX_LAUNCH(1, 1);
   else if (f16) OFA_EX_LAUNCH(1, 0);
@@ -751,6 +759,7 @@ int launch_dw_planar(const void* x, void* y, int N, int C, int H, int W, const f
   // ... unless the active kernel size IS the stored one: then the [C][ks * ks] active filter is the parameter itself
   // (the max sub-network of the headline frame: one 5 us launch per block less)
   float* filt = nullptr;
+  p.filt_from_kernel = ks == kmax ? 0 : 1;
   if (ks == kmax) {
     p.filt = w7;
   } else {
@@ -792,7 +801,7 @@ int launch_dw_planar(const void* x, void* y, int N, int C, int H, int W, const f
   do {                                                                                                           \
     OFA_CUDA(cudaFuncSetAttribute(dw_planar_kernel<KS_, F16_, R6_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                   (int)smem));                                                                   \
-    dw_planar_kernel<KS_, F16_, R6_><<<(unsigned)grid, DW_THREADS, smem, st>>>(tx, txs, ty, p);                      \
+    launch_pdl(dw_planar_kernel<KS_, F16_, R6_>, dim3((unsigned)grid), dim3(DW_THREADS), smem, st, tx, txs, ty, p);                      \
   } while (0)
 #define OFA_DW_LAUNCH_KS(KS_)                                           \
   do {                                                                  \
@@ -848,7 +857,7 @@ int launch_project_planar(const void* x, const void* res, void* y, const void* w
   int grid = sm_count();
   const int tiles = N * p.tiles_per_img;
   if (grid > tiles) grid = tiles;
-  project_planar_kernel<<<grid, PJ_THREADS, smem, st>>>(ta, tw, tr, ty, p);
+  launch_pdl(project_planar_kernel, dim3(grid), dim3(PJ_THREADS), smem, st, ta, tw, tr, ty, p);
   return check_launch("project_planar_kernel");
 }
 
