@@ -8,7 +8,8 @@ All activation math runs in libofa_sr_b200.so (include/ofa_sr_b200.h); there is 
 """
 from . import backend, functional  # noqa: F401
 from .functional import (set_compute_dtype, get_compute_dtype, set_impl, set_train_dtype, get_train_dtype,  # noqa: F401
-                         set_mid_dtype, check_finite, set_overflow_policy, invalidate_packed_weights)
+                         set_mid_dtype, check_finite, set_overflow_policy, invalidate_packed_weights,
+                         set_block_train, set_train_side_stream)
 
 from .graphs import GraphedModule  # noqa: F401,E402
 
