@@ -6,12 +6,16 @@
 //   backward:  dy -> (dx, dW_exp, dW_dw [+ dM75, dM53], dW_proj, dgamma / dbeta of the three BatchNorms)
 //
 // The kernels are the ones the layer-by-layer autograd path launches (conv_tc / wgrad_tc on tcgen05, dw_fast,
-// dw_bwd_filter_rows, the vec8 BatchNorm kernels), in the same order with the same arguments -- results are bit-identical
-// to that path.  What changes is the HOST side: the eager training step was bounded by the Python launch loop (~10 ms of
-// interpreter time per step for ~7.5 ms of kernels, tools/hosttime_train.py); a block now costs one autograd node and one
-// ctypes call each way instead of three nodes and ~12 calls.  The five intermediates the backward needs live in one
-// caller-owned workspace; backward scratch is stream-ordered (cudaMallocAsync).  The residual's gradient is folded into the
-// epilogue of the expand data-gradient conv (dx = conv(dz1, W_exp^T) + dy) instead of a separate add.
+// dw_bwd_filter_rows, the vec8 BatchNorm kernels), in the same order with the same arguments: outputs, BatchNorm
+// gradients and buffers equal that path bit for bit, the atomically summed weight gradients to rounding
+// (test_block_training_call_is_bit_identical_to_layerwise_path).  What changes is the HOST side: the eager training
+// step was bounded by the Python launch loop (~10 ms of interpreter time per step for ~7.5 ms of kernels,
+// tools/hosttime_train.py); a block now costs one autograd node and one ctypes call each way instead of three nodes and
+// ~12 calls.  Device-side differences: the block's four weight copies are packed by ONE launch in the forward (the two
+// transposed ones are kept in the workspace for the backward); the identity branch's gradient is folded into the fp32
+// epilogue of the expand data-gradient conv (dx = conv(dz1, W_exp^T) + dy: one rounding instead of two); the three
+// weight-gradient computations can run on a side stream (ofa_train_side_mode).  The five intermediates the backward
+// needs live in one caller-owned workspace; backward scratch is stream-ordered (cudaMallocAsync).
 #include "ofa_common.cuh"
 #include "kernels.h"
 
