@@ -595,6 +595,47 @@ def test_block_training_call_is_bit_identical_to_layerwise_path(dev, ks, e, dtyp
         ofa_b200.set_train_dtype(torch.float32)
 
 
+def test_block_backward_side_stream_changes_nothing(dev):
+    """ofa_train_side_mode(1) only moves the three weight-gradient computations of a block onto a second stream (fork /
+    join inside the call): outputs, data gradients and BatchNorm gradients are bit-equal to mode 0, the atomically summed
+    weight gradients equal to rounding -- also when the next op on the main stream consumes them immediately."""
+    import ofa_b200
+    from ofa_b200 import functional as OF
+    from ofa_b200.layers import MobileInvertedResidualBlock, IdentityLayer
+    ofa_b200.set_train_dtype(torch.bfloat16)
+    try:
+        rs = np.random.RandomState(77)
+        x0 = torch.from_numpy(rs.randn(8, 64, 24, 24).astype(np.float32)).to(dev).to(torch.bfloat16) \
+            .contiguous(memory_format=torch.channels_last)
+        dy = torch.from_numpy(rs.randn(8, 64, 24, 24).astype(np.float32)).to(dev).to(torch.bfloat16) \
+            .contiguous(memory_format=torch.channels_last)
+        out = []
+        for side in (False, True):
+            ofa_b200.set_train_side_stream(side)
+            layer = _block_layer(dev).train()
+            layer.active_kernel_size, layer.active_expand_ratio = 5, 4
+            mod = MobileInvertedResidualBlock(layer, IdentityLayer(64, 64))
+            x = x0.clone().requires_grad_(True)
+            y = mod(x)
+            y.backward(dy)
+            # consumed on the main stream right away (no synchronisation in between)
+            gsum = sum(p.grad.double().sum() for p in layer.parameters() if p.grad is not None)
+            out.append((y.detach().clone(), x.grad.clone(), {n: p.grad.clone() for n, p in layer.named_parameters() if p.grad is not None},
+                        float(gsum)))
+        (ya, dxa, ga, sa), (yb, dxb, gb, sb) = out
+        assert torch.equal(ya, yb) and torch.equal(dxa, dxb)
+        assert set(ga) == set(gb)
+        for n in ga:
+            if 'bn.' in n:
+                assert torch.equal(ga[n], gb[n]), n
+            else:
+                assert relerr(ga[n], gb[n]) < 1e-5, n
+        assert abs(sa - sb) <= 1e-4 * max(1.0, abs(sa))
+    finally:
+        ofa_b200.set_train_side_stream(True)
+        ofa_b200.set_train_dtype(torch.float32)
+
+
 def test_block_training_call_in_network_step(dev):
     """The S4 training step (sampled sub-network, bf16, FusedAdam) with the block-level calls equals the layer-by-layer
     path: loss and every parameter after two steps."""
