@@ -226,11 +226,9 @@ def build_net(dev):
 
 
 def pin_rank_to_cores(local_rank, local_world):
-    """Several ranks share the box's host cores: give each rank its own slice so that eight Python launch loops (and the
-    NCCL proxy threads they spawn) do not migrate over each other.  The slice is taken from the cores NVML reports as
-    local to the rank's GPU (same NUMA node: the pinned frame buffers are first-touched there, and the device -> host
-    copies do not cross the socket link), shared evenly by the ranks whose GPUs report the same set.  No-op when it
-    cannot be done."""
+    """Several ranks share the box's host cores: keep each rank on the cores NVML reports as local to its GPU (same NUMA
+    node: the pinned frame buffers are first-touched there, and the device -> host copies do not cross the socket
+    link).  No-op when it cannot be done."""
     try:
         allowed = sorted(os.sched_getaffinity(0))
         groups = None
@@ -251,11 +249,15 @@ def pin_rank_to_cores(local_rank, local_world):
         if groups is None:
             groups = [tuple(allowed)] * local_world
         mine = groups[local_rank]
-        peers = [r for r in range(local_world) if groups[r] == mine]
-        per = max(1, len(mine) // len(peers))
-        k = peers.index(local_rank)
-        sl = list(mine[k * per:(k + 1) * per]) or list(mine)
-        os.sched_setaffinity(0, sl)
+        # the whole NUMA-local set, NOT an exclusive slice of it: a rank runs its Python loop, autograd's device thread,
+        # the NCCL proxy and the driver's helper threads; 16 cores / 8 ranks = 2-core slices starved the launch-heavy C4
+        # step (54.7 ms at 4 ranks against 40.0 ms unpinned); the node's scheduler balances the bursty threads better
+        if os.environ.get('OFA_BENCH_PIN_SLICES', '0') == '1':
+            peers = [r for r in range(local_world) if groups[r] == mine]
+            per = max(1, len(mine) // len(peers))
+            k = peers.index(local_rank)
+            mine = tuple(mine[k * per:(k + 1) * per]) or mine
+        os.sched_setaffinity(0, list(mine))
     except Exception:
         pass
 
